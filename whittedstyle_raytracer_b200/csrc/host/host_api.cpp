@@ -1,0 +1,117 @@
+// host_api.cpp — C ABI over the host front-end (see include/wrt_host.h).
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "../../../include/wrt_host.h"
+#include "host_scene.hpp"
+
+struct WrtScene {
+    wrt::HostScene hs;
+    std::string out_name;
+};
+
+namespace {
+thread_local std::string g_err;
+
+int finish_load(std::unique_ptr<WrtScene>& s, const char* obj_path, int variant, WrtScene** out) {
+    if (obj_path && *obj_path)
+        s->hs.loadObjLikeMain(obj_path, wrt::main_cpp_material(variant == WRT_MATERIAL_GLASS));
+    s->hs.buildAndFlatten();
+    s->out_name = s->hs.outputName();
+    *out = s.release();
+    return 0;
+}
+} // namespace
+
+extern "C" {
+
+const char* wrt_host_last_error(void) { return g_err.c_str(); }
+
+int wrt_scene_load(const char* config_path, const char* obj_path, const char* asset_dir, int variant, WrtScene** out) {
+    try {
+        std::unique_ptr<WrtScene> s(new WrtScene());
+        if (asset_dir) s->hs.assetDir = asset_dir;
+        s->hs.parseConfigFile(config_path ? config_path : "");
+        return finish_load(s, obj_path, variant, out);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+int wrt_scene_load_text(const char* text, const char* obj_path, const char* asset_dir, int variant, WrtScene** out) {
+    try {
+        std::unique_ptr<WrtScene> s(new WrtScene());
+        if (asset_dir) s->hs.assetDir = asset_dir;
+        s->hs.inputName = "scene.txt";
+        s->hs.parseConfigText(text ? text : "");
+        return finish_load(s, obj_path, variant, out);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+void wrt_scene_free(WrtScene* s) { delete s; }
+
+const WrtSceneDesc* wrt_scene_desc(const WrtScene* s) { return &s->hs.desc; }
+const WrtCamera* wrt_scene_camera(const WrtScene* s) { return &s->hs.cam; }
+
+int wrt_scene_set_imsize(WrtScene* s, int width, int height) {
+    if (width < 0 || height < 0) { g_err = "imsize must be non-negative"; return 1; }
+    s->hs.width = width;
+    s->hs.height = height;
+    s->hs.cam = s->hs.camera();
+    return 0;
+}
+
+int wrt_scene_set_shadow_type(WrtScene* s, int soft) {
+    s->hs.shadowType = soft ? 1 : 0;
+    s->hs.desc.shadow_type = s->hs.shadowType;
+    return 0;
+}
+
+int wrt_scene_bvh_depth(const WrtScene* s) { return s->hs.bvh_depth; }
+
+int64_t wrt_scene_upload_bytes(const WrtScene* s) {
+    const wrt::HostScene& h = s->hs;
+    return (int64_t)(h.nodes.size() * sizeof(WrtNode) + h.prim_geom.size() * 4 + h.prim_normals.size() * 4 +
+                     h.prim_uv.size() * 4 + h.prim_flags.size() * 4 * 6 + h.materials.size() * sizeof(WrtMaterial) +
+                     h.lights.size() * sizeof(WrtLight) + h.texels.size() * 4);
+}
+
+const char* wrt_scene_output_name(const WrtScene* s) { return s->out_name.c_str(); }
+
+// PPMGenerator::writeHeader / writePixel (include/PPMGenerator.hpp:631-646):
+// "P3\nW\nH\n255\n" then "r g b\n" per pixel, row-major.
+int wrt_write_ppm_p3(const char* path, int width, int height, const uint8_t* rgb) {
+    FILE* f = fopen(path, "wb");
+    if (!f) { g_err = std::string("cannot open ") + path; return 1; }
+    static const char digits[] = "0123456789";
+    std::vector<char> buf;
+    buf.reserve((size_t)1 << 22);
+    char hdr[64];
+    int hl = snprintf(hdr, sizeof hdr, "P3\n%d\n%d\n255\n", width, height);
+    buf.insert(buf.end(), hdr, hdr + hl);
+    size_t n = (size_t)width * height;
+    for (size_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) {
+            unsigned v = rgb[i * 3 + k];
+            if (v >= 100) { buf.push_back(digits[v / 100]); v %= 100; buf.push_back(digits[v / 10]); buf.push_back(digits[v % 10]); }
+            else if (v >= 10) { buf.push_back(digits[v / 10]); buf.push_back(digits[v % 10]); }
+            else buf.push_back(digits[v]);
+            buf.push_back(k == 2 ? '\n' : ' ');
+        }
+        if (buf.size() > ((size_t)1 << 22) - 16) {
+            if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); g_err = "short write"; return 1; }
+            buf.clear();
+        }
+    }
+    bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { g_err = "short write"; return 1; }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,103 @@
+/* wrt_cuda.h — C ABI of the sm_100a render core (libwrt_cuda.so).
+ *
+ * Drop-in boundary for the reference's render hot path.  Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference):
+ *
+ *   wrt_trace_closest      <- IIntersectStrategy::UpdateInter         include/IIntersectStrategy.h:10-11
+ *                             (BVHStrategy::UpdateInter -> getIntersection, include/BVHStrategy.hpp:8-11, include/BVH.hpp:137-159)
+ *   wrt_shadow_hard        <- IIntersectStrategy::getShadowCoeffi     include/IIntersectStrategy.h:14
+ *                             (BVHStrategy::getShadowCoeffi/ShadowHelper, include/BVHStrategy.hpp:13-48)
+ *   wrt_shadow_soft        <- Renderer::getShadowCoeffi(Intersection&, Vector3f&) with EXPEDITE
+ *                             (include/Renderer.hpp:347-376 -> hasIntersection, include/BVH.hpp:162-186);
+ *                             this query bypasses the strategy interface in the reference
+ *   wrt_shadow_directional <- Renderer::getShadowCoeffi(Intersection&, Vector4f&)   include/Renderer.hpp:381-400
+ *   wrt_render*            <- Renderer::render()                      include/Renderer.hpp:57-137
+ *                             (traceRay :151-260, blinnPhongShader :265-341, getAreaLightShadowCoeffi :405-414,
+ *                              changeNormalDir :417-474), output = PPMGenerator::rgb as 8-bit
+ *   wrt_upload_scene       <- the Scene& / PPMGenerator* the Renderer reads (include/Renderer.hpp:38-49)
+ *   wrt_set_camera         <- camera locals of Renderer::render       include/Renderer.hpp:65-100
+ *
+ * Conventions: plain C, opaque handle, every call returns 0 on success and a
+ * non-zero code on failure with wrt_last_error() describing it.  Host buffers
+ * stay owned by the caller; the library copies during upload.  There is no CPU
+ * fallback: without a CUDA device wrt_create() fails.
+ * Not thread-safe per context; use one context per GPU / per host thread.
+ */
+#ifndef WRT_CUDA_H
+#define WRT_CUDA_H
+
+#include "wrt_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct WrtContext WrtContext;
+
+#define WRT_TRAVERSAL_EXHAUSTIVE 0  /* visit every node whose box is hit, like BVH.hpp:137-159 */
+#define WRT_TRAVERSAL_PRUNED     1  /* near-first order, skip boxes entered beyond the best hit (same result) */
+
+int  wrt_create(int device, WrtContext** out);
+void wrt_destroy(WrtContext* ctx);
+const char* wrt_last_error(void);
+
+int wrt_upload_scene(WrtContext* ctx, const WrtSceneDesc* scene);
+int wrt_set_camera(WrtContext* ctx, const WrtCamera* cam);
+
+/* Image sharding: the image is cut into tile_w x tile_h tiles (multiples of 8 x 4),
+ * tile t (row-major) belongs to rank t % world.  Default: 32 x 16, rank 0 of 1. */
+int wrt_set_tiles(WrtContext* ctx, int tile_w, int tile_h, int rank, int world);
+
+/* traversal: WRT_TRAVERSAL_*; seed: soft-shadow RNG seed (include/wrt_rng.h);
+ * queue_factor: capacity of each secondary-ray level as a multiple of the primary
+ * level (<= 0 keeps the default 2.0; overflow is detected and re-rendered in
+ * smaller batches, never dropped). */
+int wrt_set_options(WrtContext* ctx, int traversal, uint32_t seed, float queue_factor);
+
+/* Brackets every kernel launch of wrt_render* with CUDA events on the launching
+ * stream so that wrt_get_kernel_times() can report per-family device time. */
+int wrt_enable_kernel_timing(WrtContext* ctx, int on);
+
+/* ---- batch forms of the strategy queries (host pointers, synchronous) ---- */
+int wrt_trace_closest(WrtContext* ctx, const float* orig, const float* dir, int64_t n, WrtHit* hits);
+int wrt_shadow_hard(WrtContext* ctx, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff);
+int wrt_shadow_soft(WrtContext* ctx, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff);
+int wrt_shadow_directional(WrtContext* ctx, const float* pos, const int32_t* self_object, const float* lightdir4,
+                           int64_t n, float* coeff);
+
+/* ---- frame ---- */
+/* Renders this rank's tiles and copies the 8-bit image (width*height*3, row-major,
+ * pixels of other ranks' tiles left untouched) to host memory.  Synchronous. */
+int wrt_render(WrtContext* ctx, uint8_t* rgb_host, WrtStats* stats);
+
+/* Asynchronous form on caller-provided device memory and stream (cudaStream_t as void*,
+ * NULL = the context's own stream).  d_rgb_tiles receives this rank's pixels in tile
+ * order: wrt_tile_pixel_count(ctx, rank, world) * 3 bytes.  Call wrt_finish_device()
+ * before reading statistics. */
+int wrt_render_device(WrtContext* ctx, void* d_rgb_tiles, void* cuda_stream);
+int wrt_finish_device(WrtContext* ctx, WrtStats* stats);
+int wrt_get_stats(WrtContext* ctx, WrtStats* stats);
+
+/* Pixel slots (tile area, including clipped padding) rank `rank` of `world` owns. */
+int64_t wrt_tile_pixel_count(WrtContext* ctx, int rank, int world);
+
+/* Rank-0 side of the NCCL gather: d_gathered holds `world` buffers of `stride_bytes`
+ * each (rank r's tile-order pixels at r*stride_bytes); writes the row-major
+ * width*height*3 image to d_rgb_image. */
+int wrt_scatter_tiles(WrtContext* ctx, const void* d_gathered, int world, int64_t stride_bytes,
+                      void* d_rgb_image, void* cuda_stream);
+
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t wrt_kernel_launch_count(WrtContext* ctx);
+
+/* Per-kernel-family device milliseconds of the last wrt_render* call (CUDA events
+ * on the launching stream).  Order: raygen, trace_closest, surface, shadow_hard,
+ * shadow_soft, shadow_directional, shade, combine, resolve.  Returns the number
+ * of entries written. */
+#define WRT_KERNEL_FAMILIES 9
+int wrt_get_kernel_times(WrtContext* ctx, float* ms, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WRT_CUDA_H */

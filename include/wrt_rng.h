@@ -22,7 +22,9 @@
 #define WRT_HD static inline
 #endif
 
+#ifndef WRT_DEFAULT_SEED
 #define WRT_DEFAULT_SEED 0x5EEDu
+#endif
 
 typedef struct WrtRand4 { uint32_t x, y, z, w; } WrtRand4;
 

@@ -147,6 +147,9 @@ typedef struct WrtStats {
 
 #define WRT_MAX_DEPTH 9           /* Renderer.hpp:25 */
 #define WRT_SOFT_SAMPLES 50       /* Renderer.hpp:407 */
+#ifndef WRT_DEFAULT_SEED
+#define WRT_DEFAULT_SEED 0x5EEDu   /* soft-shadow RNG seed, see wrt_rng.h */
+#endif
 
 #ifdef __cplusplus
 }

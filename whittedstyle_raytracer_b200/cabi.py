@@ -85,7 +85,7 @@ HOST_SYMBOLS = [
 # Entry points include/wrt_cuda.h declares
 CUDA_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_upload_scene", "wrt_set_camera", "wrt_set_tiles",
-    "wrt_set_options", "wrt_trace_closest", "wrt_shadow_hard", "wrt_shadow_soft", "wrt_shadow_directional",
+    "wrt_set_options", "wrt_enable_kernel_timing", "wrt_trace_closest", "wrt_shadow_hard", "wrt_shadow_soft", "wrt_shadow_directional",
     "wrt_render", "wrt_render_device", "wrt_finish_device", "wrt_get_stats", "wrt_tile_pixel_count",
     "wrt_scatter_tiles", "wrt_kernel_launch_count", "wrt_get_kernel_times",
 ]
@@ -150,7 +150,8 @@ def load_cuda() -> C.CDLL:
         lib.wrt_get_stats.argtypes = [vp, C.POINTER(WrtStats)]
         lib.wrt_tile_pixel_count.argtypes = [vp, i32, i32]
         lib.wrt_tile_pixel_count.restype = i64
-        lib.wrt_scatter_tiles.argtypes = [vp, vp, i32, i32, vp, vp]
+        lib.wrt_scatter_tiles.argtypes = [vp, vp, i32, i64, vp, vp]
+        lib.wrt_enable_kernel_timing.argtypes = [vp, i32]
         lib.wrt_kernel_launch_count.argtypes = [vp]
         lib.wrt_kernel_launch_count.restype = i64
         lib.wrt_get_kernel_times.argtypes = [vp, vp, i32]

@@ -1,0 +1,500 @@
+// kernels.cuh — the wavefront kernels (sm_100a, SIMT FP32; tensor cores unused:
+// the path is divergent traversal, not a dense contraction).
+//
+// One frame = for each ray-tree level d = 0..8 (Renderer.hpp:25 MAX_DEPTH 9):
+//   k_trace_closest   rays[d]  -> hits              (persistent warps, smem stacks)
+//   k_surface_spawn   hits     -> surface records, shadow requests, child rays[d+1], node[d].{fr,kT,children}
+//   k_shadow_*        requests -> coeff[node, light]  (hard product / soft 50-sample count / directional)
+//   k_shade           surface + coeff -> node[d].local
+// then bottom-up k_combine(d = 8..0): colour = local + fr*R + (1-fr)(1-alpha)*T in the
+// reference's own association (Renderer.hpp:259), and k_resolve: int(255*min(c,1)) (Renderer.hpp:128-130).
+//
+// Every queue length lives in device memory (Counters); kernels read it there, so
+// the host enqueues the whole frame without synchronising.
+#pragma once
+#include "dev_shade.cuh"
+#include "../../../include/wrt_rng.h"
+
+namespace wrt {
+
+enum CounterSlot {
+    C_NRAYS = 0,                 // [WRT_MAX_DEPTH + 1] rays per level (level 9 is never traced)
+    C_NPREQ = 16,                // [9] point-light shadow requests per level
+    C_NDREQ = 32,                // [9] directional-light shadow requests per level
+    C_VALID0 = 48,               // valid (non-padding) primary rays
+    C_OVERFLOW = 49,             // set when a queue append was dropped
+    C_WORK = 64,                 // work-distribution counters, one per persistent launch
+    C_TOTAL = 192
+};
+
+struct TileMap {
+    int width, height;
+    int tile_w, tile_h, tiles_x, tiles_y;
+    int rank, world;
+    __host__ __device__ int tile_pixels() const { return tile_w * tile_h; }
+    // local slot -> pixel; false when the slot is padding outside the image
+    __host__ __device__ bool slot_to_pixel(long long slot, int rank_, int& px, int& py) const {
+        int tp = tile_w * tile_h;
+        long long tl = slot / tp;
+        int within = (int)(slot - tl * tp);
+        long long t = tl * world + rank_;
+        if (t >= (long long)tiles_x * tiles_y) return false;
+        int tx = (int)(t % tiles_x), ty = (int)(t / tiles_x);
+        int bw = tile_w / 8;
+        int b = within >> 5, lane = within & 31;
+        int bx = b % bw, by = b / bw;
+        px = tx * tile_w + bx * 8 + (lane & 7);
+        py = ty * tile_h + by * 4 + (lane >> 3);
+        return px < width && py < height;
+    }
+};
+
+struct FrameBuffers {
+    float4* ray_o[2];            // {o.xyz, pixel id}
+    float4* ray_d[2];            // {d.xyz, path id}
+    float4* hit;                 // {t, prim, b1, b2}
+    float4* surf;                // 3 per node: {pos, prim} {nDir, material} {Od, -}
+    float4* node_a[WRT_MAX_DEPTH];   // {local.rgb -> colour.rgb, fr}
+    float4* node_b[WRT_MAX_DEPTH];   // {kT, childR, childT, composite flag}
+    float4* preq_o;              // point-light request: {shadow ray origin, node}
+    uint4*  preq_k;              //                      {light, pixel, path, -}
+    float4* dreq_o;              // directional request: {pos, node}
+    uint4*  dreq_k;              //                      {light, self prim, -, -}
+    float*  coeff;               // [node * n_lights + light]
+    unsigned* counters;
+    unsigned cap;                // capacity of every per-level array
+    unsigned preq_cap, dreq_cap;
+};
+
+// ---- warp-aggregated queue append: k in {0,1,2} slots per lane, one atomic per warp ----
+__device__ __forceinline__ unsigned warp_alloc(unsigned* counter, int k, unsigned cap, unsigned* overflow) {
+    unsigned lane = threadIdx.x & 31;
+    int incl = k;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (unsigned)off) incl += n;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(counter, (unsigned)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned mine = base + (unsigned)(incl - k);
+    if (k > 0 && mine + (unsigned)k > cap) { *overflow = 1u; return 0xffffffffu; }
+    return mine;
+}
+
+__device__ __forceinline__ unsigned queue_len(const unsigned* counters, int slot, unsigned cap) {
+    unsigned n = counters[slot];
+    return n < cap ? n : cap;
+}
+
+// ---- K1: primary rays, Renderer.hpp:104-125 ----
+__global__ void k_raygen(WrtCamera cam, TileMap tm, long long slot0, unsigned n, FrameBuffers fb) {
+    unsigned valid = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int x, y;
+        float4 ro, rd;
+        if (tm.slot_to_pixel(slot0 + i, tm.rank, x, y)) {
+            f3 ul = mk3(cam.ul[0], cam.ul[1], cam.ul[2]);
+            f3 v_off = (float)y * mk3(cam.delta_v[0], cam.delta_v[1], cam.delta_v[2]);
+            f3 h_off = (float)x * mk3(cam.delta_h[0], cam.delta_h[1], cam.delta_h[2]);
+            f3 pixelPos = ul + h_off + v_off + mk3(cam.c_off_h[0], cam.c_off_h[1], cam.c_off_h[2]) +
+                          mk3(cam.c_off_v[0], cam.c_off_v[1], cam.c_off_v[2]);
+            f3 eye = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
+            f3 nrm = mk3(cam.n[0], cam.n[1], cam.n[2]);
+            f3 dir, org;
+            if (!cam.parallel) { dir = normalized(pixelPos - eye); org = eye; }
+            else { dir = nrm; org = pixelPos - cam.d * nrm; }
+            ro = make_float4(org.x, org.y, org.z, __uint_as_float((unsigned)(y * cam.width + x)));
+            rd = make_float4(dir.x, dir.y, dir.z, __uint_as_float(1u));
+            ++valid;
+        } else {
+            ro = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));   // dead slot
+            rd = make_float4(0.f, 0.f, 1.f, __uint_as_float(0u));
+        }
+        fb.ray_o[0][i] = ro;
+        fb.ray_d[0][i] = rd;
+    }
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(fb.counters + C_VALID0, valid);
+    if (blockIdx.x == 0 && threadIdx.x == 0) fb.counters[C_NRAYS + 0] = n;
+}
+
+// ---- K2: closest hit, persistent warps pulling 32 rays at a time ----
+__global__ void __launch_bounds__(128) k_trace_closest(DevScene s, FrameBuffers fb, int level, int work_slot,
+                                                       float prune_rel) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
+    const float4* ray_o = fb.ray_o[level & 1];
+    const float4* ray_d = fb.ray_d[level & 1];
+    unsigned lane = threadIdx.x & 31;
+    while (true) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(fb.counters + work_slot, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned i = base + lane;
+        if (i < n) {
+            float4 o = ray_o[i], d = ray_d[i];
+            float4 out = make_float4(FLT_MAX, __int_as_float(-1), 0.f, 0.f);
+            if (__float_as_uint(o.w) == 0xffffffffu) out.y = __int_as_float(-2);       // dead slot
+            else if (s.n_nodes > 0) {
+                Ray r = make_ray(mk3(o), mk3(d));
+                Closest c = closest_hit(s, 0, r, st, prune_rel);
+                out = make_float4(c.t, __int_as_float(c.prim), c.u, c.v);
+            }
+            fb.hit[i] = out;
+        }
+    }
+}
+
+// ---- K3: hit -> surface, shadow requests, child rays (Renderer.hpp:170-257) ----
+__global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers fb, int level) {
+    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
+    const float4* ray_o = fb.ray_o[level & 1];
+    const float4* ray_d = fb.ray_d[level & 1];
+    float4* nray_o = fb.ray_o[(level + 1) & 1];
+    float4* nray_d = fb.ray_d[(level + 1) & 1];
+    unsigned* overflow = fb.counters + C_OVERFLOW;
+    const unsigned n_round = (n + 31u) & ~31u;         // whole warps stay converged for the aggregated appends
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool shade = false;
+        int n_children = 0;
+        bool spawnT = false, spawnR = false;
+        float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 nb = make_float4(0.f, __int_as_float(-1), __int_as_float(-1), 0.f);
+        f3 org = mk3(0.f, 0.f, 0.f), dir = org, pos = org, nDir = org, N = org;
+        f3 refractDir = org, reflectDir = org, refRayOrig = org, traRayOrig = org;
+        unsigned pixel = 0, path = 0;
+        int prim = -1;
+        if (i < n) {
+            float4 o4 = ray_o[i], d4 = ray_d[i], h = fb.hit[i];
+            org = mk3(o4); dir = mk3(d4);
+            pixel = __float_as_uint(o4.w); path = __float_as_uint(d4.w);
+            prim = __float_as_int(h.y);
+            if (prim == -1) {
+                na = make_float4(s.bkg[0], s.bkg[1], s.bkg[2], 0.f);            // miss: bkgcolor, :170
+            } else if (prim >= 0) {
+                Surface sf = complete_hit(s, org, dir, h.x, prim, h.z, h.w);
+                Mtl m = load_material(s, sf.material);
+                if (sf.flags & WRT_PRIM_LIGHT) {
+                    na = make_float4(m.diffuse.x, m.diffuse.y, m.diffuse.z, 0.f); // light avatar, :172
+                } else {
+                    shade = true;
+                    f3 Od = m.diffuse;
+                    if (!float_equal(-1.f, (float)sf.textureIndex) && !float_equal(-1.f, sf.u) && !float_equal(-1.f, sf.v))
+                        Od = texture_at(s, s.textures + sf.textureIndex, sf.u, sf.v);      // :176-180
+                    if (sf.normalMapIndex != -1) sf.nDir = change_normal_dir(s, sf);        // :182-184
+                    pos = sf.pos; nDir = sf.nDir;
+                    float4* sv = fb.surf + 3 * (size_t)i;
+                    sv[0] = make_float4(pos.x, pos.y, pos.z, __int_as_float(prim));
+                    sv[1] = make_float4(nDir.x, nDir.y, nDir.z, __int_as_float(sf.material));
+                    sv[2] = make_float4(Od.x, Od.y, Od.z, 0.f);
+                    // ---- reflection / transmission, :194-257 ----
+                    refRayOrig = pos; traRayOrig = pos;
+                    N = normalized(nDir);
+                    float fr, eta_i, eta_t;
+                    float cosN_Dir = dot(N, -dir);
+                    if (cosN_Dir > 0) { eta_i = s.eta; eta_t = m.eta; }
+                    else { eta_i = m.eta; eta_t = s.eta; }
+                    fr = fresnel(dir, N, eta_i, eta_t);
+                    refractDir = normalized(refraction_dir(dir, N, eta_i, eta_t));
+                    reflectDir = normalized(reflection_dir(dir, nDir));
+                    float cos_refle_N = dot(reflectDir, N);
+                    float cos_refra_N = dot(refractDir, N);
+                    const float EPSILON = 0.00005f;
+                    if (cos_refle_N < 0) refRayOrig = refRayOrig - EPSILON * N;
+                    else refRayOrig = refRayOrig + EPSILON * N;
+                    if (cos_refra_N < 0) traRayOrig = traRayOrig - EPSILON * N;
+                    else traRayOrig = traRayOrig + EPSILON * N;
+                    if (float_equal(0.f, norm(refractDir))) fr = 1.f;
+                    spawnT = !float_equal(1.f, m.alpha) && !float_equal(fr, 1.f);
+                    spawnR = m.ks != 0;
+                    if (level + 1 >= WRT_MAX_DEPTH) { spawnT = false; spawnR = false; }    // traceRay depth cut, :152
+                    n_children = (spawnT ? 1 : 0) + (spawnR ? 1 : 0);
+                    na.w = fr;
+                    nb.x = (1 - fr) * (1 - m.alpha);
+                    nb.w = 1.f;                                                    // composite node
+                }
+            }
+        }
+        if (i < n && !shade) fb.surf[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        // child rays
+        unsigned cslot = warp_alloc(fb.counters + C_NRAYS + level + 1, n_children, fb.cap, overflow);
+        if (n_children > 0 && cslot != 0xffffffffu) {
+            unsigned c = cslot;
+            if (spawnR) {
+                nray_o[c] = make_float4(refRayOrig.x, refRayOrig.y, refRayOrig.z, __uint_as_float(pixel));
+                nray_d[c] = make_float4(reflectDir.x, reflectDir.y, reflectDir.z, __uint_as_float(path * 2u));
+                nb.y = __int_as_float((int)c);
+                ++c;
+            }
+            if (spawnT) {
+                nray_o[c] = make_float4(traRayOrig.x, traRayOrig.y, traRayOrig.z, __uint_as_float(pixel));
+                nray_d[c] = make_float4(refractDir.x, refractDir.y, refractDir.z, __uint_as_float(path * 2u + 1u));
+                nb.z = __int_as_float((int)c);
+            }
+        }
+        // shadow requests: one per (shaded hit, light)
+        unsigned pslot = warp_alloc(fb.counters + C_NPREQ + level, shade ? s.n_point_lights : 0, fb.preq_cap, overflow);
+        unsigned dslot = 0xffffffffu;
+        if (s.n_dir_lights > 0)
+            dslot = warp_alloc(fb.counters + C_NDREQ + level, shade ? s.n_dir_lights : 0, fb.dreq_cap, overflow);
+        if (shade) {
+            f3 sorig = pos + 0.0005f * nDir;                               // BVHStrategy.hpp:15, Renderer.hpp:349
+            for (int li = 0; li < s.n_lights; li++) {
+                fb.coeff[(size_t)i * s.n_lights + li] = 0.f;
+                bool point = float_equal(s.lights[li].pos[3], 1.f);
+                if (point && pslot != 0xffffffffu) {
+                    fb.preq_o[pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(i));
+                    fb.preq_k[pslot] = make_uint4((unsigned)li, pixel, path, 0u);
+                    ++pslot;
+                } else if (!point && dslot != 0xffffffffu) {
+                    fb.dreq_o[dslot] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(i));
+                    fb.dreq_k[dslot] = make_uint4((unsigned)li, (unsigned)prim, 0u, 0u);
+                    ++dslot;
+                }
+            }
+        }
+        if (i < n) {
+            fb.node_a[level][i] = na;
+            fb.node_b[level][i] = nb;
+        }
+    }
+}
+
+// ---- K4a: hard shadows, BVHStrategy::getShadowCoeffi ----
+__global__ void __launch_bounds__(128) k_shadow_hard(DevScene s, FrameBuffers fb, int level, int work_slot) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    const unsigned n = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
+    unsigned lane = threadIdx.x & 31;
+    while (true) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(fb.counters + work_slot, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned i = base + lane;
+        if (i < n) {
+            float4 o4 = fb.preq_o[i];
+            uint4 k = fb.preq_k[i];
+            const WrtLight* L = s.lights + k.x;
+            f3 orig = mk3(o4);
+            f3 lightPos = mk3(L->pos[0], L->pos[1], L->pos[2]);
+            f3 raydir = normalized(lightPos - orig);
+            float distance = norm(lightPos - orig);
+            Ray r = make_ray(orig, raydir);
+            float c = shadow_product(s, r, distance, st);
+            fb.coeff[(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = c;
+        }
+    }
+}
+
+// ---- K4b: soft shadows: 50 area-light samples per request (Renderer.hpp:405-414) ----
+// Work item = (request, sample); a warp's 32 consecutive items share one or two
+// shading points, so its rays start at the same origin and stay coherent.
+__global__ void __launch_bounds__(128) k_shadow_soft(DevScene s, FrameBuffers fb, int level, int work_slot,
+                                                     unsigned seed, float prune_rel) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
+    const unsigned long long n = (unsigned long long)nreq * WRT_SOFT_SAMPLES;
+    unsigned lane = threadIdx.x & 31;
+    unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
+    while (true) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned long long item = base + lane;
+        unsigned req = 0xffffffffu;
+        bool lit = false;
+        if (item < n) {
+            req = (unsigned)(item / WRT_SOFT_SAMPLES);
+            unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
+            float4 o4 = fb.preq_o[req];
+            uint4 k = fb.preq_k[req];
+            const WrtLight* L = s.lights + k.x;
+            float u, v;
+            wrt_light_sample_uv(seed, k.y, k.z, k.x, sample, &u, &v);
+            // randomSampleTriangle, Triangle.hpp:139-145: (1-u-v)*v0 + u*v1 + v*v2
+            f3 v0 = mk3(L->tri[0], L->tri[1], L->tri[2]), v1 = mk3(L->tri[3], L->tri[4], L->tri[5]),
+               v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
+            f3 lightPos = (1 - u - v) * v0 + u * v1 + v * v2;
+            f3 orig = mk3(o4);
+            f3 raydir = normalized(lightPos - orig);
+            float distance = norm(lightPos - orig);
+            Ray r = make_ray(orig, raydir);
+            lit = !occluded(s, r, distance, st, prune_rel);
+        }
+        // a warp spans at most two requests (50 > 32): count the lit samples of each
+        unsigned req0 = __shfl_sync(0xffffffffu, req, 0);
+        unsigned m0 = __ballot_sync(0xffffffffu, lit && req == req0);
+        unsigned m1 = __ballot_sync(0xffffffffu, lit && req != req0 && req != 0xffffffffu);
+        unsigned req1 = __shfl_sync(0xffffffffu, req, 31);
+        if (lane == 0 && m0) {
+            float4 o4 = fb.preq_o[req0];
+            atomicAdd(fb.coeff + (size_t)__float_as_uint(o4.w) * s.n_lights + fb.preq_k[req0].x, (float)__popc(m0));
+        }
+        if (lane == 31 && m1) {
+            float4 o4 = fb.preq_o[req1];
+            atomicAdd(fb.coeff + (size_t)__float_as_uint(o4.w) * s.n_lights + fb.preq_k[req1].x, (float)__popc(m1));
+        }
+    }
+}
+
+// ---- K4c: directional-light shadows, Renderer.hpp:381-400 ----
+__global__ void __launch_bounds__(128) k_shadow_directional(DevScene s, FrameBuffers fb, int level) {
+    const unsigned n = queue_len(fb.counters, C_NDREQ + level, fb.dreq_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 o4 = fb.dreq_o[i];
+        uint4 k = fb.dreq_k[i];
+        const WrtLight* L = s.lights + k.x;
+        f3 negDir = mk3(-L->pos[0], -L->pos[1], -L->pos[2]);
+        Ray r = make_ray(mk3(o4), normalized(negDir));
+        fb.coeff[(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product(s, r, (int)k.y);
+    }
+}
+
+// ---- K5: local shading, Renderer::blinnPhongShader ----
+#define WRT_MAX_LIGHTS_FAST 8
+__global__ void __launch_bounds__(256) k_shade(DevScene s, FrameBuffers fb, int level) {
+    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
+    const float4* ray_o = fb.ray_o[level & 1];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4* sv = fb.surf + 3 * (size_t)i;
+        float4 s0 = sv[0];
+        if (__float_as_int(s0.w) < 0) continue;
+        float4 s1 = sv[1], s2 = sv[2];
+        Mtl m = load_material(s, __float_as_int(s1.w));
+        m.diffuse = mk3(s2);
+        f3 local = blinn_phong(s, mk3(ray_o[i]), mk3(s0), mk3(s1), m, fb.coeff + (size_t)i * s.n_lights);
+        float4 na = fb.node_a[level][i];
+        na.x = local.x; na.y = local.y; na.z = local.z;
+        fb.node_a[level][i] = na;
+    }
+}
+
+// ---- K6: bottom-up combine, Renderer.hpp:259 ----
+__global__ void __launch_bounds__(256) k_combine(FrameBuffers fb, int level) {
+    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 nb = fb.node_b[level][i];
+        if (nb.w == 0.f) continue;                       // miss / light avatar: returned as is
+        float4 na = fb.node_a[level][i];
+        int cR = __float_as_int(nb.y), cT = __float_as_int(nb.z);
+        f3 R = mk3(0.f, 0.f, 0.f), T = R;
+        if (cR >= 0) R = mk3(fb.node_a[level + 1][cR]);
+        if (cT >= 0) T = mk3(fb.node_a[level + 1][cT]);
+        f3 c = mk3(na) + na.w * R + nb.x * T;
+        fb.node_a[level][i] = make_float4(c.x, c.y, c.z, na.w);
+    }
+}
+
+__device__ __forceinline__ unsigned char quantize(float c) {   // int(255 * std::min(c, 1.f)), truncating
+    float m = (1.f < c) ? 1.f : c;
+    int q = (int)(255 * m);
+    return (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
+}
+
+// ---- K7: 8-bit resolve.  image != nullptr: row-major image; else tile-order pack ----
+__global__ void __launch_bounds__(256) k_resolve(FrameBuffers fb, TileMap tm, long long slot0, unsigned n,
+                                                 unsigned char* image, unsigned char* packed) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 c = fb.node_a[0][i];
+        unsigned char r = quantize(c.x), g = quantize(c.y), b = quantize(c.z);
+        if (packed) {
+            unsigned char* p = packed + 3 * (size_t)(slot0 + i);
+            p[0] = r; p[1] = g; p[2] = b;
+        }
+        int x, y;
+        if (image && tm.slot_to_pixel(slot0 + i, tm.rank, x, y)) {
+            unsigned char* p = image + 3 * ((size_t)y * tm.width + x);
+            p[0] = r; p[1] = g; p[2] = b;
+        }
+    }
+}
+
+// ---- rank-0 de-interleave after the NCCL gather ----
+__global__ void __launch_bounds__(256) k_scatter_tiles(const unsigned char* gathered, long long stride_bytes, TileMap tm,
+                                                       int world, long long slots_per_rank, unsigned char* image) {
+    long long total = slots_per_rank * world;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(g / slots_per_rank);
+        long long slot = g - (long long)r * slots_per_rank;
+        int x, y;
+        if (tm.slot_to_pixel(slot, r, x, y)) {
+            const unsigned char* p = gathered + (size_t)r * stride_bytes + 3 * (size_t)slot;
+            unsigned char* q = image + 3 * ((size_t)y * tm.width + x);
+            q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+        }
+    }
+}
+
+// ======================= batch forms of the strategy queries =======================
+
+__global__ void __launch_bounds__(128) k_batch_closest(DevScene s, const float* orig, const float* dir, long long n,
+                                                       WrtHit* out, float prune_rel) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        f3 o = mk3(orig[3 * i], orig[3 * i + 1], orig[3 * i + 2]);
+        f3 d = mk3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        WrtHit h;
+        h.hit = 0; h.object = -1; h.t = FLT_MAX; h.pos[0] = h.pos[1] = h.pos[2] = 0.f;
+        h.ndir[0] = h.ndir[1] = h.ndir[2] = 0.f; h.uv[0] = h.uv[1] = -1.f;
+        h.texture = -1; h.normalmap = -1; h.material = -1; h.prim = -1;
+        if (s.n_nodes > 0) {
+            Ray r = make_ray(o, d);
+            Closest c = closest_hit(s, 0, r, st, prune_rel);
+            if (c.prim >= 0) {
+                Surface sf = complete_hit(s, o, d, c.t, c.prim, c.u, c.v);
+                h.hit = 1; h.prim = c.prim; h.object = __ldg(s.ids + c.prim).w; h.t = c.t;
+                h.pos[0] = sf.pos.x; h.pos[1] = sf.pos.y; h.pos[2] = sf.pos.z;
+                h.ndir[0] = sf.nDir.x; h.ndir[1] = sf.nDir.y; h.ndir[2] = sf.nDir.z;
+                h.uv[0] = sf.u; h.uv[1] = sf.v; h.texture = sf.textureIndex; h.normalmap = sf.normalMapIndex;
+                h.material = sf.material;
+            }
+        }
+        out[i] = h;
+    }
+}
+
+// mode 0: BVHStrategy::getShadowCoeffi (hard); mode 1: Renderer::getShadowCoeffi(Vector3f&) (soft sample)
+__global__ void __launch_bounds__(128) k_batch_shadow(DevScene s, const float* pos, const float* ndir, const float* lightpos,
+                                                      long long n, float* out, int mode, float prune_rel) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        f3 p = mk3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        f3 nd = mk3(ndir[3 * i], ndir[3 * i + 1], ndir[3 * i + 2]);
+        f3 lightPos = mk3(lightpos[3 * i], lightpos[3 * i + 1], lightpos[3 * i + 2]);
+        f3 orig = p + 0.0005f * nd;
+        f3 raydir = normalized(lightPos - orig);
+        float distance = norm(lightPos - orig);
+        Ray r = make_ray(orig, raydir);
+        if (mode == 0) out[i] = shadow_product(s, r, distance, st);
+        else out[i] = occluded(s, r, distance, st, prune_rel) ? 0.f : 1.f;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_batch_shadow_directional(DevScene s, const float* pos, const int* self_object,
+                                                                  const float* lightdir4, long long n, float* out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        f3 p = mk3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        f3 negDir = mk3(-lightdir4[4 * i], -lightdir4[4 * i + 1], -lightdir4[4 * i + 2]);
+        int so = self_object[i];
+        int self_prim = (so >= 0 && so < s.n_prims) ? __ldg(s.object_prim + so) : -1;
+        Ray r = make_ray(p, normalized(negDir));
+        out[i] = directional_product(s, r, self_prim);
+    }
+}
+
+} // namespace wrt

@@ -1,0 +1,752 @@
+// wrt_cuda.cu — host side of libwrt_cuda.so: context, scene upload, frame
+// scheduling and the C ABI of include/wrt_cuda.h.  Compiled for sm_100a only,
+// with -fmad=false (see dev_math.cuh).  No CPU fallback exists in this library.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../../include/wrt_cuda.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + ")");                                              \
+        }                                                                                             \
+    } while (0)
+
+enum Family { F_RAYGEN, F_TRACE, F_SURFACE, F_SHADOW_HARD, F_SHADOW_SOFT, F_SHADOW_DIR, F_SHADE, F_COMBINE, F_RESOLVE };
+
+struct TimedLaunch {
+    int family;
+    cudaEvent_t e0, e1;
+};
+
+} // namespace
+
+struct WrtContext {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+
+    // scene
+    wrt::DevScene ds{};
+    std::vector<void*> scene_allocs;
+    bool has_scene = false;
+    int bvh_depth = 0;
+    int stack_rows = 2;
+
+    // camera / tiling / options
+    WrtCamera cam{};
+    bool has_cam = false;
+    int tile_w = 32, tile_h = 16, rank = 0, world = 1;
+    int traversal = WRT_TRAVERSAL_PRUNED;
+    uint32_t seed = WRT_DEFAULT_SEED;
+    float queue_factor = 2.0f;
+    float prune_rel = 1e-3f;
+    bool kernel_timing = false;
+
+    // frame buffers
+    wrt::FrameBuffers fb{};
+    std::vector<void*> frame_allocs;
+    unsigned batch_slots = 0;          // primary slots the buffers were sized for
+    int fb_lights = -1, fb_point = -1, fb_dir = -1;
+    unsigned* h_counters = nullptr;    // pinned
+    uint8_t* d_image = nullptr;        // full image, row-major (wrt_render)
+    size_t d_image_bytes = 0;
+    uint8_t* h_image = nullptr;        // pinned staging
+    size_t h_image_bytes = 0;
+
+    // batch-query scratch
+    void* d_scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
+
+    // bookkeeping
+    int64_t launches = 0;
+    int work_seq = 0;
+    WrtStats stats{};
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_next = 0;
+    float family_ms[WRT_KERNEL_FAMILIES] = {0};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool frame_pending = false;
+
+    wrt::TileMap tilemap() const {
+        wrt::TileMap tm;
+        tm.width = cam.width; tm.height = cam.height;
+        tm.tile_w = tile_w; tm.tile_h = tile_h;
+        tm.tiles_x = (cam.width + tile_w - 1) / tile_w;
+        tm.tiles_y = (cam.height + tile_h - 1) / tile_h;
+        tm.rank = rank; tm.world = world;
+        return tm;
+    }
+    long long local_slots(int r, int w) const {
+        wrt::TileMap tm = tilemap();
+        long long tiles = (long long)tm.tiles_x * tm.tiles_y;
+        long long mine = (tiles - r + w - 1) / w;
+        if (mine < 0) mine = 0;
+        return mine * tile_w * tile_h;
+    }
+};
+
+namespace {
+
+using wrt::FrameBuffers;
+
+template <class T>
+int dev_upload(WrtContext* c, const T* src, size_t count, const T** dst) {
+    *dst = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    c->scene_allocs.push_back(p);
+    if (count) CK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)p;
+    return 0;
+}
+
+void free_scene(WrtContext* c) {
+    for (void* p : c->scene_allocs) cudaFree(p);
+    c->scene_allocs.clear();
+    c->has_scene = false;
+}
+
+void free_frame(WrtContext* c) {
+    for (void* p : c->frame_allocs) cudaFree(p);
+    c->frame_allocs.clear();
+    c->batch_slots = 0;
+    memset(&c->fb, 0, sizeof c->fb);
+}
+
+int tree_depth(const WrtSceneDesc* s) {
+    if (s->n_nodes == 0) return 0;
+    int maxd = 0;
+    std::vector<std::pair<int, int>> st;
+    st.push_back({0, 0});
+    while (!st.empty()) {
+        auto [n, d] = st.back();
+        st.pop_back();
+        maxd = std::max(maxd, d);
+        int link = s->nodes[n].link;
+        if (link >= 0) { st.push_back({link, d + 1}); st.push_back({link + 1, d + 1}); }
+    }
+    return maxd;
+}
+
+template <class T>
+int frame_alloc(WrtContext* c, T** p, size_t count) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    c->frame_allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+int ensure_frame_buffers(WrtContext* c, unsigned slots) {
+    const wrt::DevScene& ds = c->ds;
+    if (c->batch_slots >= slots && c->fb_lights == ds.n_lights && c->fb_point == ds.n_point_lights &&
+        c->fb_dir == ds.n_dir_lights)
+        return 0;
+    free_frame(c);
+    FrameBuffers& fb = c->fb;
+    double f = c->queue_factor > 0 ? c->queue_factor : 2.0;
+    unsigned long long cap64 = (unsigned long long)((double)slots * std::max(1.0, f)) + 64;
+    if (cap64 > 0x7fffff00ull) return fail("frame batch too large for 32-bit queue indices");
+    unsigned cap = (unsigned)cap64;
+    fb.cap = cap;
+    fb.preq_cap = cap * (unsigned)std::max(1, ds.n_point_lights);
+    fb.dreq_cap = cap * (unsigned)std::max(1, ds.n_dir_lights);
+    if ((unsigned long long)cap * std::max(1, ds.n_lights) > 0xffffff00ull) return fail("too many (node, light) pairs");
+    for (int k = 0; k < 2; k++) {
+        if (frame_alloc(c, &fb.ray_o[k], cap)) return 1;
+        if (frame_alloc(c, &fb.ray_d[k], cap)) return 1;
+    }
+    if (frame_alloc(c, &fb.hit, cap)) return 1;
+    if (frame_alloc(c, &fb.surf, 3 * (size_t)cap)) return 1;
+    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
+        if (frame_alloc(c, &fb.node_a[d], cap)) return 1;
+        if (frame_alloc(c, &fb.node_b[d], cap)) return 1;
+    }
+    if (frame_alloc(c, &fb.preq_o, ds.n_point_lights ? fb.preq_cap : 1)) return 1;
+    if (frame_alloc(c, &fb.preq_k, ds.n_point_lights ? fb.preq_cap : 1)) return 1;
+    if (frame_alloc(c, &fb.dreq_o, ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
+    if (frame_alloc(c, &fb.dreq_k, ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
+    if (frame_alloc(c, &fb.coeff, (size_t)cap * std::max(1, ds.n_lights))) return 1;
+    if (frame_alloc(c, &fb.counters, wrt::C_TOTAL)) return 1;
+    c->batch_slots = slots;
+    c->fb_lights = ds.n_lights; c->fb_point = ds.n_point_lights; c->fb_dir = ds.n_dir_lights;
+    return 0;
+}
+
+int ensure_scratch(WrtContext* c, int k, size_t bytes) {
+    if (c->scratch_bytes[k] >= bytes) return 0;
+    if (c->d_scratch[k]) cudaFree(c->d_scratch[k]);
+    c->d_scratch[k] = nullptr;
+    c->scratch_bytes[k] = 0;
+    CK(cudaMalloc(&c->d_scratch[k], bytes));
+    c->scratch_bytes[k] = bytes;
+    return 0;
+}
+
+cudaEvent_t next_event(WrtContext* c) {
+    if (c->event_next == c->event_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->event_pool.push_back(e);
+    }
+    return c->event_pool[c->event_next++];
+}
+
+struct LaunchScope {                      // counts the launch; optionally brackets it with events
+    WrtContext* c;
+    cudaStream_t st;
+    TimedLaunch tl{};
+    bool timed;
+    LaunchScope(WrtContext* ctx, cudaStream_t s, int family) : c(ctx), st(s), timed(ctx->kernel_timing) {
+        ++c->launches;
+        if (timed) {
+            tl.family = family;
+            tl.e0 = next_event(c);
+            tl.e1 = next_event(c);
+            cudaEventRecord(tl.e0, st);
+        }
+    }
+    ~LaunchScope() {
+        if (timed) {
+            cudaEventRecord(tl.e1, st);
+            c->timed.push_back(tl);
+        }
+    }
+};
+
+int grid_for(WrtContext* c, int blocks_per_sm) { return c->num_sms * blocks_per_sm; }
+
+size_t stack_bytes(WrtContext* c, int threads) { return (size_t)c->stack_rows * threads * sizeof(int); }
+
+float prune_value(const WrtContext* c) { return c->traversal == WRT_TRAVERSAL_PRUNED ? c->prune_rel : -1.f; }
+
+// Enqueues one batch of primary slots [slot0, slot0+n) on `st`.
+int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, uint8_t* d_image, uint8_t* d_packed) {
+    using namespace wrt;
+    FrameBuffers& fb = c->fb;
+    const DevScene& ds = c->ds;
+    TileMap tm = c->tilemap();
+    CK(cudaMemsetAsync(fb.counters, 0, C_TOTAL * sizeof(unsigned), st));
+    c->work_seq = 0;
+    auto work_slot = [&]() { int s = C_WORK + 2 * c->work_seq; ++c->work_seq; return s; };
+    const int TB = 128;
+    const int trace_grid = grid_for(c, 8), wide_grid = grid_for(c, 8);
+    const size_t sb = stack_bytes(c, TB);
+    const float prune = prune_value(c);
+    {
+        LaunchScope ls(c, st, F_RAYGEN);
+        k_raygen<<<wide_grid, 256, 0, st>>>(c->cam, tm, slot0, n, fb);
+    }
+    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
+        {
+            LaunchScope ls(c, st, F_TRACE);
+            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune);
+        }
+        {
+            LaunchScope ls(c, st, F_SURFACE);
+            k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, d);
+        }
+        if (ds.n_point_lights > 0) {
+            if (ds.shadow_type == 0) {
+                LaunchScope ls(c, st, F_SHADOW_HARD);
+                k_shadow_hard<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot());
+            } else {
+                LaunchScope ls(c, st, F_SHADOW_SOFT);
+                k_shadow_soft<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), c->seed, prune);
+            }
+        }
+        if (ds.n_dir_lights > 0) {
+            LaunchScope ls(c, st, F_SHADOW_DIR);
+            k_shadow_directional<<<wide_grid, TB, 0, st>>>(ds, fb, d);
+        }
+        {
+            LaunchScope ls(c, st, F_SHADE);
+            k_shade<<<wide_grid, 256, 0, st>>>(ds, fb, d);
+        }
+    }
+    for (int d = WRT_MAX_DEPTH - 1; d >= 0; d--) {
+        LaunchScope ls(c, st, F_COMBINE);
+        k_combine<<<wide_grid, 256, 0, st>>>(fb, d);
+    }
+    {
+        LaunchScope ls(c, st, F_RESOLVE);
+        k_resolve<<<wide_grid, 256, 0, st>>>(fb, tm, slot0, n, d_image, d_packed);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+void add_batch_stats(WrtContext* c, const unsigned* cnt) {
+    WrtStats& s = c->stats;
+    const wrt::DevScene& ds = c->ds;
+    s.rays_per_depth[0] += cnt[wrt::C_VALID0];
+    s.closest_rays += cnt[wrt::C_VALID0];
+    for (int d = 1; d < WRT_MAX_DEPTH; d++) {
+        s.rays_per_depth[d] += cnt[wrt::C_NRAYS + d];
+        s.closest_rays += cnt[wrt::C_NRAYS + d];
+    }
+    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
+        int64_t p = cnt[wrt::C_NPREQ + d], q = cnt[wrt::C_NDREQ + d];
+        s.shadow_requests += p + q;
+        s.shadow_rays += p * (ds.shadow_type ? WRT_SOFT_SAMPLES : 1) + q;
+    }
+}
+
+// Renders all local slots.  Batches that overflow a queue are re-rendered in halves.
+int render_all(WrtContext* c, cudaStream_t st, uint8_t* d_image, uint8_t* d_packed) {
+    if (!c->has_scene) return fail("wrt_render: no scene uploaded");
+    if (!c->has_cam) return fail("wrt_render: no camera set");
+    if (c->cam.width <= 0 || c->cam.height <= 0) return fail("wrt_render: empty image");
+    const long long total = c->local_slots(c->rank, c->world);
+    const long long max_batch = 1ll << 24;
+    memset(&c->stats, 0, sizeof c->stats);
+    c->timed.clear();
+    c->event_next = 0;
+    c->last_stream = st;
+    CK(cudaEventRecord(c->ev_begin, st));
+    if (total > 0) {
+        unsigned want = (unsigned)std::min(total, max_batch);
+        if (ensure_frame_buffers(c, want)) return 1;
+    }
+    struct Span { long long s0; long long n; };
+    std::vector<Span> todo;
+    for (long long s0 = total; s0 > 0;) {              // push in reverse so spans pop in order
+        long long b = (s0 - 1) / max_batch * max_batch;
+        todo.push_back({b, s0 - b});
+        s0 = b;
+    }
+    const bool single = todo.size() <= 1;
+    while (!todo.empty()) {
+        Span sp = todo.back();
+        todo.pop_back();
+        if (enqueue_batch(c, st, sp.s0, (unsigned)sp.n, d_image, d_packed)) return 1;
+        CK(cudaMemcpyAsync(c->h_counters, c->fb.counters, wrt::C_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        if (single) {                                  // common case: stay asynchronous, check in finish
+            c->frame_pending = true;
+            CK(cudaEventRecord(c->ev_end, st));
+            return 0;
+        }
+        CK(cudaStreamSynchronize(st));
+        if (c->h_counters[wrt::C_OVERFLOW]) {
+            if (sp.n <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
+            long long half = ((sp.n / 2 + 31) / 32) * 32;
+            ++c->stats.overflow_retries;
+            todo.push_back({sp.s0 + half, sp.n - half});
+            todo.push_back({sp.s0, half});
+            continue;
+        }
+        add_batch_stats(c, c->h_counters);
+    }
+    CK(cudaEventRecord(c->ev_end, st));
+    return 0;
+}
+
+int finish_frame(WrtContext* c, uint8_t* d_image, uint8_t* d_packed) {
+    cudaStream_t st = c->last_stream;
+    CK(cudaStreamSynchronize(st));
+    if (c->frame_pending) {
+        c->frame_pending = false;
+        if (c->h_counters[wrt::C_OVERFLOW]) {
+            // single-batch frame overflowed: redo it synchronously in halves
+            const long long total = c->local_slots(c->rank, c->world);
+            int retries = 1;
+            std::vector<std::pair<long long, long long>> todo;
+            long long half = ((total / 2 + 31) / 32) * 32;
+            todo.push_back({half, total - half});
+            todo.push_back({0, half});
+            memset(&c->stats, 0, sizeof c->stats);
+            while (!todo.empty()) {
+                auto [s0, n] = todo.back();
+                todo.pop_back();
+                if (n <= 0) continue;
+                if (enqueue_batch(c, st, s0, (unsigned)n, d_image, d_packed)) return 1;
+                CK(cudaMemcpyAsync(c->h_counters, c->fb.counters, wrt::C_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (c->h_counters[wrt::C_OVERFLOW]) {
+                    if (n <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
+                    long long h2 = ((n / 2 + 31) / 32) * 32;
+                    ++retries;
+                    todo.push_back({s0 + h2, n - h2});
+                    todo.push_back({s0, h2});
+                    continue;
+                }
+                add_batch_stats(c, c->h_counters);
+            }
+            c->stats.overflow_retries = retries;
+            CK(cudaEventRecord(c->ev_end, st));
+            CK(cudaStreamSynchronize(st));
+        } else {
+            add_batch_stats(c, c->h_counters);
+        }
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) c->stats.gpu_ms = ms;
+    for (float& f : c->family_ms) f = 0.f;
+    for (const TimedLaunch& tl : c->timed) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, tl.e0, tl.e1) == cudaSuccess) c->family_ms[tl.family] += t;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* wrt_last_error(void) { return g_err.c_str(); }
+
+int wrt_create(int device, WrtContext** out) {
+    if (!out) return fail("wrt_create: null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(std::string("wrt_create: no CUDA device (") + cudaGetErrorString(e) +
+                    "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail("wrt_create: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(std::string("wrt_create: ") + prop.name + " is sm_" + std::to_string(prop.major) +
+                    std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    WrtContext* c = new WrtContext();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_counters, wrt::C_TOTAL * sizeof(unsigned)) != cudaSuccess) {
+        delete c;
+        return fail("wrt_create: stream/event/pinned allocation failed");
+    }
+    memset(c->h_counters, 0, wrt::C_TOTAL * sizeof(unsigned));
+    *out = c;
+    return 0;
+}
+
+void wrt_destroy(WrtContext* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_scene(c);
+    free_frame(c);
+    for (int k = 0; k < 5; k++) if (c->d_scratch[k]) cudaFree(c->d_scratch[k]);
+    if (c->d_image) cudaFree(c->d_image);
+    if (c->h_image) cudaFreeHost(c->h_image);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
+    if (!c || !s) return fail("wrt_upload_scene: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    free_scene(c);
+    wrt::DevScene& ds = c->ds;
+    memset(&ds, 0, sizeof ds);
+    const int np = s->n_prims;
+    // nodes: identical 32-byte records, viewed as float4 pairs on the device
+    static_assert(sizeof(WrtNode) == 32, "WrtNode must be 32 bytes");
+    if (dev_upload(c, (const float4*)s->nodes, 2 * (size_t)s->n_nodes, &ds.nodes)) return 1;
+    std::vector<float4> geom(3 * (size_t)np), attr(4 * (size_t)np);
+    std::vector<int4> ids(np);
+    int has_light = 0;
+    for (int p = 0; p < np; p++) {
+        const float* g = s->prim_geom + 12 * (size_t)p;
+        const WrtMaterial& m = s->materials[s->prim_material[p]];
+        unsigned flags = s->prim_flags[p];
+        if (flags & WRT_PRIM_LIGHT) has_light = 1;
+        float oma = 1 - m.alpha;                       // (1 - inter.mtlcolor.alpha), BVHStrategy.hpp:38
+        float fl;
+        memcpy(&fl, &flags, 4);
+        geom[3 * (size_t)p + 0] = make_float4(g[0], g[1], g[2], g[3]);
+        geom[3 * (size_t)p + 1] = make_float4(g[4], g[5], g[6], oma);
+        geom[3 * (size_t)p + 2] = make_float4(g[8], g[9], g[10], fl);
+        const float* nn = s->prim_normals + 9 * (size_t)p;
+        const float* uv = s->prim_uv + 6 * (size_t)p;
+        attr[4 * (size_t)p + 0] = make_float4(nn[0], nn[1], nn[2], uv[0]);
+        attr[4 * (size_t)p + 1] = make_float4(nn[3], nn[4], nn[5], uv[1]);
+        attr[4 * (size_t)p + 2] = make_float4(nn[6], nn[7], nn[8], uv[2]);
+        attr[4 * (size_t)p + 3] = make_float4(uv[3], uv[4], uv[5], 0.f);
+        ids[p] = make_int4(s->prim_material[p], s->prim_texture[p], s->prim_normalmap[p], s->prim_object[p]);
+        if (s->prim_texture[p] >= s->n_textures || s->prim_normalmap[p] >= s->n_normalmaps)
+            return fail("wrt_upload_scene: texture index out of range");
+    }
+    std::vector<float4> mats(3 * (size_t)s->n_materials);
+    for (int i = 0; i < s->n_materials; i++) {
+        const WrtMaterial& m = s->materials[i];
+        mats[3 * (size_t)i + 0] = make_float4(m.diffuse[0], m.diffuse[1], m.diffuse[2], m.ka);
+        mats[3 * (size_t)i + 1] = make_float4(m.specular[0], m.specular[1], m.specular[2], m.kd);
+        mats[3 * (size_t)i + 2] = make_float4(m.ks, m.n, m.alpha, m.eta);
+    }
+    if (dev_upload(c, geom.data(), geom.size(), &ds.geom)) return 1;
+    if (dev_upload(c, attr.data(), attr.size(), &ds.attr)) return 1;
+    if (dev_upload(c, ids.data(), ids.size(), &ds.ids)) return 1;
+    if (dev_upload(c, s->object_prim, (size_t)np, &ds.object_prim)) return 1;
+    if (dev_upload(c, mats.data(), mats.size(), &ds.materials)) return 1;
+    if (dev_upload(c, s->lights, (size_t)s->n_lights, &ds.lights)) return 1;
+    if (dev_upload(c, s->textures, (size_t)s->n_textures, &ds.textures)) return 1;
+    if (dev_upload(c, s->normalmaps, (size_t)s->n_normalmaps, &ds.normalmaps)) return 1;
+    if (dev_upload(c, s->texels, 3 * (size_t)s->n_texels, &ds.texels)) return 1;
+    ds.n_nodes = s->n_nodes; ds.n_prims = np; ds.n_lights = s->n_lights;
+    ds.n_point_lights = ds.n_dir_lights = 0;
+    for (int i = 0; i < s->n_lights; i++) {
+        if (fabsf(s->lights[i].pos[3] - 1.f) < 0.00001f) ++ds.n_point_lights;      // FLOAT_EQUAL(w, 1), Renderer.hpp:275
+        else ++ds.n_dir_lights;
+    }
+    ds.has_light_prims = has_light;
+    ds.shadow_type = s->shadow_type; ds.depth_cueing = s->depth_cueing;
+    for (int k = 0; k < 3; k++) { ds.bkg[k] = s->bkgcolor[k]; ds.dc[k] = s->dc[k]; ds.eye[k] = s->eye[k]; }
+    ds.eta = s->eta;
+    ds.amin = s->amin; ds.amax = s->amax; ds.distmin = s->distmin; ds.distmax = s->distmax;
+    c->bvh_depth = tree_depth(s);
+    c->stack_rows = c->bvh_depth + 2;
+    c->has_scene = true;
+    return 0;
+}
+
+int wrt_set_camera(WrtContext* c, const WrtCamera* cam) {
+    if (!c || !cam) return fail("wrt_set_camera: null argument");
+    if (cam->width < 0 || cam->height < 0) return fail("wrt_set_camera: negative image size");
+    c->cam = *cam;
+    c->has_cam = true;
+    return 0;
+}
+
+int wrt_set_tiles(WrtContext* c, int tile_w, int tile_h, int rank, int world) {
+    if (!c) return fail("wrt_set_tiles: null context");
+    if (tile_w <= 0 || tile_h <= 0 || tile_w % 8 || tile_h % 4) return fail("wrt_set_tiles: tile must be a multiple of 8 x 4");
+    if (world < 1 || rank < 0 || rank >= world) return fail("wrt_set_tiles: bad rank/world");
+    c->tile_w = tile_w; c->tile_h = tile_h; c->rank = rank; c->world = world;
+    return 0;
+}
+
+int wrt_set_options(WrtContext* c, int traversal, uint32_t seed, float queue_factor) {
+    if (!c) return fail("wrt_set_options: null context");
+    if (traversal != WRT_TRAVERSAL_EXHAUSTIVE && traversal != WRT_TRAVERSAL_PRUNED) return fail("wrt_set_options: bad traversal mode");
+    c->traversal = traversal;
+    c->seed = seed;
+    if (queue_factor > 0 && queue_factor != c->queue_factor) {
+        c->queue_factor = queue_factor;
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        free_frame(c);
+    }
+    return 0;
+}
+
+int wrt_enable_kernel_timing(WrtContext* c, int on) {
+    if (!c) return fail("wrt_enable_kernel_timing: null context");
+    c->kernel_timing = on != 0;
+    return 0;
+}
+
+// ---------------- batch queries ----------------
+
+static int batch_common(WrtContext* c, int64_t n) {
+    if (!c) return fail("null context");
+    if (!c->has_scene) return fail("no scene uploaded");
+    if (n < 0) return fail("negative count");
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+int wrt_trace_closest(WrtContext* c, const float* orig, const float* dir, int64_t n, WrtHit* hits) {
+    if (batch_common(c, n)) return 1;
+    if (n == 0) return 0;
+    cudaStream_t st = c->own_stream;
+    size_t vb = (size_t)n * 3 * sizeof(float);
+    if (ensure_scratch(c, 0, vb) || ensure_scratch(c, 1, vb) || ensure_scratch(c, 2, (size_t)n * sizeof(WrtHit))) return 1;
+    CK(cudaMemcpyAsync(c->d_scratch[0], orig, vb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_scratch[1], dir, vb, cudaMemcpyHostToDevice, st));
+    int grid = (int)std::min<int64_t>((n + 127) / 128, grid_for(c, 8));
+    ++c->launches;
+    wrt::k_batch_closest<<<grid, 128, stack_bytes(c, 128), st>>>(c->ds, (const float*)c->d_scratch[0],
+                                                                  (const float*)c->d_scratch[1], n,
+                                                                  (WrtHit*)c->d_scratch[2], prune_value(c));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hits, c->d_scratch[2], (size_t)n * sizeof(WrtHit), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int batch_shadow(WrtContext* c, const float* pos, const float* ndir, const float* lightpos, int64_t n,
+                        float* coeff, int mode) {
+    if (batch_common(c, n)) return 1;
+    if (n == 0) return 0;
+    cudaStream_t st = c->own_stream;
+    size_t vb = (size_t)n * 3 * sizeof(float);
+    for (int k = 0; k < 3; k++) if (ensure_scratch(c, k, std::max(vb, c->scratch_bytes[k]))) return 1;
+    if (ensure_scratch(c, 3, (size_t)n * sizeof(float))) return 1;
+    CK(cudaMemcpyAsync(c->d_scratch[0], pos, vb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_scratch[1], ndir, vb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_scratch[2], lightpos, vb, cudaMemcpyHostToDevice, st));
+    int grid = (int)std::min<int64_t>((n + 127) / 128, grid_for(c, 8));
+    ++c->launches;
+    wrt::k_batch_shadow<<<grid, 128, stack_bytes(c, 128), st>>>(c->ds, (const float*)c->d_scratch[0],
+                                                                 (const float*)c->d_scratch[1],
+                                                                 (const float*)c->d_scratch[2], n,
+                                                                 (float*)c->d_scratch[3], mode, prune_value(c));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(coeff, c->d_scratch[3], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int wrt_shadow_hard(WrtContext* c, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff) {
+    return batch_shadow(c, pos, ndir, lightpos, n, coeff, 0);
+}
+
+int wrt_shadow_soft(WrtContext* c, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff) {
+    return batch_shadow(c, pos, ndir, lightpos, n, coeff, 1);
+}
+
+int wrt_shadow_directional(WrtContext* c, const float* pos, const int32_t* self_object, const float* lightdir4,
+                           int64_t n, float* coeff) {
+    if (batch_common(c, n)) return 1;
+    if (n == 0) return 0;
+    cudaStream_t st = c->own_stream;
+    if (ensure_scratch(c, 0, (size_t)n * 12) || ensure_scratch(c, 1, (size_t)n * 4) ||
+        ensure_scratch(c, 2, (size_t)n * 16) || ensure_scratch(c, 3, (size_t)n * 4))
+        return 1;
+    CK(cudaMemcpyAsync(c->d_scratch[0], pos, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_scratch[1], self_object, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_scratch[2], lightdir4, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    int grid = (int)std::min<int64_t>((n + 127) / 128, grid_for(c, 8));
+    ++c->launches;
+    wrt::k_batch_shadow_directional<<<grid, 128, 0, st>>>(c->ds, (const float*)c->d_scratch[0], (const int*)c->d_scratch[1],
+                                                          (const float*)c->d_scratch[2], n, (float*)c->d_scratch[3]);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(coeff, c->d_scratch[3], (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---------------- frame ----------------
+
+int wrt_render(WrtContext* c, uint8_t* rgb_host, WrtStats* stats) {
+    if (!c || !rgb_host) return fail("wrt_render: null argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->has_cam) return fail("wrt_render: no camera set");
+    size_t bytes = (size_t)c->cam.width * c->cam.height * 3;
+    if (bytes == 0) return fail("wrt_render: empty image");
+    if (c->d_image_bytes < bytes) {
+        if (c->d_image) cudaFree(c->d_image);
+        c->d_image = nullptr; c->d_image_bytes = 0;
+        CK(cudaMalloc((void**)&c->d_image, bytes));
+        c->d_image_bytes = bytes;
+    }
+    if (c->h_image_bytes < bytes) {
+        if (c->h_image) cudaFreeHost(c->h_image);
+        c->h_image = nullptr; c->h_image_bytes = 0;
+        CK(cudaMallocHost((void**)&c->h_image, bytes));
+        c->h_image_bytes = bytes;
+    }
+    cudaStream_t st = c->own_stream;
+    if (c->world > 1) CK(cudaMemsetAsync(c->d_image, 0, bytes, st));
+    if (render_all(c, st, c->d_image, nullptr)) return 1;
+    if (finish_frame(c, c->d_image, nullptr)) return 1;
+    CK(cudaMemcpyAsync(c->h_image, c->d_image, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (c->world == 1) memcpy(rgb_host, c->h_image, bytes);
+    else {
+        // only this rank's pixels are defined; copy them, leave the rest of the caller's buffer alone
+        wrt::TileMap tm = c->tilemap();
+        long long slots = c->local_slots(c->rank, c->world);
+        for (long long s = 0; s < slots; s++) {
+            int x, y;
+            if (tm.slot_to_pixel(s, c->rank, x, y)) {
+                size_t o = 3 * ((size_t)y * tm.width + x);
+                rgb_host[o] = c->h_image[o]; rgb_host[o + 1] = c->h_image[o + 1]; rgb_host[o + 2] = c->h_image[o + 2];
+            }
+        }
+    }
+    if (stats) *stats = c->stats;
+    return 0;
+}
+
+int wrt_render_device(WrtContext* c, void* d_rgb_tiles, void* cuda_stream) {
+    if (!c || !d_rgb_tiles) return fail("wrt_render_device: null argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return render_all(c, st, nullptr, (uint8_t*)d_rgb_tiles);
+}
+
+int wrt_finish_device(WrtContext* c, WrtStats* stats) {
+    if (!c) return fail("wrt_finish_device: null context");
+    CK(cudaSetDevice(c->device));
+    if (!c->last_stream && !c->frame_pending) return fail("wrt_finish_device: no frame in flight");
+    // the packed pointer is only needed again if an overflowed frame must be re-rendered
+    if (c->frame_pending && c->h_counters) {
+        CK(cudaStreamSynchronize(c->last_stream));
+        if (c->h_counters[wrt::C_OVERFLOW]) return fail("ray queue overflow in wrt_render_device: raise queue_factor via wrt_set_options");
+    }
+    if (finish_frame(c, nullptr, nullptr)) return 1;
+    if (stats) *stats = c->stats;
+    return 0;
+}
+
+int wrt_get_stats(WrtContext* c, WrtStats* stats) {
+    if (!c || !stats) return fail("wrt_get_stats: null argument");
+    *stats = c->stats;
+    return 0;
+}
+
+int64_t wrt_tile_pixel_count(WrtContext* c, int rank, int world) {
+    if (!c || !c->has_cam || world < 1 || rank < 0 || rank >= world) return -1;
+    return c->local_slots(rank, world);
+}
+
+int wrt_scatter_tiles(WrtContext* c, const void* d_gathered, int world, int64_t stride_bytes, void* d_rgb_image,
+                      void* cuda_stream) {
+    if (!c || !d_gathered || !d_rgb_image) return fail("wrt_scatter_tiles: null argument");
+    if (!c->has_cam) return fail("wrt_scatter_tiles: no camera set");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    wrt::TileMap tm = c->tilemap();
+    tm.world = world;
+    long long slots_per_rank = c->local_slots(0, world);   // rank 0 owns the most tiles
+    if (stride_bytes < slots_per_rank * 3) return fail("wrt_scatter_tiles: stride smaller than rank 0's tile buffer");
+    ++c->launches;
+    wrt::k_scatter_tiles<<<grid_for(c, 8), 256, 0, st>>>((const unsigned char*)d_gathered, stride_bytes, tm, world,
+                                                         slots_per_rank, (unsigned char*)d_rgb_image);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int64_t wrt_kernel_launch_count(WrtContext* c) { return c ? c->launches : 0; }
+
+int wrt_get_kernel_times(WrtContext* c, float* ms, int capacity) {
+    if (!c || !ms) return 0;
+    int n = std::min(capacity, (int)WRT_KERNEL_FAMILIES);
+    for (int i = 0; i < n; i++) ms[i] = c->family_ms[i];
+    return n;
+}
+
+} // extern "C"

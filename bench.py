@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s (all ray types) and ms/frame of the Whitted hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A step = one frame of the workload (default: BASELINE.json configs[3], out/water_bunny_tex.txt
++ `shadow soft` at 3840x2160 — the configuration the north-star metric is quoted on).
+N > 1 (launched by torchrun, one rank per GPU): the same frame strong-scaled over interleaved
+tiles, gathered to rank 0 with one NCCL gather; time = max over ranks.
+Prints ONE JSON line (rank 0).  `value` = rays of the whole frame / device time with the scene
+resident in HBM; `e2e` = the same through the host-buffer C-ABI call (scene H2D upload +
+render + image D2H inside the timed region).  `--impl reference` times the UNMODIFIED
+reference (oracle/_ref, single-threaded by construction) on a bounded pixel sample of the
+same frame.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "Mrays/s (all ray types), out/water_bunny_tex.txt + shadow soft @ 3840x2160"
+UNIT = "Mrays/s"
+DEFAULT_WORKLOAD = "water_bunny_tex_soft_4k"
+WORKLOAD_DESC = {
+    "config": "config.txt (== bunny_shadow.txt) @ 800x600, hard shadows (BASELINE.json configs[0])",
+    "bunny_shadow_4k": "bunny_shadow.txt @ 3840x2160, hard shadows (BASELINE.json configs[1])",
+    "gla_bunny_tex_4k": "gla_bunny_tex.txt @ 3840x2160, hard shadows + Fresnel recursion (BASELINE.json configs[2])",
+    "water_bunny_tex_soft_4k": "out/water_bunny_tex.txt + shadow soft @ 3840x2160 (BASELINE.json configs[3])",
+    "glass_bunny_soft_8k": "glass-bunny + shadow soft @ 7680x4320 (BASELINE.json configs[4])",
+}
+# Reference traversal work per ray: box tests, triangle tests -> FLOPs at 21 / 61 per test
+ALGO_TESTS = {"config": (75.1, 4.11), "bunny_shadow_4k": (77.5, 4.28), "gla_bunny_tex_4k": (69.5, 4.30),
+              "water_bunny_tex_soft_4k": (48.6, 2.86), "glass_bunny_soft_8k": (48.6, 2.86)}
+ALGO_BYTES_PER_RAY = 112      # wavefront queue traffic (ray 40 B + hit 16 B) x (write + read)
+
+
+def flops_per_ray(workload):
+    b, t = ALGO_TESTS[workload]
+    return 21.0 * b + 61.0 * t
+
+
+def peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def prepare_scene(workload, workdir):
+    from whittedstyle_raytracer_b200 import Scene, fixtures
+    fixtures.ensure_assets(workdir)
+    fixtures.write_config(workdir, workload, fixtures.bench_config_text(workload))
+    glass = bool(fixtures.BENCH_CONFIGS[workload].get("glass"))
+    return Scene.from_workdir(workdir, workload, glass=glass), glass
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the unmodified reference on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_reference_sample(scene, workdir, workload, glass, target_seconds):
+    """Traces a strided pixel sample of the workload's frame with the reference's own traceRay
+    (oracle/_ref/libwhitted_ref.so, 1 thread — the reference has no threading), or with the
+    oracle port (all cores) when the reference library did not travel.  Returns a dict."""
+    sys.path.insert(0, str(REPO / "tests"))
+    import numpy as np
+    import oracle_bindings as ob
+    w, h = scene.width, scene.height
+    soft = scene.desc.shadow_type != 0
+    rays_per_px = 90.0 if soft else 4.0
+    ref_rate = 0.7e6 if soft else 0.33e6                     # BASELINE.md section 2, Mrays/s of the reference
+    if ob.have_reference():
+        want_px = max(256.0, target_seconds * ref_rate / rays_per_px)
+        stride = max(1, int(round((w * h / want_px) ** 0.5)))
+        ref = ob.ReferenceScene(workdir, workload, glass=glass)
+        o, d = ob.OracleScene(scene).primary_rays()
+        o = o.reshape(h, w, 3)[::stride, ::stride].reshape(-1, 3)
+        d = d.reshape(h, w, 3)[::stride, ::stride].reshape(-1, 3)
+        ref.counters(reset=True)
+        _, secs = ref.trace_pixels(o, d)
+        closest, shadow = ref.counters(reset=True)
+        rays = closest + shadow
+        return dict(value=rays / secs / 1e6, unit=UNIT, cores=1, kind="reference", seconds=secs, rays=rays,
+                    sample=f"every {stride}th pixel in x and y of the {w}x{h} frame ({len(o)} primary rays, {rays} rays) "
+                           f"through the unmodified reference's traceRay, 1 thread (the reference is single-threaded)")
+    cores = os.cpu_count() or 1
+    want_px = max(256.0, target_seconds * ref_rate * cores * 0.5 / rays_per_px)
+    stride = max(1, int(round((w * h / want_px) ** 0.5)))
+    t0 = time.time()
+    _, st = ob.OracleScene(scene).render(stride=(stride, stride))
+    secs = time.time() - t0
+    rays = st.closest_rays + st.shadow_rays
+    return dict(value=rays / secs / 1e6, unit=UNIT, cores=cores, kind="port", seconds=secs, rays=rays,
+                sample=f"every {stride}th pixel in x and y of the {w}x{h} frame ({rays} rays) through the oracle port "
+                       f"(oracle/whitted_oracle.c, OpenMP, {cores} threads); oracle/_ref was not available")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workdir = Path(tempfile.mkdtemp(prefix="wrt_bench_ref_"))
+    scene, glass = prepare_scene(args.workload, workdir)
+    total = args.steps + args.warmup
+    per_step = min(10.0, max(1.0, 150.0 / max(1, total)))
+    vals, last = [], None
+    for i in range(total):
+        last = cpu_reference_sample(scene, workdir, args.workload, glass, per_step)
+        if i >= args.warmup:
+            vals.append(last)
+    rays = sum(v["rays"] for v in vals)
+    secs = sum(v["seconds"] for v in vals)
+    value = rays / secs / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / max(1, len(vals)) * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[args.workload], "step": "bounded pixel sample of the frame: " + last["sample"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from whittedstyle_raytracer_b200 import cabi
+    from whittedstyle_raytracer_b200.parallel import DistributedRenderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus} (one rank per GPU)")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    workdir = Path(tempfile.mkdtemp(prefix=f"wrt_bench_{rank}_"))
+    scene, glass = prepare_scene(args.workload, workdir)
+    dr = DistributedRenderer(scene, rank, world, local)
+    ctx = dr.renderer.ctx
+    w, h = scene.width, scene.height
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+
+    def l2_flush():
+        flush.fill_(rank + 1)
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        dr.frame()
+        stats = dr.finish()
+    barrier()
+    rays_local = stats["rays"]
+    rays_t = torch.tensor([rays_local, stats["closest_rays"], stats["shadow_rays"]], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(rays_t)
+    rays_frame, closest_frame, shadow_frame = (int(x) for x in rays_t.tolist())
+
+    # ---- timed: device-resident scene, CUDA events on the launching (current) stream ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        l2_flush()
+        if world > 1:
+            dist.barrier()
+        ev[k][0].record()
+        dr.frame()
+        ev[k][1].record()
+        dr.finish()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launches - launches0
+    ms_local = sum(a.elapsed_time(b) for a, b in ev)
+    ms_t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_t.item())
+    ms_per_step = ms_total / args.steps
+    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---- per-kernel times of one frame (events around every launch; separate, untimed pass) ----
+    ctx.enable_kernel_timing(True)
+    fam_ms, fam_n = {}, 3
+    for _ in range(fam_n):
+        l2_flush()
+        dr.frame()
+        dr.finish()
+        for k2, v in ctx.kernel_times().items():
+            fam_ms[k2] = fam_ms.get(k2, 0.0) + v / fam_n
+    ctx.enable_kernel_timing(False)
+    barrier()
+
+    # ---- e2e: host buffers through the C ABI; scene H2D + render + image D2H every step ----
+    lib = cabi.load_cuda()
+    host_img = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
+    st = cabi.WrtStats()
+    import ctypes as C
+    d2h = 0
+
+    def e2e_step():
+        nonlocal d2h
+        ctx._check(lib.wrt_upload_scene(ctx.h, scene.desc_ptr))
+        ctx._check(lib.wrt_set_camera(ctx.h, scene.camera_ptr))
+        if world == 1:
+            ctx._check(lib.wrt_render(ctx.h, host_img.data_ptr(), C.byref(st)))
+            d2h = h * w * 3
+        else:
+            img = dr.frame()
+            dr.finish()
+            if rank == 0:
+                host_img.copy_(img, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                d2h = h * w * 3
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(e2e_t.item()) / args.steps * 1e3
+    e2e_value = rays_frame / (e2e_ms_per_step * 1e-3) / 1e6
+    launches += 0
+    checksum = int(host_img.numpy().astype(np.uint64).sum()) if rank == 0 else 0
+
+    # ---- roofline of the dominant kernel family ----
+    hbm_peak, peak_src = peaks()
+    dom = max(fam_ms, key=fam_ms.get)
+    dom_share = fam_ms[dom] / max(1e-9, sum(fam_ms.values()))
+    # units the dominant family processes in one frame on this rank
+    if dom.startswith("shadow"):
+        dom_units = stats["shadow_rays"]
+    elif dom == "trace_closest":
+        dom_units = stats["closest_rays"]
+    else:
+        dom_units = stats["rays"]
+    dom_launches = 9 if dom not in ("raygen", "resolve") else 1
+    dom_s = fam_ms[dom] * 1e-3
+    fma_tf, muladd_tf = ctx.measure_fp32_peak()
+    fpr = flops_per_ray(args.workload)
+    roofline = {
+        "kernel": f"k_{dom}", "share_of_step": dom_share, "launches_per_step": dom_launches,
+        "avg_launch_ms": fam_ms[dom] / dom_launches, "units_per_step": dom_units,
+        "bound": "hbm", "achieved": dom_units * ALGO_BYTES_PER_RAY / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": dom_units * ALGO_BYTES_PER_RAY / dom_s / 1e9 / hbm_peak, "peak_source": peak_src,
+        "algorithmic_bytes_per_ray": ALGO_BYTES_PER_RAY, "traffic": profile_traffic(dom),
+        "binding_bound": "fp32-issue/latency (divergent BVH traversal; working set L1/L2-resident) — neither HBM nor tensor",
+        "fp32": {"algorithmic_flops_per_ray": fpr, "achieved_tflops": dom_units * fpr / dom_s / 1e12,
+                 "peak_tflops_fma_measured": fma_tf, "peak_tflops_fmul_fadd_measured": muladd_tf,
+                 "frac_of_fma_peak": dom_units * fpr / dom_s / 1e12 / max(fma_tf, 1e-9),
+                 "frac_of_fmul_fadd_peak": dom_units * fpr / dom_s / 1e12 / max(muladd_tf, 1e-9)},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c = cpu_reference_sample(scene, workdir, args.workload, glass, args.cpu_seconds)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["seconds"] = c["seconds"]
+
+    if rank == 0:
+        line = {
+            "metric": METRIC if args.workload == DEFAULT_WORKLOAD else f"Mrays/s (all ray types), {WORKLOAD_DESC[args.workload]}",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "width": w, "height": h, "rays_per_frame": rays_frame,
+                       "closest_hit_rays": closest_frame, "shadow_rays": shadow_frame,
+                       "parallelism": f"tiles32x16-interleaved x{world}" + ("+nccl-gather" if world > 1 else ""),
+                       "traversal": "pruned", "l2": "flushed between timed steps (256 MiB write)",
+                       "scene_bytes": scene.upload_bytes, "image_checksum": checksum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
+                    "h2d_bytes_per_step": int(scene.upload_bytes), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": fam_ms,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    dr.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def profile_traffic(family):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/*.json written by tools/summarize_ncu.py), or None."""
+    p = REPO / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(f"k_{family}")
+        except (ValueError, OSError):
+            return None
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="size of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,6 +90,11 @@ int wrt_scatter_tiles(WrtContext* ctx, const void* d_gathered, int world, int64_
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t wrt_kernel_launch_count(WrtContext* ctx);
 
+/* FP32 SIMT issue-rate microbenchmark on this GPU: TFLOP/s of dependent-chain FFMA
+ * (2 flops/instruction) and of the separate FMUL+FADD form this library's
+ * -fmad=false kernels issue (1 flop/instruction).  Roofline denominators. */
+int wrt_measure_fp32_peak(WrtContext* ctx, float* tflops_fma, float* tflops_mul_add);
+
 /* Per-kernel-family device milliseconds of the last wrt_render* call (CUDA events
  * on the launching stream).  Order: raygen, trace_closest, surface, shadow_hard,
  * shadow_soft, shadow_directional, shade, combine, resolve.  Returns the number

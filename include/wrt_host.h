@@ -50,6 +50,16 @@ const char* wrt_scene_output_name(const WrtScene* s);
 /* ASCII P3 writer, byte-identical to the reference's output for 8-bit data. */
 int wrt_write_ppm_p3(const char* path, int width, int height, const uint8_t* rgb);
 
+/* Image sharding (include/wrt_tiles.h) for the multi-GPU driver and its CPU tests.
+ * wrt_tile_slot_count: slots (tile area incl. padding) rank `rank` of `world` owns.
+ * wrt_tile_pixel_map:  out[slot] = y*width + x of that slot's pixel, or -1 for padding.
+ * wrt_scatter_tiles_host: CPU twin of the rank-0 scatter kernel — `gathered` holds `world`
+ *   tile-order RGB buffers of stride_bytes each; writes the row-major image. */
+int64_t wrt_tile_slot_count(int width, int height, int tile_w, int tile_h, int rank, int world);
+int wrt_tile_pixel_map(int width, int height, int tile_w, int tile_h, int rank, int world, int64_t* out, int64_t capacity);
+int wrt_scatter_tiles_host(int width, int height, int tile_w, int tile_h, int world, const uint8_t* gathered,
+                           int64_t stride_bytes, uint8_t* rgb_image);
+
 const char* wrt_host_last_error(void);
 
 #ifdef __cplusplus

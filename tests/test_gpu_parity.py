@@ -1,0 +1,309 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the
+same inputs, against the reference's golden vectors, and — at BASELINE.json's full
+sizes — through size-independent properties.
+
+Bars (DESIGN.md section "Parity"):
+  * closest hit (flag, object, t, position, normal, triangle uv), soft / directional
+    shadow queries: bit-exact;
+  * hard-shadow coefficient: bit-exact whenever <= 3 translucent crossings, else <= 4 ulp
+    (the reference multiplies the (1-alpha) factors in BVH-tree association);
+  * sphere uv (acos/atan2): <= 2 ulp;
+  * images: within 1 LSB per channel on >= 99.9 % of pixels vs the reference (north star),
+    and >= 99.99 % bit-identical vs the oracle (only powf's last ulp differs);
+  * soft shadows vs the true reference: PSNR >= 30 dB against the reference's mean image.
+"""
+import ctypes as C
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_bindings as ob
+from conftest import GOLD, IMG_SCENES, RAY_SCENES, SOFT_SCENES, REPO, image_diff, load_golden_scene, psnr, ulp_diff
+from whittedstyle_raytracer_b200 import Renderer, Scene, fixtures, read_ppm_p3
+from whittedstyle_raytracer_b200.renderer import TRAVERSAL_EXHAUSTIVE, TRAVERSAL_PRUNED
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_render(scene, traversal=TRAVERSAL_PRUNED, **tiles):
+    r = Renderer(scene)
+    r.ctx.set_options(traversal=traversal)
+    if tiles:
+        r.ctx.set_tiles(**tiles)
+    img = r.render()
+    st = r.last_stats
+    r.ctx.close()
+    return img, st
+
+
+@pytest.mark.parametrize("traversal", [TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE])
+@pytest.mark.parametrize("name", IMG_SCENES)
+def test_image_matches_oracle_and_reference(workdir, name, traversal):
+    scene, g = load_golden_scene(workdir, name)
+    img, st = gpu_render(scene, traversal)
+    ref, ost = ob.OracleScene(scene).render()
+    d = image_diff(img, ref)
+    assert d["exact"] >= 0.9999 * d["n"] and d["within1"] >= 0.999 * d["n"], ("vs oracle", d)
+    d = image_diff(img, g["rgb"])
+    assert d["within1"] >= 0.999 * d["n"], ("vs reference golden", d)
+    assert st["closest_rays"] == ost.closest_rays == int(g["closest_rays"])
+    assert st["shadow_rays"] == ost.shadow_rays == int(g["shadow_rays"])
+    assert st["rays_per_depth"] == [int(x) for x in ost.rays_per_depth]
+
+
+def test_config_txt_800x600_pixel_gate(workdir):
+    """BASELINE.json configs[0] — the PR1 gate: +-1 LSB on >= 99.9 % of the reference's pixels."""
+    scene, g = load_golden_scene(workdir, "config_800x600")
+    img, st = gpu_render(scene)
+    d = image_diff(img, g["rgb"])
+    assert d["within1"] >= 0.999 * d["n"], d
+    assert d["exact"] >= 0.999 * d["n"], d
+    assert (st["closest_rays"], st["shadow_rays"]) == (952311, 817273)
+
+
+@pytest.mark.parametrize("name", RAY_SCENES)
+def test_strategy_queries_match_oracle_and_reference(workdir, name):
+    scene, _ = load_golden_scene(workdir, name)
+    g = np.load(GOLD / f"rays_{name}.npz")
+    orc = ob.OracleScene(scene)
+    r = Renderer(scene)
+    for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
+        r.ctx.set_options(traversal=traversal)
+        h = r.interStrategy.UpdateInter(g["orig"], g["dir"])
+        for ref in (orc.trace_closest(g["orig"], g["dir"]), g["hits"]):
+            for k in ("hit", "object", "texture", "normalmap"):
+                assert np.array_equal(h[k], ref[k]), (k, traversal)
+            for k in ("t", "pos", "ndir"):
+                assert np.array_equal(h[k].view(np.int32), ref[k].view(np.int32)), (k, traversal)
+            assert ulp_diff(h["uv"], ref["uv"]).max() <= 2
+        soft = r.interStrategy.getSoftShadowSample(g["sh_pos"], g["sh_ndir"], g["sh_light"])
+        assert np.array_equal(soft, g["sh_soft"])
+    hard = r.interStrategy.getShadowCoeffi(g["sh_pos"], g["sh_ndir"], g["sh_light"])
+    assert ulp_diff(hard, g["sh_hard"]).max() <= 4
+    assert (hard == g["sh_hard"]).mean() >= 0.99
+    assert np.array_equal(hard == 0, g["sh_hard"] == 0) and np.array_equal(hard == 1, g["sh_hard"] == 1)
+    dirc = r.interStrategy.getDirectionalShadowCoeffi(g["sh_pos"], g["sh_self"], g["sh_ldir"])
+    assert np.array_equal(dirc, g["sh_dir"])
+    r.ctx.close()
+
+
+def test_million_random_rays_bit_exact(workdir):
+    """1e6 rays (uniform, surface-leaving, axis-parallel) through the bunny BVH: both GPU
+    traversals equal the oracle's exhaustive recursive traversal bit for bit."""
+    scene, _ = load_golden_scene(workdir, "water_small")
+    rng = np.random.default_rng(11)
+    n = 1_000_000
+    o = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
+    o[:, 1] -= 1.0
+    o[:, 2] -= 3.0
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:3000] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 3000)]
+    orc = ob.OracleScene(scene)
+    ref = orc.trace_closest(o, d)
+    hp = ref["pos"][ref["hit"] == 1]
+    k = len(hp)
+    o[-k:] = hp + 5e-5 * d[-k:]                      # secondary-ray-like origins on the surface
+    ref = orc.trace_closest(o, d)
+    assert 0.05 < ref["hit"].mean() < 0.95
+    r = Renderer(scene)
+    for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
+        r.ctx.set_options(traversal=traversal)
+        h = r.interStrategy.UpdateInter(o, d)
+        for f in ("hit", "object", "prim"):
+            assert np.array_equal(h[f], ref[f]), (f, traversal)
+        for f in ("t", "pos", "ndir"):
+            assert np.array_equal(h[f].view(np.int32), ref[f].view(np.int32)), (f, traversal)
+    # shadow queries from the same points
+    m = ref["hit"] == 1
+    pos, nd = ref["pos"][m][:200000], ref["ndir"][m][:200000]
+    lp = np.tile(np.array([[-20, 70, 20]], np.float32), (len(pos), 1))
+    lp[::3] = rng.uniform(-25, 25, (len(lp[::3]), 3)).astype(np.float32)
+    assert np.array_equal(r.interStrategy.getSoftShadowSample(pos, nd, lp), orc.shadow_soft(pos, nd, lp))
+    hard, href = r.interStrategy.getShadowCoeffi(pos, nd, lp), orc.shadow_hard(pos, nd, lp)
+    assert ulp_diff(hard, href).max() <= 4 and (hard == href).mean() > 0.99
+    r.ctx.close()
+
+
+@pytest.mark.parametrize("name", SOFT_SCENES)
+def test_soft_shadows(workdir, name):
+    """Same counter RNG on both sides: GPU == oracle bit for bit; both agree with the
+    non-deterministic reference in the mean image (PSNR gate 30 dB)."""
+    scene, g = load_golden_scene(workdir, name, kind="soft")
+    img, st = gpu_render(scene)
+    ref, ost = ob.OracleScene(scene).render()
+    d = image_diff(img, ref)
+    assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+    assert psnr(img, g["mean_rgb"]) >= 30.0
+    assert st["shadow_rays"] == ost.shadow_rays == int(g["shadow_rays"])
+    img2, _ = gpu_render(scene, TRAVERSAL_EXHAUSTIVE)
+    assert np.array_equal(img, img2)                 # deterministic, traversal-independent
+    r = Renderer(scene)
+    r.ctx.set_options(seed=1234)
+    other = r.render()
+    assert not np.array_equal(other, img) and psnr(other, g["mean_rgb"]) >= 30.0
+    r.ctx.close()
+
+
+@pytest.mark.parametrize("name,world,tile", [("water_small", 2, (32, 16)), ("spheres", 3, (8, 4)), ("smooth", 8, (64, 32))])
+def test_tile_sharding_is_rank_count_invariant(workdir, name, world, tile):
+    """N-rank interleaved tiles (each rank rendered on this one GPU in turn) reassemble
+    into exactly the 1-rank image, via host buffers and via the packed device path +
+    rank-0 scatter kernel that follows the NCCL gather."""
+    import torch
+    scene, _ = load_golden_scene(workdir, name)
+    full, st_full = gpu_render(scene)
+    h, w = full.shape[:2]
+    merged = np.zeros_like(full)
+    r = Renderer(scene)
+    counts = [r.ctx.tile_pixel_count(k, world) for k in range(world)]
+    stride = max(counts) * 3
+    gathered = torch.zeros(world * stride, dtype=torch.uint8, device="cuda")
+    rays = 0
+    for k in range(world):
+        r.ctx.set_tiles(tile_w=tile[0], tile_h=tile[1], rank=k, world=world)
+        r.render(out=merged)                          # only rank k's pixels are written
+        part = gathered[k * stride:(k + 1) * stride]
+        r.render_device(part.data_ptr())
+        rays += r.finish_device()["rays"]
+    assert np.array_equal(merged, full)
+    assert rays == st_full["rays"]
+    r.ctx.set_tiles(tile_w=tile[0], tile_h=tile[1], rank=0, world=world)
+    image = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda")
+    r.scatter_tiles(gathered.data_ptr(), world, stride, image.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(image.cpu().numpy().reshape(h, w, 3), full)
+    r.ctx.close()
+
+
+def test_queue_overflow_is_rerendered_not_dropped(workdir):
+    """Eye inside a glass ball: every primary hit spawns a reflection and a transmission,
+    so level 1 holds ~2x the primary rays.  With queue_factor 1 the level overflows; the
+    frame must come out identical (re-rendered in halves), with the retry reported."""
+    text = """imsize 160 96
+eye 0 0 0
+viewdir 0 0 -1
+hfov 80
+updir 0 1 0
+bkgcolor 0.2 0.3 0.5 1.0
+light 3 4 2 1 1 1 1
+mtlcolor 0.9 0.9 1 1 1 1 0.1 0.2 0.4 50 0.1 1.5
+sphere 0 0 0 2
+mtlcolor 0.8 0.3 0.2 1 1 1 0.2 0.7 0.3 20 1 1
+sphere 0 0 -6 1.5
+sphere 4 1 -5 1.5
+"""
+    scene = Scene(text=text, asset_dir=workdir)
+    ref, ost = ob.OracleScene(scene).render()
+    r = Renderer(scene)
+    img = r.render()
+    assert r.last_stats["overflow_retries"] == 0
+    assert r.last_stats["rays_per_depth"][1] > 1.5 * 160 * 96
+    r.ctx.set_options(queue_factor=1.0)
+    img2 = r.render()
+    assert r.last_stats["overflow_retries"] >= 1
+    assert np.array_equal(img, img2)
+    assert r.last_stats["closest_rays"] == ost.closest_rays and r.last_stats["shadow_rays"] == ost.shadow_rays
+    d = image_diff(img, ref)
+    assert d["exact"] >= 0.9999 * d["n"], d
+    r.ctx.close()
+
+
+@pytest.mark.parametrize("text,expect", [
+    ("imsize 7 5\neye 0 0 0\nviewdir 0 0 -1\nupdir 0 1 0\nhfov 60\nbkgcolor 0.5 0.25 1 1\n", "empty"),
+    ("imsize 33 17\neye 0 0 0\nviewdir 0 0 -1\nupdir 0 1 0\nhfov 60\nbkgcolor 0.1 0.1 0.1 1\nlight 1 1 1 1 1 1 1\n"
+     "mtlcolor 0.8 0.4 0.2 1 1 1 0.3 0.6 0.2 10 1 1\nsphere 0 0 -3 1\n", "one object (root is a leaf)"),
+    ("imsize 1 1\neye 0 0 0\nviewdir 0 0 -1\nupdir 0 1 0\nhfov 60\nbkgcolor 0.1 0.1 0.1 1\nlight 1 1 1 1 1 1 1\nshadow soft\n"
+     "mtlcolor 0.8 0.4 0.2 1 1 1 0.3 0.6 0.2 10 0.5 1.3\nsphere 0 0 -3 1\nsphere 0.5 0 -5 1\n", "two objects, 1x1 image, soft"),
+    ("imsize 40 30\neye 0 0 0\nviewdir 0 0 -1\nupdir 0 1 0\nhfov 60\nbkgcolor 0.1 0.1 0.1 1\nlight 0 5 -3 1 1 1 1\nshadow soft\n"
+     "mtlcolor 1 1 1 1 1 1 1 1 1 0 1 1\nsphere 0 5 -3 0.5\nmtlcolor 0.8 0.4 0.2 1 1 1 0.3 0.6 0.2 10 1 1\n"
+     "sphere 0 0 -4 1\nv -5 -1 0\nv 5 -1 0\nv 0 -1 -9\nf 1 2 3\n", "light avatar + soft shadows (literal hasIntersection path)"),
+])
+def test_edge_scenes(workdir, text, expect):
+    scene = Scene(text=text, asset_dir=workdir)
+    ref, ost = ob.OracleScene(scene).render()
+    for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
+        img, st = gpu_render(scene, traversal)
+        d = image_diff(img, ref)
+        assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, (expect, d)
+        assert st["closest_rays"] == ost.closest_rays and st["shadow_rays"] == ost.shadow_rays, expect
+
+
+def test_render_is_deterministic_and_reusable(workdir):
+    scene, _ = load_golden_scene(workdir, "water_small")
+    r = Renderer(scene)
+    a = r.render().copy()
+    scene.set_imsize(97, 61)                         # not a multiple of the tile size
+    r.ctx.set_camera(scene)
+    small = r.render()
+    ref, _ = ob.OracleScene(scene).render()
+    assert image_diff(small, ref)["exact"] >= 0.9999 * 97 * 61
+    scene.set_imsize(200, 150)
+    r.ctx.set_camera(scene)
+    assert np.array_equal(r.render(), a)
+    assert r.ctx.launches > 0
+    r.ctx.close()
+
+
+def test_drop_in_executable(workdir):
+    """`wrt <config>` in a cwd holding bunny.obj + textures writes the same P3 file the
+    reference's executable would (here: the oracle's pixels through the same writer)."""
+    exe = REPO / "whittedstyle_raytracer_b200" / "wrt"
+    fixtures.write_config(workdir, "cli_scene", fixtures.bunny_shadow_config(120, 90))
+    p = subprocess.run([str(exe), "cli_scene.txt"], cwd=workdir, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Generating is done successfully!" in p.stdout and "Rendering Time consumed" in p.stdout
+    got = read_ppm_p3(workdir / "cli_scene.ppm")
+    scene = Scene.from_workdir(workdir, "cli_scene")
+    ref, _ = ob.OracleScene(scene).render()
+    assert image_diff(got, ref)["exact"] >= 0.9999 * 120 * 90
+    text = (workdir / "cli_scene.ppm").read_text()
+    assert text.startswith("P3\n120\n90\n255\n") and text.count("\n") == 4 + 120 * 90
+    (workdir / "bad.txt").write_text("imsize 4 4\nfoo 1\n")
+    p = subprocess.run([str(exe), "bad.txt"], cwd=workdir, capture_output=True, text=True)
+    assert p.returncode == 255 and "ERROR: extraneous string in the input file" in p.stdout
+
+
+# ---------------- BASELINE.json full sizes: size-independent properties ----------------
+
+FULL = [("bunny_shadow_4k", 17959375, 15256192), ("gla_bunny_tex_4k", 17959375, 14487729)]
+
+
+@pytest.mark.parametrize("name,closest,shadow", FULL)
+def test_4k_hard_shadow_configs(workdir, name, closest, shadow):
+    """3840x2160: ray counts equal the reference's own (measured with the
+    instrumented reference); a 1/16 x 1/16 pixel sample equals the oracle; pruned == exhaustive;
+    a 4-rank tile split reassembles into the same frame."""
+    fixtures.write_config(workdir, name, fixtures.bench_config_text(name))
+    scene = Scene.from_workdir(workdir, name)
+    r = Renderer(scene)
+    img = r.render().copy()
+    assert (r.last_stats["closest_rays"], r.last_stats["shadow_rays"]) == (closest, shadow)
+    sample, _ = ob.OracleScene(scene).render(stride=(16, 16))
+    d = image_diff(img[::16, ::16], sample[::16, ::16])
+    assert d["exact"] >= 0.9995 * d["n"] and d["within1"] >= 0.999 * d["n"], d
+    r.ctx.set_options(traversal=TRAVERSAL_EXHAUSTIVE)
+    assert np.array_equal(r.render(), img)
+    r.ctx.set_options(traversal=TRAVERSAL_PRUNED)
+    merged = np.zeros_like(img)
+    for k in range(4):
+        r.ctx.set_tiles(rank=k, world=4)
+        r.render(out=merged)
+    assert np.array_equal(merged, img)
+    r.ctx.close()
+
+
+def test_4k_soft_shadow_config(workdir):
+    """water_bunny_tex + shadow soft at 3840x2160 (BASELINE.json's metric config): 742,345,825 rays
+    like the reference; a strided pixel sample equals the oracle (same RNG keys at full size)."""
+    name = "water_bunny_tex_soft_4k"
+    fixtures.write_config(workdir, name, fixtures.bench_config_text(name))
+    scene = Scene.from_workdir(workdir, name)
+    r = Renderer(scene)
+    img = r.render()
+    assert (r.last_stats["closest_rays"], r.last_stats["shadow_rays"]) == (17959375, 724386450)
+    sample, _ = ob.OracleScene(scene).render(stride=(48, 40))
+    d = image_diff(img[::40, ::48], sample[::40, ::48])
+    assert d["exact"] >= 0.999 * d["n"] and d["max"] <= 1, d
+    r.ctx.close()

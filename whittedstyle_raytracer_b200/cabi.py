@@ -80,14 +80,15 @@ HIT_DTYPE = [("hit", "<i4"), ("object", "<i4"), ("t", "<f4"), ("pos", "<f4", 3),
 HOST_SYMBOLS = [
     "wrt_scene_load", "wrt_scene_load_text", "wrt_scene_free", "wrt_scene_desc", "wrt_scene_camera",
     "wrt_scene_set_imsize", "wrt_scene_set_shadow_type", "wrt_scene_bvh_depth", "wrt_scene_upload_bytes",
-    "wrt_scene_output_name", "wrt_write_ppm_p3", "wrt_host_last_error",
+    "wrt_scene_output_name", "wrt_write_ppm_p3", "wrt_host_last_error", "wrt_tile_slot_count", "wrt_tile_pixel_map",
+    "wrt_scatter_tiles_host",
 ]
 # Entry points include/wrt_cuda.h declares
 CUDA_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_upload_scene", "wrt_set_camera", "wrt_set_tiles",
     "wrt_set_options", "wrt_enable_kernel_timing", "wrt_trace_closest", "wrt_shadow_hard", "wrt_shadow_soft", "wrt_shadow_directional",
     "wrt_render", "wrt_render_device", "wrt_finish_device", "wrt_get_stats", "wrt_tile_pixel_count",
-    "wrt_scatter_tiles", "wrt_kernel_launch_count", "wrt_get_kernel_times",
+    "wrt_scatter_tiles", "wrt_kernel_launch_count", "wrt_get_kernel_times", "wrt_measure_fp32_peak",
 ]
 
 _host = None
@@ -118,6 +119,10 @@ def load_host() -> C.CDLL:
         lib.wrt_scene_output_name.restype = cp
         lib.wrt_write_ppm_p3.argtypes = [cp, i32, i32, vp]
         lib.wrt_host_last_error.restype = cp
+        lib.wrt_tile_slot_count.argtypes = [i32] * 6
+        lib.wrt_tile_slot_count.restype = C.c_int64
+        lib.wrt_tile_pixel_map.argtypes = [i32] * 6 + [vp, C.c_int64]
+        lib.wrt_scatter_tiles_host.argtypes = [i32] * 5 + [vp, C.c_int64, vp]
         _host = lib
     return _host
 
@@ -152,6 +157,7 @@ def load_cuda() -> C.CDLL:
         lib.wrt_tile_pixel_count.restype = i64
         lib.wrt_scatter_tiles.argtypes = [vp, vp, i32, i64, vp, vp]
         lib.wrt_enable_kernel_timing.argtypes = [vp, i32]
+        lib.wrt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.wrt_kernel_launch_count.argtypes = [vp]
         lib.wrt_kernel_launch_count.restype = i64
         lib.wrt_get_kernel_times.argtypes = [vp, vp, i32]

@@ -14,6 +14,7 @@
 #pragma once
 #include "dev_shade.cuh"
 #include "../../../include/wrt_rng.h"
+#include "../../../include/wrt_tiles.h"
 
 namespace wrt {
 
@@ -27,25 +28,9 @@ enum CounterSlot {
     C_TOTAL = 192
 };
 
-struct TileMap {
-    int width, height;
-    int tile_w, tile_h, tiles_x, tiles_y;
-    int rank, world;
-    __host__ __device__ int tile_pixels() const { return tile_w * tile_h; }
-    // local slot -> pixel; false when the slot is padding outside the image
+struct TileMap : WrtTileMap {     // include/wrt_tiles.h
     __host__ __device__ bool slot_to_pixel(long long slot, int rank_, int& px, int& py) const {
-        int tp = tile_w * tile_h;
-        long long tl = slot / tp;
-        int within = (int)(slot - tl * tp);
-        long long t = tl * world + rank_;
-        if (t >= (long long)tiles_x * tiles_y) return false;
-        int tx = (int)(t % tiles_x), ty = (int)(t / tiles_x);
-        int bw = tile_w / 8;
-        int b = within >> 5, lane = within & 31;
-        int bx = b % bw, by = b / bw;
-        px = tx * tile_w + bx * 8 + (lane & 7);
-        py = ty * tile_h + by * 4 + (lane >> 3);
-        return px < width && py < height;
+        return wrt_tilemap_slot_to_pixel(this, slot, rank_, &px, &py) != 0;
     }
 };
 
@@ -495,6 +480,31 @@ __global__ void __launch_bounds__(128) k_batch_shadow_directional(DevScene s, co
         Ray r = make_ray(p, normalized(negDir));
         out[i] = directional_product(s, r, self_prim);
     }
+}
+
+// ---- FP32 issue-rate microbenchmark (the roofline denominator SURVEY.md section 8d asks for) ----
+// mode 0: 8 independent FFMA chains per thread (2 flops per instruction);
+// mode 1: the same chains as separate FMUL + FADD (what -fmad=false code issues).
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, int mode) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 1.0f + 1e-3f * (float)((threadIdx.x + k) & 31);
+    const float m = 0.999999f, c = 1e-7f;
+    if (mode == 0) {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = __fmaf_rn(a[k], m, c);
+        }
+    } else {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = __fadd_rn(__fmul_rn(a[k], m), c);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += a[k];
+    if (sum == 12345.678f) out[0] = sum;       // never true; keeps the chains alive
 }
 
 } // namespace wrt

@@ -90,19 +90,12 @@ struct WrtContext {
 
     wrt::TileMap tilemap() const {
         wrt::TileMap tm;
-        tm.width = cam.width; tm.height = cam.height;
-        tm.tile_w = tile_w; tm.tile_h = tile_h;
-        tm.tiles_x = (cam.width + tile_w - 1) / tile_w;
-        tm.tiles_y = (cam.height + tile_h - 1) / tile_h;
-        tm.rank = rank; tm.world = world;
+        static_cast<WrtTileMap&>(tm) = wrt_tilemap_make(cam.width, cam.height, tile_w, tile_h, rank, world);
         return tm;
     }
     long long local_slots(int r, int w) const {
-        wrt::TileMap tm = tilemap();
-        long long tiles = (long long)tm.tiles_x * tm.tiles_y;
-        long long mine = (tiles - r + w - 1) / w;
-        if (mine < 0) mine = 0;
-        return mine * tile_w * tile_h;
+        WrtTileMap tm = wrt_tilemap_make(cam.width, cam.height, tile_w, tile_h, r, w);
+        return wrt_tilemap_slots(&tm, r, w);
     }
 };
 
@@ -741,6 +734,36 @@ int wrt_scatter_tiles(WrtContext* c, const void* d_gathered, int world, int64_t 
 }
 
 int64_t wrt_kernel_launch_count(WrtContext* c) { return c ? c->launches : 0; }
+
+int wrt_measure_fp32_peak(WrtContext* c, float* tflops_fma, float* tflops_mul_add) {
+    if (!c || !tflops_fma || !tflops_mul_add) return fail("wrt_measure_fp32_peak: null argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->own_stream;
+    if (ensure_scratch(c, 4, 256)) return 1;
+    const int iters = 1 << 15, blocks = c->num_sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best[2] = {0.f, 0.f};
+    for (int mode = 0; mode < 2; mode++) {
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(e0, st));
+            wrt::k_fp32_peak<<<blocks, threads, 0, st>>>((float*)c->d_scratch[4], iters, mode);
+            CK(cudaEventRecord(e1, st));
+            CK(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            double flops = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+            float tf = (float)(flops / (ms * 1e-3) / 1e12);
+            if (rep > 0 && tf > best[mode]) best[mode] = tf;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_fma = best[0];
+    *tflops_mul_add = best[1];
+    return 0;
+}
 
 int wrt_get_kernel_times(WrtContext* c, float* ms, int capacity) {
     if (!c || !ms) return 0;

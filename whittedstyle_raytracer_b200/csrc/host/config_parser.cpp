@@ -8,7 +8,9 @@
 //   * every argument read is preceded by checkFin() (:671-675);
 //   * keyword table :371-618, objects :209-365, faces :679-823, textures :827-881;
 //   * errors do not exit here: they throw ParseError carrying the text the
-//     reference prints after "ERROR: "; the CLI turns that into exit(-1).
+//     reference prints after "ERROR: " (or the whole line when the reference
+//     prints it directly and the text starts with "ERROR:"); the CLI turns that
+//     into the same console line + exit(-1).
 #include <fstream>
 #include <regex>
 #include <sstream>
@@ -119,12 +121,12 @@ struct Parser {
         std::string path = name;
         if (!g.assetDir.empty() && !(name.size() && name[0] == '/')) path = g.assetDir + "/" + name;
         std::ifstream input(path, std::ios::in | std::ios::binary);
-        if (!input.is_open()) throw ParseError(": texture file does not exits, program terminates.\n");
+        if (!input.is_open()) throw ParseError("ERROR:: texture file does not exits, program terminates.\n");
         TokenStream in;
         in.data.assign(std::istreambuf_iterator<char>(input), std::istreambuf_iterator<char>());
         std::string b0, b1, b2;
         in.read(b0); in.read(b1); in.read(b2);
-        if (b0 != "P3") throw ParseError(": Need P3 keyword, program terminates.\n");
+        if (b0 != "P3") throw ParseError("ERROR:: Need P3 keyword, program terminates.\n");
         Texture t;
         t.name = name;
         checkPosInt(b1); checkPosInt(b2);
@@ -414,7 +416,7 @@ void HostScene::parseConfigText(const std::string& text) {
 
 void HostScene::parseConfigFile(const std::string& path) {
     std::ifstream f(path, std::ios::in | std::ios::binary);
-    if (!f.is_open()) throw ParseError(": inputfile does not exits, program terminates.\n");
+    if (!f.is_open()) throw ParseError("ERROR:: inputfile does not exits, program terminates.\n");
     inputName = path;
     std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     parseConfigText(text);

@@ -4,6 +4,7 @@
 #include <memory>
 
 #include "../../../include/wrt_host.h"
+#include "../../../include/wrt_tiles.h"
 #include "host_scene.hpp"
 
 struct WrtScene {
@@ -82,6 +83,43 @@ int64_t wrt_scene_upload_bytes(const WrtScene* s) {
 }
 
 const char* wrt_scene_output_name(const WrtScene* s) { return s->out_name.c_str(); }
+
+int64_t wrt_tile_slot_count(int width, int height, int tile_w, int tile_h, int rank, int world) {
+    if (width < 0 || height < 0 || tile_w <= 0 || tile_h <= 0 || tile_w % 8 || tile_h % 4 || world < 1 || rank < 0 || rank >= world)
+        return -1;
+    WrtTileMap tm = wrt_tilemap_make(width, height, tile_w, tile_h, rank, world);
+    return wrt_tilemap_slots(&tm, rank, world);
+}
+
+int wrt_tile_pixel_map(int width, int height, int tile_w, int tile_h, int rank, int world, int64_t* out, int64_t capacity) {
+    int64_t n = wrt_tile_slot_count(width, height, tile_w, tile_h, rank, world);
+    if (n < 0) { g_err = "wrt_tile_pixel_map: bad tile geometry"; return 1; }
+    if (capacity < n) { g_err = "wrt_tile_pixel_map: output too small"; return 1; }
+    WrtTileMap tm = wrt_tilemap_make(width, height, tile_w, tile_h, rank, world);
+    for (int64_t s = 0; s < n; s++) {
+        int x, y;
+        out[s] = wrt_tilemap_slot_to_pixel(&tm, s, rank, &x, &y) ? (int64_t)y * width + x : -1;
+    }
+    return 0;
+}
+
+int wrt_scatter_tiles_host(int width, int height, int tile_w, int tile_h, int world, const uint8_t* gathered,
+                           int64_t stride_bytes, uint8_t* rgb_image) {
+    if (wrt_tile_slot_count(width, height, tile_w, tile_h, 0, world) < 0) { g_err = "wrt_scatter_tiles_host: bad tile geometry"; return 1; }
+    for (int r = 0; r < world; r++) {
+        WrtTileMap tm = wrt_tilemap_make(width, height, tile_w, tile_h, r, world);
+        int64_t n = wrt_tilemap_slots(&tm, r, world);
+        if (n * 3 > stride_bytes) { g_err = "wrt_scatter_tiles_host: stride smaller than a rank's tile buffer"; return 1; }
+        for (int64_t s = 0; s < n; s++) {
+            int x, y;
+            if (!wrt_tilemap_slot_to_pixel(&tm, s, r, &x, &y)) continue;
+            const uint8_t* p = gathered + (size_t)r * stride_bytes + 3 * (size_t)s;
+            uint8_t* q = rgb_image + 3 * ((size_t)y * width + x);
+            q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+        }
+    }
+    return 0;
+}
 
 // PPMGenerator::writeHeader / writePixel (include/PPMGenerator.hpp:631-646):
 // "P3\nW\nH\n255\n" then "r g b\n" per pixel, row-major.

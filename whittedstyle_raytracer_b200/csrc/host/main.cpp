@@ -35,7 +35,8 @@ int main(int argc, char* argv[]) {
                   << std::chrono::duration_cast<std::chrono::seconds>(b1 - b0).count() << " seconds\n";
     } catch (const std::exception& e) {
         const char* w = e.what();
-        std::cout << (w[0] == ':' ? "ERROR:" : "ERROR: ") << w;
+        if (strncmp(w, "ERROR:", 6) != 0) std::cout << "ERROR: ";
+        std::cout << w;
         exit(-1);
     }
     try {

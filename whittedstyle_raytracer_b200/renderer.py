@@ -93,6 +93,12 @@ class Context:
         n = self.lib.wrt_get_kernel_times(self.h, ms, len(KERNEL_FAMILIES))
         return {KERNEL_FAMILIES[i]: float(ms[i]) for i in range(n)}
 
+    def measure_fp32_peak(self) -> tuple[float, float]:
+        """(TFLOP/s with FFMA, TFLOP/s with separate FMUL+FADD) measured on this GPU."""
+        a, b = C.c_float(0), C.c_float(0)
+        self._check(self.lib.wrt_measure_fp32_peak(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     def tile_pixel_count(self, rank, world) -> int:
         return int(self.lib.wrt_tile_pixel_count(self.h, rank, world))
 

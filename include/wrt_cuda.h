@@ -70,8 +70,8 @@ int wrt_shadow_directional(WrtContext* ctx, const float* pos, const int32_t* sel
  * pixels of other ranks' tiles left untouched) to host memory.  Synchronous. */
 int wrt_render(WrtContext* ctx, uint8_t* rgb_host, WrtStats* stats);
 
-/* Asynchronous form on caller-provided device memory and stream (cudaStream_t as void*,
- * NULL = the context's own stream).  d_rgb_tiles receives this rank's pixels in tile
+/* Asynchronous form on caller-provided device memory and stream (cudaStream_t as void*;
+ * NULL is CUDA's legacy default stream, e.g. torch's default current stream).  d_rgb_tiles receives this rank's pixels in tile
  * order: wrt_tile_pixel_count(ctx, rank, world) * 3 bytes.  Call wrt_finish_device()
  * before reading statistics. */
 int wrt_render_device(WrtContext* ctx, void* d_rgb_tiles, void* cuda_stream);

@@ -157,9 +157,11 @@ def test_tile_sharding_is_rank_count_invariant(workdir, name, world, tile):
     h, w = full.shape[:2]
     merged = np.zeros_like(full)
     r = Renderer(scene)
+    r.ctx.set_tiles(tile_w=tile[0], tile_h=tile[1], rank=0, world=world)
     counts = [r.ctx.tile_pixel_count(k, world) for k in range(world)]
     stride = max(counts) * 3
     gathered = torch.zeros(world * stride, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     rays = 0
     for k in range(world):
         r.ctx.set_tiles(tile_w=tile[0], tile_h=tile[1], rank=k, world=world)
@@ -197,6 +199,7 @@ sphere 4 1 -5 1.5
     scene = Scene(text=text, asset_dir=workdir)
     ref, ost = ob.OracleScene(scene).render()
     r = Renderer(scene)
+    r.ctx.set_options(queue_factor=4.0)
     img = r.render()
     assert r.last_stats["overflow_retries"] == 0
     assert r.last_stats["rays_per_depth"][1] > 1.5 * 160 * 96

@@ -687,7 +687,7 @@ int wrt_render(WrtContext* c, uint8_t* rgb_host, WrtStats* stats) {
 int wrt_render_device(WrtContext* c, void* d_rgb_tiles, void* cuda_stream) {
     if (!c || !d_rgb_tiles) return fail("wrt_render_device: null argument");
     CK(cudaSetDevice(c->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;        // NULL = the legacy default stream, as in CUDA
     return render_all(c, st, nullptr, (uint8_t*)d_rgb_tiles);
 }
 
@@ -721,7 +721,7 @@ int wrt_scatter_tiles(WrtContext* c, const void* d_gathered, int world, int64_t 
     if (!c || !d_gathered || !d_rgb_image) return fail("wrt_scatter_tiles: null argument");
     if (!c->has_cam) return fail("wrt_scatter_tiles: no camera set");
     CK(cudaSetDevice(c->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;        // NULL = the legacy default stream, as in CUDA
     wrt::TileMap tm = c->tilemap();
     tm.world = world;
     long long slots_per_rank = c->local_slots(0, world);   // rank 0 owns the most tiles

@@ -16,7 +16,8 @@
 namespace wrt {
 
 struct DevScene {
-    const float4* nodes;
+    const float4* nodes;      // reference-topology tree (host-built, BVH.hpp:49-125)
+    const float4* fnodes;     // SAH tree over the same leaf boxes (fast_bvh.hpp), same record layout
     const float4* geom;
     const float4* attr;       // per prim 4x float4: {n0,uv0.x} {n1,uv0.y} {n2,uv1.x} {uv1.y,uv2.x,uv2.y,0}
     const int4*   ids;        // per prim {material, texture, normalmap, object}
@@ -82,12 +83,14 @@ __device__ __forceinline__ bool tri_test(const float4 A, const float4 B, const f
     return false;
 }
 
-// Sphere::intersect root selection, Sphere.hpp:25-47,80-90 + solveQuadratic global.hpp:105-125
-__device__ __noinline__ bool sphere_test(const float4 A, const Ray& r, PrimHit& h) {
-    float cx = A.x, cy = A.y, cz = A.z, radius = A.w;
+// Sphere::intersect root selection, Sphere.hpp:25-47,80-90 + solveQuadratic global.hpp:105-125.
+// Out of line (spheres are rare next to triangle meshes) and by value, so that the
+// caller's ray stays in registers.  Returns {hit ? 1 : 0, t}.
+__device__ __noinline__ float2 sphere_test(float cx, float cy, float cz, float radius, float ox, float oy, float oz,
+                                           float dx_, float dy_, float dz_) {
     float Aq = 1.f;
-    float Bq = 2 * (r.d.x * (r.o.x - cx) + r.d.y * (r.o.y - cy) + r.d.z * (r.o.z - cz));
-    double dx = (double)(r.o.x - cx), dy = (double)(r.o.y - cy), dz = (double)(r.o.z - cz);
+    float Bq = 2 * (dx_ * (ox - cx) + dy_ * (oy - cy) + dz_ * (oz - cz));
+    double dx = (double)(ox - cx), dy = (double)(oy - cy), dz = (double)(oz - cz);
     float Cq = (float)(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)),
                                  -(double)(radius * radius)));
     float disc = Bq * Bq - 4 * Aq * Cq;
@@ -97,18 +100,17 @@ __device__ __noinline__ bool sphere_test(const float4 A, const Ray& r, PrimHit& 
     else { t1 = (-Bq + sqrtf(disc)) / 2 * Aq; t2 = (-Bq - sqrtf(disc)) / 2 * Aq; }
     if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
     float t;
-    if (float_equal(t1, FLT_MAX) && float_equal(t2, FLT_MAX)) return false;
+    if (float_equal(t1, FLT_MAX) && float_equal(t2, FLT_MAX)) return make_float2(0.f, 0.f);
     else if (float_equal(t1, t2)) {
-        if (t1 < 0) return false;
+        if (t1 < 0) return make_float2(0.f, 0.f);
         t = t1;
     } else {
         if (t1 > 0 && t2 > 0) t = t1;
         else if (t1 > 0 && t2 < 0) t = t1;
         else if (t1 < 0 && t2 > 0) t = t2;
-        else return false;
+        else return make_float2(0.f, 0.f);
     }
-    h.t = t; h.u = 0.f; h.v = 0.f;
-    return true;
+    return make_float2(1.f, t);
 }
 
 __device__ __forceinline__ bool prim_test(const DevScene& s, int p, const Ray& r, PrimHit& h, float& one_minus_alpha,
@@ -117,14 +119,16 @@ __device__ __forceinline__ bool prim_test(const DevScene& s, int p, const Ray& r
     float4 A = ldg4(g), B = ldg4(g + 1), C = ldg4(g + 2);
     one_minus_alpha = B.w;
     flags = __float_as_uint(C.w);
-    if ((flags & WRT_PRIM_KIND_MASK) == WRT_PRIM_SPHERE) return sphere_test(A, r, h);
+    if ((flags & WRT_PRIM_KIND_MASK) == WRT_PRIM_SPHERE) {
+        float2 sp = sphere_test(A.x, A.y, A.z, A.w, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+        h.t = sp.y; h.u = 0.f; h.v = 0.f;
+        return sp.x != 0.f;
+    }
     return tri_test(A, B, C, r, h);
 }
 
-#define WRT_STACK_DEPTH 40   // median-split tree over N prims is ceil(log2 N) deep; 40 covers any 32-bit N
-
 // Per-thread traversal stack in shared memory, column `tid` of a
-// [WRT_STACK_DEPTH][blockDim.x] array: consecutive lanes hit consecutive banks.
+// [rows][blockDim.x] array (rows = tree depth + 2): consecutive lanes hit consecutive banks.
 struct Stack {
     int* base;
     int stride;
@@ -135,158 +139,165 @@ struct Stack {
     __device__ __forceinline__ bool empty() const { return sp == 0; }
 };
 
+// A ray whose direction has a zero component takes the inf/NaN paths of
+// BoundBox::IntersectRay (BoundBox.hpp:55-84), where box inclusion no longer implies
+// slab-test inclusion; such rays walk the reference-topology tree exhaustively.
+__device__ __forceinline__ bool degenerate_dir(f3 d) { return d.x == 0.f || d.y == 0.f || d.z == 0.f; }
+
+// One traversal step: test the two children of pair `cur`, hand hit leaves to `leaf`,
+// descend / push / pop.  Returns false when the walk is over.  `limit`: boxes entered
+// beyond it are skipped (FLT_MAX or +inf = never).  NEAR_FIRST orders by entry distance.
+template <bool NEAR_FIRST, class LeafFn>
+__device__ __forceinline__ bool traverse_step(const float4* __restrict__ nodes, const Ray& r, Stack& st, int& cur,
+                                              const float& limit, LeafFn&& leaf) {
+    const float4* n = nodes + 2 * cur;
+    float4 l0 = ldg4(n), l1 = ldg4(n + 1), r0 = ldg4(n + 2), r1 = ldg4(n + 3);
+    float tl, tr;
+    bool hl = slab(l0, l1, r, tl), hr = slab(r0, r1, r, tr);
+    hl = hl && !(tl > limit);
+    int linkL = __float_as_int(l0.w), linkR = __float_as_int(r0.w);
+    if (hl && linkL < 0) { leaf(~linkL); hl = false; }
+    hr = hr && !(tr > limit);                      // `limit` may have tightened in leaf()
+    if (hr && linkR < 0) { leaf(~linkR); hr = false; }
+    if (hl && hr) {
+        bool right_first = NEAR_FIRST && (tr < tl);
+        st.push(right_first ? linkL : linkR);
+        cur = right_first ? linkR : linkL;
+        return true;
+    }
+    if (hl) { cur = linkL; return true; }
+    if (hr) { cur = linkR; return true; }
+    if (st.empty()) return false;
+    cur = st.pop();
+    return true;
+}
+
 struct Closest {
     float t; int prim; float u, v;
 };
 
-// getIntersection, BVH.hpp:137-159, over the subtree rooted at record `root`.
-// The reference visits every node whose box the ray hits and keeps the minimum
-// t, left subtree on ties.  Here: explicit stack, near child first; with
-// `prune_rel >= 0` a box whose entry distance exceeds best_t*(1+prune_rel)+prune_rel
-// is skipped (its leaves cannot hold a closer hit; the margin absorbs the ulp-level
-// disagreement between slab and Moller-Trumbore distances).  prune_rel < 0 keeps
-// the reference's exhaustive visit.  Ties still resolve to the smaller DFS rank.
-__device__ __forceinline__ Closest closest_hit(const DevScene& s, int root, const Ray& r, Stack& st, float prune_rel) {
+// ---- closest hit: getIntersection, BVH.hpp:137-159 ----
+// Minimum t over every primitive whose own box and intersection test pass; ties go to the
+// smaller reference DFS rank (the left subtree of BVH.hpp:157).  With prune_rel >= 0 a box
+// entered beyond best_t*(1+prune_rel)+prune_rel is skipped: its primitives lie inside it,
+// so they cannot be closer; the margin absorbs the ulp-level disagreement between slab and
+// Moller-Trumbore distances.  prune_rel < 0 visits every hit box like the reference does.
+struct ClosestState {
     Closest best;
-    best.t = FLT_MAX; best.prim = -1; best.u = 0.f; best.v = 0.f;
-    float limit = FLT_MAX;    // prune threshold derived from best.t
-    auto leaf = [&](int p) {
+    float limit;
+    float prune_rel;
+    __device__ __forceinline__ void reset(float prune) {
+        best.t = FLT_MAX; best.prim = -1; best.u = 0.f; best.v = 0.f;
+        limit = FLT_MAX; prune_rel = prune;
+    }
+    __device__ __forceinline__ void leaf(const DevScene& s, const Ray& r, int p) {
         PrimHit h; float oma; unsigned fl;
         if (prim_test(s, p, r, h, oma, fl)) {
-            // `linter.t <= rinter.t` keeps the left (smaller rank) candidate on ties; a candidate
-            // with t == FLT_MAX can never displace the default miss on the left
             if (h.t < best.t || (h.t == best.t && p < best.prim)) {
                 best.t = h.t; best.prim = p; best.u = h.u; best.v = h.v;
                 if (prune_rel >= 0.f) limit = fabsf(h.t) * prune_rel + prune_rel + h.t;
             }
         }
-    };
-    float te;
-    {
-        float4 lo = ldg4(s.nodes + 2 * root), hi = ldg4(s.nodes + 2 * root + 1);
-        if (!slab(lo, hi, r, te)) return best;
+    }
+    // returns true when a traversal starting at pair `cur` is needed
+    __device__ __forceinline__ bool begin(const DevScene& s, const float4* nodes, int root, const Ray& r, int& cur) {
+        float te;
+        float4 lo = ldg4(nodes + 2 * root), hi = ldg4(nodes + 2 * root + 1);
+        if (!slab(lo, hi, r, te)) return false;
         int link = __float_as_int(lo.w);
-        if (link < 0) { leaf(~link); return best; }
-        root = link;
+        if (link < 0) { leaf(s, r, ~link); return false; }
+        cur = link;
+        return true;
     }
+};
+
+// Whole closest-hit query in one call (batch kernels, literal hasIntersection path).
+__device__ __forceinline__ Closest closest_hit(const DevScene& s, const float4* nodes, int root, const Ray& r, Stack& st,
+                                               float prune_rel) {
+    ClosestState cs;
+    cs.reset(prune_rel);
+    int cur = 0;
     st.sp = 0;
-    int cur = root;           // index of the left record of a sibling pair
-    while (true) {
-        const float4* n = s.nodes + 2 * cur;
-        float4 l0 = ldg4(n), l1 = ldg4(n + 1), r0 = ldg4(n + 2), r1 = ldg4(n + 3);
-        float tl, tr;
-        bool hl = slab(l0, l1, r, tl), hr = slab(r0, r1, r, tr);
-        hl = hl && !(tl > limit);
-        hr = hr && !(tr > limit);
-        int linkL = __float_as_int(l0.w), linkR = __float_as_int(r0.w);
-        if (hl && linkL < 0) { leaf(~linkL); hl = false; }
-        if (hr && linkR < 0) { hr = hr && !(tr > limit); if (hr) leaf(~linkR); hr = false; }
-        if (hl && hr) {
-            bool right_first = tr < tl;
-            st.push(right_first ? linkL : linkR);
-            cur = right_first ? linkR : linkL;
-        } else if (hl) cur = linkL;
-        else if (hr) cur = linkR;
-        else {
-            if (st.empty()) break;
-            cur = st.pop();
-        }
+    if (cs.begin(s, nodes, root, r, cur)) {
+        while (traverse_step<true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); })) {}
     }
-    return best;
+    return cs.best;
 }
 
-// BVHStrategy::ShadowHelper, BVHStrategy.hpp:24-48: product of (1-alpha) over every
-// leaf reached through hit boxes whose primitive is hit with t < dis and is not a
-// light avatar.  Leaves are visited left to right; the walk stops once the
-// product is exactly 0 (0 * x == 0 for the finite factors that follow).
-__device__ __forceinline__ float shadow_product(const DevScene& s, const Ray& r, float dis, Stack& st) {
+// Tree and pruning a ray uses: the SAH tree with pruning, unless the caller asked for the
+// reference's literal exhaustive walk or the ray is axis-degenerate.
+__device__ __forceinline__ const float4* pick_tree(const DevScene& s, f3 dir, float& prune_rel) {
+    if (prune_rel < 0.f || degenerate_dir(dir)) { prune_rel = -1.f; return s.nodes; }
+    return s.fnodes;
+}
+
+// ---- hard shadow: BVHStrategy::ShadowHelper, BVHStrategy.hpp:24-48 ----
+// Product of (1-alpha) over every tested primitive hit with t < dis that is not a light
+// avatar; the walk stops once the product is exactly 0 (0 * x == 0 for finite x).
+__device__ __forceinline__ void shadow_leaf(const DevScene& s, const Ray& r, float dis, int p, float& res) {
+    PrimHit h; float oma; unsigned fl;
+    if (prim_test(s, p, r, h, oma, fl) && h.t < dis && !(fl & WRT_PRIM_LIGHT)) res = res * oma;
+}
+
+__device__ __forceinline__ float shadow_product(const DevScene& s, const float4* nodes, const Ray& r, float dis, Stack& st) {
     float res = 1.f;
     if (s.n_nodes == 0) return res;
-    auto leaf = [&](int p) {
-        PrimHit h; float oma; unsigned fl;
-        if (prim_test(s, p, r, h, oma, fl) && h.t < dis && !(fl & WRT_PRIM_LIGHT)) res = res * oma;
-    };
     float te;
-    int cur;
-    {
-        float4 lo = ldg4(s.nodes), hi = ldg4(s.nodes + 1);
-        if (!slab(lo, hi, r, te)) return res;
-        int link = __float_as_int(lo.w);
-        if (link < 0) { leaf(~link); return res; }
-        cur = link;
-    }
+    float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
+    if (!slab(lo, hi, r, te)) return res;
+    int cur = __float_as_int(lo.w);
+    if (cur < 0) { shadow_leaf(s, r, dis, ~cur, res); return res; }
     st.sp = 0;
-    while (true) {
-        const float4* n = s.nodes + 2 * cur;
-        float4 l0 = ldg4(n), l1 = ldg4(n + 1), r0 = ldg4(n + 2), r1 = ldg4(n + 3);
-        float tl, tr;
-        bool hl = slab(l0, l1, r, tl), hr = slab(r0, r1, r, tr);
-        int linkL = __float_as_int(l0.w), linkR = __float_as_int(r0.w);
-        if (hl && linkL < 0) { leaf(~linkL); hl = false; }
-        if (hr && linkR < 0) { leaf(~linkR); hr = false; }
-        if (res == 0.f) break;
-        if (hl && hr) { st.push(linkR); cur = linkL; }
-        else if (hl) cur = linkL;
-        else if (hr) cur = linkR;
-        else {
-            if (st.empty()) break;
-            cur = st.pop();
-        }
-    }
+    const float never = INFINITY;
+    while (res != 0.f && traverse_step<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); })) {}
     return res;
 }
 
-// hasIntersection, BVH.hpp:162-186.  No root-box test.  The reference takes the
-// CLOSEST hit of each root child and calls the ray occluded when that hit has
-// t < dis and is not a light avatar.  Without light-avatar primitives this is
-// "any primitive hit with t < dis" (the closest hit is < dis iff some hit is),
-// which allows an early-out any-hit walk; with light avatars the two per-child
-// closest-hit queries are done literally.
-__device__ __forceinline__ bool occluded(const DevScene& s, const Ray& r, float dis, Stack& st, float prune_rel) {
-    if (s.n_nodes == 0) return false;
+// ---- soft-shadow visibility: hasIntersection, BVH.hpp:162-186 ----
+// No root-box test.  The reference takes the CLOSEST hit of each root child and calls the
+// ray occluded when that hit has t < dis and is not a light avatar.  Without light-avatar
+// primitives this is "some tested primitive is hit with t < dis" (the closest hit is < dis
+// iff some hit is), an early-out any-hit walk; with light avatars the two per-child
+// closest-hit queries are done literally on the reference tree.
+__device__ __noinline__ bool occluded_literal(const DevScene& s, const Ray r, float dis, Stack st) {
     int root_link = __float_as_int(ldg4(s.nodes).w);
+    for (int k = 0; k < 2; k++) {
+        Closest a = closest_hit(s, s.nodes, root_link + k, r, st, -1.f);
+        if (a.prim >= 0 && a.t < dis && !(__float_as_uint(ldg4(s.geom + 3 * (size_t)a.prim + 2).w) & WRT_PRIM_LIGHT))
+            return true;
+    }
+    return false;
+}
+
+// returns true when an any-hit walk from pair `cur` is needed; otherwise `occ` is final
+__device__ __forceinline__ bool occluded_begin(const DevScene& s, const float4* nodes, const Ray& r, float dis, Stack& st,
+                                               int& cur, bool& occ) {
+    occ = false;
+    if (s.n_nodes == 0) return false;
+    int root_link = __float_as_int(ldg4(nodes).w);
     if (root_link < 0) {
         PrimHit h; float oma; unsigned fl;
         // (the reference dereferences a null obj here when the lone primitive is missed)
-        if (!prim_test(s, ~root_link, r, h, oma, fl)) return false;
-        if (fl & WRT_PRIM_LIGHT) return false;
-        return h.t < dis;
-    }
-    if (s.has_light_prims) {
-        Closest a = closest_hit(s, root_link, r, st, prune_rel);
-        if (a.prim >= 0 && a.t < dis && !(__float_as_uint(ldg4(s.geom + 3 * (size_t)a.prim + 2).w) & WRT_PRIM_LIGHT))
-            return true;
-        Closest b = closest_hit(s, root_link + 1, r, st, prune_rel);
-        if (b.prim >= 0 && b.t < dis && !(__float_as_uint(ldg4(s.geom + 3 * (size_t)b.prim + 2).w) & WRT_PRIM_LIGHT))
-            return true;
+        if (prim_test(s, ~root_link, r, h, oma, fl) && !(fl & WRT_PRIM_LIGHT)) occ = h.t < dis;
         return false;
     }
-    bool occ = false;
-    auto leaf = [&](int p) {
-        PrimHit h; float oma; unsigned fl;
-        if (prim_test(s, p, r, h, oma, fl) && h.t < dis) occ = true;
-    };
+    if (s.has_light_prims) { occ = occluded_literal(s, r, dis, st); return false; }
+    cur = root_link;
+    return true;
+}
+
+__device__ __forceinline__ void occluded_leaf(const DevScene& s, const Ray& r, float dis, int p, bool& occ) {
+    PrimHit h; float oma; unsigned fl;
+    if (prim_test(s, p, r, h, oma, fl) && h.t < dis) occ = true;
+}
+
+__device__ __forceinline__ bool occluded(const DevScene& s, const float4* nodes, const Ray& r, float dis, Stack& st) {
+    bool occ;
+    int cur = 0;
     st.sp = 0;
-    int cur = root_link;
-    while (true) {
-        const float4* n = s.nodes + 2 * cur;
-        float4 l0 = ldg4(n), l1 = ldg4(n + 1), r0 = ldg4(n + 2), r1 = ldg4(n + 3);
-        float tl, tr;
-        bool hl = slab(l0, l1, r, tl), hr = slab(r0, r1, r, tr);
-        int linkL = __float_as_int(l0.w), linkR = __float_as_int(r0.w);
-        if (hl && linkL < 0) { leaf(~linkL); hl = false; }
-        if (hr && linkR < 0) { leaf(~linkR); hr = false; }
-        if (occ) break;
-        if (hl && hr) {
-            bool right_first = tr < tl;
-            st.push(right_first ? linkL : linkR);
-            cur = right_first ? linkR : linkL;
-        } else if (hl) cur = linkL;
-        else if (hr) cur = linkR;
-        else {
-            if (st.empty()) break;
-            cur = st.pop();
-        }
+    if (occluded_begin(s, nodes, r, dis, st, cur, occ)) {
+        const float never = INFINITY;
+        while (!occ && traverse_step<true>(nodes, r, st, cur, never, [&](int p) { occluded_leaf(s, r, dis, p, occ); })) {}
     }
     return occ;
 }
@@ -305,6 +316,54 @@ __device__ __forceinline__ float directional_product(const DevScene& s, const Ra
         if (res == 0.f) break;
     }
     return res;
+}
+
+// ---- persistent warps with per-lane refill ----
+// A warp keeps pulling work items from a global counter; a lane that finishes its ray
+// goes idle, and once `refill` lanes are idle the warp fetches that many new items in one
+// atomic.  Deep ray-tree levels hold rays of wildly different traversal lengths (a
+// reflection that escapes to the background next to a refraction bouncing inside the
+// bunny); refilling keeps the SIMD lanes occupied where fixed 32-ray batches do not.
+// Q provides: bool begin(item, cur, st)  — load + start; false = resolved without a walk
+//             bool step(cur, st)         — one traversal step; false = finished
+//             void end()                 — write the result
+template <class Q>
+__device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned long long* work, Stack& st, int refill) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool active = false, drained = false;
+    int cur = 0;
+    while (true) {
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (!drained && (idle == 0xffffffffu || __popc(idle) >= refill)) {
+            unsigned cnt = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!active) {
+                unsigned long long item = base + __popc(idle & lt_mask);
+                if (item < n) {
+                    st.sp = 0;
+                    active = q.begin(item, cur, st);
+                    if (!active) q.end();
+                }
+            }
+            if (base + cnt >= n) drained = true;
+            if (!__any_sync(0xffffffffu, active)) {
+                if (drained) break;
+                continue;
+            }
+        } else if (idle == 0xffffffffu) {
+            break;                                   // drained and nothing in flight
+        }
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            if (active) {
+                active = q.step(cur, st);
+                if (!active) q.end();
+            }
+        }
+    }
 }
 
 } // namespace wrt

@@ -106,34 +106,48 @@ __global__ void k_raygen(WrtCamera cam, TileMap tm, long long slot0, unsigned n,
     if (blockIdx.x == 0 && threadIdx.x == 0) fb.counters[C_NRAYS + 0] = n;
 }
 
-// ---- K2: closest hit, persistent warps pulling 32 rays at a time ----
-__global__ void __launch_bounds__(128) k_trace_closest(DevScene s, FrameBuffers fb, int level, int work_slot,
-                                                       float prune_rel) {
+// ---- K2: closest hit; persistent warps, per-lane refill (dev_traverse.cuh run_queue) ----
+struct ClosestQuery {
+    const DevScene& s;
+    const FrameBuffers& fb;
+    const float4* ray_o;
+    const float4* ray_d;
+    float prune_cfg;
+    // per-lane state
+    Ray r;
+    ClosestState cs;
+    const float4* nodes;
+    unsigned idx;
+    __device__ __forceinline__ ClosestQuery(const DevScene& s_, const FrameBuffers& fb_, int level, float prune)
+        : s(s_), fb(fb_), ray_o(fb_.ray_o[level & 1]), ray_d(fb_.ray_d[level & 1]), prune_cfg(prune) {}
+    __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
+        idx = (unsigned)item;
+        float4 o = ray_o[idx], d = ray_d[idx];
+        cs.reset(prune_cfg);
+        if (__float_as_uint(o.w) == 0xffffffffu) { cs.best.prim = -2; return false; }       // dead slot
+        if (s.n_nodes == 0) return false;
+        r = make_ray(mk3(o), mk3(d));
+        float prune = prune_cfg;
+        nodes = pick_tree(s, r.d, prune);
+        cs.prune_rel = prune;
+        return cs.begin(s, nodes, 0, r, cur);
+    }
+    __device__ __forceinline__ bool step(int& cur, Stack& st) {
+        return traverse_step<true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
+    }
+    __device__ __forceinline__ void end() {
+        fb.hit[idx] = make_float4(cs.best.t, __int_as_float(cs.best.prim), cs.best.u, cs.best.v);
+    }
+};
+
+__global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
+                                                       float prune_rel, int refill) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
-    const float4* ray_o = fb.ray_o[level & 1];
-    const float4* ray_d = fb.ray_d[level & 1];
-    unsigned lane = threadIdx.x & 31;
-    while (true) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(fb.counters + work_slot, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned i = base + lane;
-        if (i < n) {
-            float4 o = ray_o[i], d = ray_d[i];
-            float4 out = make_float4(FLT_MAX, __int_as_float(-1), 0.f, 0.f);
-            if (__float_as_uint(o.w) == 0xffffffffu) out.y = __int_as_float(-2);       // dead slot
-            else if (s.n_nodes > 0) {
-                Ray r = make_ray(mk3(o), mk3(d));
-                Closest c = closest_hit(s, 0, r, st, prune_rel);
-                out = make_float4(c.t, __int_as_float(c.prim), c.u, c.v);
-            }
-            fb.hit[i] = out;
-        }
-    }
+    ClosestQuery q(s, fb, level, prune_rel);
+    run_queue(q, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
 }
 
 // ---- K3: hit -> surface, shadow requests, child rays (Renderer.hpp:170-257) ----
@@ -252,85 +266,105 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
 }
 
 // ---- K4a: hard shadows, BVHStrategy::getShadowCoeffi ----
-__global__ void __launch_bounds__(128) k_shadow_hard(DevScene s, FrameBuffers fb, int level, int work_slot) {
+struct HardShadowQuery {
+    const DevScene& s;
+    const FrameBuffers& fb;
+    Ray r;
+    const float4* nodes;
+    float dis, res;
+    unsigned out;
+    __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_) : s(s_), fb(fb_) {}
+    __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
+        float4 o4 = fb.preq_o[item];
+        uint4 k = fb.preq_k[item];
+        const WrtLight* L = s.lights + k.x;
+        f3 orig = mk3(o4);
+        f3 lightPos = mk3(L->pos[0], L->pos[1], L->pos[2]);
+        f3 raydir = normalized(lightPos - orig);
+        dis = norm(lightPos - orig);
+        r = make_ray(orig, raydir);
+        out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
+        res = 1.f;
+        if (s.n_nodes == 0) return false;
+        nodes = degenerate_dir(raydir) ? s.nodes : s.fnodes;
+        float te;
+        float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
+        if (!slab(lo, hi, r, te)) return false;
+        cur = __float_as_int(lo.w);
+        if (cur < 0) { shadow_leaf(s, r, dis, ~cur, res); return false; }
+        return true;
+    }
+    __device__ __forceinline__ bool step(int& cur, Stack& st) {
+        const float never = INFINITY;
+        bool more = traverse_step<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
+        return more && res != 0.f;
+    }
+    __device__ __forceinline__ void end() { fb.coeff[out] = res; }
+};
+
+__global__ void __launch_bounds__(128) k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned n = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    unsigned lane = threadIdx.x & 31;
-    while (true) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(fb.counters + work_slot, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned i = base + lane;
-        if (i < n) {
-            float4 o4 = fb.preq_o[i];
-            uint4 k = fb.preq_k[i];
-            const WrtLight* L = s.lights + k.x;
-            f3 orig = mk3(o4);
-            f3 lightPos = mk3(L->pos[0], L->pos[1], L->pos[2]);
-            f3 raydir = normalized(lightPos - orig);
-            float distance = norm(lightPos - orig);
-            Ray r = make_ray(orig, raydir);
-            float c = shadow_product(s, r, distance, st);
-            fb.coeff[(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = c;
-        }
-    }
+    HardShadowQuery q(s, fb);
+    run_queue(q, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
 }
 
 // ---- K4b: soft shadows: 50 area-light samples per request (Renderer.hpp:405-414) ----
-// Work item = (request, sample); a warp's 32 consecutive items share one or two
-// shading points, so its rays start at the same origin and stay coherent.
-__global__ void __launch_bounds__(128) k_shadow_soft(DevScene s, FrameBuffers fb, int level, int work_slot,
-                                                     unsigned seed, float prune_rel) {
+// Work item = (request, sample): consecutive items share the shading point, so a warp's
+// rays start at one or two origins and stay coherent.  Each lit sample adds 1.0f to the
+// request's coefficient (float atomics on small integers are exact and order-free).
+struct SoftShadowQuery {
+    const DevScene& s;
+    const FrameBuffers& fb;
+    unsigned seed;
+    Ray r;
+    const float4* nodes;
+    float dis;
+    bool occ;
+    unsigned out;
+    __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_)
+        : s(s_), fb(fb_), seed(seed_) {}
+    __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack& st) {
+        unsigned req = (unsigned)(item / WRT_SOFT_SAMPLES);
+        unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
+        float4 o4 = fb.preq_o[req];
+        uint4 k = fb.preq_k[req];
+        const WrtLight* L = s.lights + k.x;
+        float u, v;
+        wrt_light_sample_uv(seed, k.y, k.z, k.x, sample, &u, &v);
+        // randomSampleTriangle, Triangle.hpp:139-145: (1-u-v)*v0 + u*v1 + v*v2
+        f3 v0 = mk3(L->tri[0], L->tri[1], L->tri[2]), v1 = mk3(L->tri[3], L->tri[4], L->tri[5]),
+           v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
+        f3 lightPos = (1 - u - v) * v0 + u * v1 + v * v2;
+        f3 orig = mk3(o4);
+        f3 raydir = normalized(lightPos - orig);
+        dis = norm(lightPos - orig);
+        r = make_ray(orig, raydir);
+        out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
+        nodes = degenerate_dir(raydir) ? s.nodes : s.fnodes;
+        return occluded_begin(s, nodes, r, dis, st, cur, occ);
+    }
+    __device__ __forceinline__ bool step(int& cur, Stack& st) {
+        const float never = INFINITY;
+        bool more = traverse_step<true>(nodes, r, st, cur, never, [&](int p) { occluded_leaf(s, r, dis, p, occ); });
+        return more && !occ;
+    }
+    __device__ __forceinline__ void end() {
+        if (!occ) atomicAdd(fb.coeff + out, 1.0f);
+    }
+};
+
+__global__ void __launch_bounds__(128) k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
+                                                     unsigned seed, int refill) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    const unsigned long long n = (unsigned long long)nreq * WRT_SOFT_SAMPLES;
-    unsigned lane = threadIdx.x & 31;
-    unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
-    while (true) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(work, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned long long item = base + lane;
-        unsigned req = 0xffffffffu;
-        bool lit = false;
-        if (item < n) {
-            req = (unsigned)(item / WRT_SOFT_SAMPLES);
-            unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
-            float4 o4 = fb.preq_o[req];
-            uint4 k = fb.preq_k[req];
-            const WrtLight* L = s.lights + k.x;
-            float u, v;
-            wrt_light_sample_uv(seed, k.y, k.z, k.x, sample, &u, &v);
-            // randomSampleTriangle, Triangle.hpp:139-145: (1-u-v)*v0 + u*v1 + v*v2
-            f3 v0 = mk3(L->tri[0], L->tri[1], L->tri[2]), v1 = mk3(L->tri[3], L->tri[4], L->tri[5]),
-               v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
-            f3 lightPos = (1 - u - v) * v0 + u * v1 + v * v2;
-            f3 orig = mk3(o4);
-            f3 raydir = normalized(lightPos - orig);
-            float distance = norm(lightPos - orig);
-            Ray r = make_ray(orig, raydir);
-            lit = !occluded(s, r, distance, st, prune_rel);
-        }
-        // a warp spans at most two requests (50 > 32): count the lit samples of each
-        unsigned req0 = __shfl_sync(0xffffffffu, req, 0);
-        unsigned m0 = __ballot_sync(0xffffffffu, lit && req == req0);
-        unsigned m1 = __ballot_sync(0xffffffffu, lit && req != req0 && req != 0xffffffffu);
-        unsigned req1 = __shfl_sync(0xffffffffu, req, 31);
-        if (lane == 0 && m0) {
-            float4 o4 = fb.preq_o[req0];
-            atomicAdd(fb.coeff + (size_t)__float_as_uint(o4.w) * s.n_lights + fb.preq_k[req0].x, (float)__popc(m0));
-        }
-        if (lane == 31 && m1) {
-            float4 o4 = fb.preq_o[req1];
-            atomicAdd(fb.coeff + (size_t)__float_as_uint(o4.w) * s.n_lights + fb.preq_k[req1].x, (float)__popc(m1));
-        }
-    }
+    SoftShadowQuery q(s, fb, seed);
+    run_queue(q, (unsigned long long)nreq * WRT_SOFT_SAMPLES, reinterpret_cast<unsigned long long*>(fb.counters + work_slot),
+              st, refill);
 }
 
 // ---- K4c: directional-light shadows, Renderer.hpp:381-400 ----
@@ -437,7 +471,9 @@ __global__ void __launch_bounds__(128) k_batch_closest(DevScene s, const float* 
         h.texture = -1; h.normalmap = -1; h.material = -1; h.prim = -1;
         if (s.n_nodes > 0) {
             Ray r = make_ray(o, d);
-            Closest c = closest_hit(s, 0, r, st, prune_rel);
+            float prune = prune_rel;
+            const float4* nodes = pick_tree(s, d, prune);
+            Closest c = closest_hit(s, nodes, 0, r, st, prune);
             if (c.prim >= 0) {
                 Surface sf = complete_hit(s, o, d, c.t, c.prim, c.u, c.v);
                 h.hit = 1; h.prim = c.prim; h.object = __ldg(s.ids + c.prim).w; h.t = c.t;
@@ -465,8 +501,9 @@ __global__ void __launch_bounds__(128) k_batch_shadow(DevScene s, const float* p
         f3 raydir = normalized(lightPos - orig);
         float distance = norm(lightPos - orig);
         Ray r = make_ray(orig, raydir);
-        if (mode == 0) out[i] = shadow_product(s, r, distance, st);
-        else out[i] = occluded(s, r, distance, st, prune_rel) ? 0.f : 1.f;
+        const float4* nodes = (prune_rel < 0.f || degenerate_dir(raydir)) ? s.nodes : s.fnodes;
+        if (mode == 0) out[i] = shadow_product(s, nodes, r, distance, st);
+        else out[i] = occluded(s, nodes, r, distance, st) ? 0.f : 1.f;
     }
 }
 

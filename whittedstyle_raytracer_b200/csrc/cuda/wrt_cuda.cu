@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../../include/wrt_cuda.h"
+#include "fast_bvh.hpp"
 #include "kernels.cuh"
 
 namespace {
@@ -60,6 +61,9 @@ struct WrtContext {
     float queue_factor = 2.0f;
     float prune_rel = 1e-3f;
     bool kernel_timing = false;
+    int refill = 8;                    // idle lanes that trigger a refill on deep ray-tree levels
+    int refill_soft = 16;
+    int trace_blocks_per_sm = 10;
 
     // frame buffers
     wrt::FrameBuffers fb{};
@@ -245,7 +249,7 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
     c->work_seq = 0;
     auto work_slot = [&]() { int s = C_WORK + 2 * c->work_seq; ++c->work_seq; return s; };
     const int TB = 128;
-    const int trace_grid = grid_for(c, 8), wide_grid = grid_for(c, 8);
+    const int trace_grid = grid_for(c, c->trace_blocks_per_sm), wide_grid = grid_for(c, 8);
     const size_t sb = stack_bytes(c, TB);
     const float prune = prune_value(c);
     {
@@ -255,7 +259,7 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
         {
             LaunchScope ls(c, st, F_TRACE);
-            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune);
+            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, d == 0 ? 32 : c->refill);
         }
         {
             LaunchScope ls(c, st, F_SURFACE);
@@ -264,10 +268,10 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         if (ds.n_point_lights > 0) {
             if (ds.shadow_type == 0) {
                 LaunchScope ls(c, st, F_SHADOW_HARD);
-                k_shadow_hard<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot());
+                k_shadow_hard<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), d == 0 ? 32 : c->refill);
             } else {
                 LaunchScope ls(c, st, F_SHADOW_SOFT);
-                k_shadow_soft<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), c->seed, prune);
+                k_shadow_soft<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft);
             }
         }
         if (ds.n_dir_lights > 0) {
@@ -467,6 +471,11 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     // nodes: identical 32-byte records, viewed as float4 pairs on the device
     static_assert(sizeof(WrtNode) == 32, "WrtNode must be 32 bytes");
     if (dev_upload(c, (const float4*)s->nodes, 2 * (size_t)s->n_nodes, &ds.nodes)) return 1;
+    // SAH tree over the same leaf boxes (fast_bvh.hpp explains why results are identical)
+    wrt::FastBvhBuilder fbvh;
+    fbvh.build(s);
+    if (fbvh.nodes.size() != (size_t)s->n_nodes) return fail("wrt_upload_scene: fast BVH build failed");
+    if (dev_upload(c, (const float4*)fbvh.nodes.data(), 2 * fbvh.nodes.size(), &ds.fnodes)) return 1;
     std::vector<float4> geom(3 * (size_t)np), attr(4 * (size_t)np);
     std::vector<int4> ids(np);
     int has_light = 0;
@@ -519,7 +528,8 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     ds.eta = s->eta;
     ds.amin = s->amin; ds.amax = s->amax; ds.distmin = s->distmin; ds.distmax = s->distmax;
     c->bvh_depth = tree_depth(s);
-    c->stack_rows = c->bvh_depth + 2;
+    c->stack_rows = std::max(c->bvh_depth, fbvh.max_depth) + 2;
+    if (c->stack_rows > 96) return fail("wrt_upload_scene: acceleration tree deeper than 94 levels");
     c->has_scene = true;
     return 0;
 }

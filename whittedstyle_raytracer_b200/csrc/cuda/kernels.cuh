@@ -19,13 +19,14 @@
 namespace wrt {
 
 enum CounterSlot {
-    C_NRAYS = 0,                 // [WRT_MAX_DEPTH + 1] rays per level (level 9 is never traced)
+    C_NRAYS = 0,                 // [WRT_MAX_DEPTH + 1] level 0: primary rays; level d >= 1: reflection rays
+    C_NTRAYS = 112,              // [WRT_MAX_DEPTH + 1] level d >= 1: transmission rays (second half of the level's arrays)
     C_NPREQ = 16,                // [9] point-light shadow requests per level
     C_NDREQ = 32,                // [9] directional-light shadow requests per level
     C_VALID0 = 48,               // valid (non-padding) primary rays
     C_OVERFLOW = 49,             // set when a queue append was dropped
     C_WORK = 64,                 // work-distribution counters, one per persistent launch
-    C_TOTAL = 192
+    C_TOTAL = 256
 };
 
 struct TileMap : WrtTileMap {     // include/wrt_tiles.h
@@ -67,6 +68,28 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned* counter, int k, unsigne
     unsigned mine = base + (unsigned)(incl - k);
     if (k > 0 && mine + (unsigned)k > cap) { *overflow = 1u; return 0xffffffffu; }
     return mine;
+}
+
+// Rays of a ray-tree level.  Level 0 is one segment [0, n).  Deeper levels keep reflection
+// rays in the first half of the level's arrays and transmission rays in the second half:
+// a warp then traces rays of one kind from neighbouring pixels, which stay on similar
+// paths much longer than an interleaved reflect/refract mix does.
+struct LevelSpan {
+    unsigned nR, nT, half;
+    __device__ __forceinline__ unsigned count() const { return nR + nT; }
+    __device__ __forceinline__ unsigned slot(unsigned item) const { return item < nR ? item : half + (item - nR); }
+};
+__device__ __forceinline__ LevelSpan level_span(const unsigned* counters, int level, unsigned cap) {
+    LevelSpan sp;
+    if (level == 0) {
+        sp.half = cap; sp.nT = 0;
+        sp.nR = counters[C_NRAYS] < cap ? counters[C_NRAYS] : cap;
+    } else {
+        sp.half = cap / 2;
+        sp.nR = counters[C_NRAYS + level] < sp.half ? counters[C_NRAYS + level] : sp.half;
+        sp.nT = counters[C_NTRAYS + level] < cap - sp.half ? counters[C_NTRAYS + level] : cap - sp.half;
+    }
+    return sp;
 }
 
 __device__ __forceinline__ unsigned queue_len(const unsigned* counters, int slot, unsigned cap) {
@@ -118,10 +141,12 @@ struct ClosestQuery {
     ClosestState cs;
     const float4* nodes;
     unsigned idx;
+    LevelSpan span;
     __device__ __forceinline__ ClosestQuery(const DevScene& s_, const FrameBuffers& fb_, int level, float prune)
-        : s(s_), fb(fb_), ray_o(fb_.ray_o[level & 1]), ray_d(fb_.ray_d[level & 1]), prune_cfg(prune) {}
+        : s(s_), fb(fb_), ray_o(fb_.ray_o[level & 1]), ray_d(fb_.ray_d[level & 1]), prune_cfg(prune),
+          span(level_span(fb_.counters, level, fb_.cap)) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
-        idx = (unsigned)item;
+        idx = span.slot((unsigned)item);
         float4 o = ray_o[idx], d = ray_d[idx];
         cs.reset(prune_cfg);
         if (__float_as_uint(o.w) == 0xffffffffu) { cs.best.prim = -2; return false; }       // dead slot
@@ -145,23 +170,26 @@ __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ D
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
-    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
     ClosestQuery q(s, fb, level, prune_rel);
+    const unsigned n = q.span.count();
     run_queue(q, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
 }
 
 // ---- K3: hit -> surface, shadow requests, child rays (Renderer.hpp:170-257) ----
 __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers fb, int level) {
-    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
+    const LevelSpan span = level_span(fb.counters, level, fb.cap);
+    const unsigned n = span.count();
+    const unsigned child_half = fb.cap / 2;
     const float4* ray_o = fb.ray_o[level & 1];
     const float4* ray_d = fb.ray_d[level & 1];
     float4* nray_o = fb.ray_o[(level + 1) & 1];
     float4* nray_d = fb.ray_d[(level + 1) & 1];
     unsigned* overflow = fb.counters + C_OVERFLOW;
     const unsigned n_round = (n + 31u) & ~31u;         // whole warps stay converged for the aggregated appends
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += gridDim.x * blockDim.x) {
+        const unsigned i = span.slot(item < n ? item : 0);       // slot in this level's arrays
+        const bool live = item < n;
         bool shade = false;
-        int n_children = 0;
         bool spawnT = false, spawnR = false;
         float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 nb = make_float4(0.f, __int_as_float(-1), __int_as_float(-1), 0.f);
@@ -169,7 +197,7 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
         f3 refractDir = org, reflectDir = org, refRayOrig = org, traRayOrig = org;
         unsigned pixel = 0, path = 0;
         int prim = -1;
-        if (i < n) {
+        if (live) {
             float4 o4 = ray_o[i], d4 = ray_d[i], h = fb.hit[i];
             org = mk3(o4); dir = mk3(d4);
             pixel = __float_as_uint(o4.w); path = __float_as_uint(d4.w);
@@ -213,29 +241,26 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
                     spawnT = !float_equal(1.f, m.alpha) && !float_equal(fr, 1.f);
                     spawnR = m.ks != 0;
                     if (level + 1 >= WRT_MAX_DEPTH) { spawnT = false; spawnR = false; }    // traceRay depth cut, :152
-                    n_children = (spawnT ? 1 : 0) + (spawnR ? 1 : 0);
                     na.w = fr;
                     nb.x = (1 - fr) * (1 - m.alpha);
                     nb.w = 1.f;                                                    // composite node
                 }
             }
         }
-        if (i < n && !shade) fb.surf[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        // child rays
-        unsigned cslot = warp_alloc(fb.counters + C_NRAYS + level + 1, n_children, fb.cap, overflow);
-        if (n_children > 0 && cslot != 0xffffffffu) {
-            unsigned c = cslot;
-            if (spawnR) {
-                nray_o[c] = make_float4(refRayOrig.x, refRayOrig.y, refRayOrig.z, __uint_as_float(pixel));
-                nray_d[c] = make_float4(reflectDir.x, reflectDir.y, reflectDir.z, __uint_as_float(path * 2u));
-                nb.y = __int_as_float((int)c);
-                ++c;
-            }
-            if (spawnT) {
-                nray_o[c] = make_float4(traRayOrig.x, traRayOrig.y, traRayOrig.z, __uint_as_float(pixel));
-                nray_d[c] = make_float4(refractDir.x, refractDir.y, refractDir.z, __uint_as_float(path * 2u + 1u));
-                nb.z = __int_as_float((int)c);
-            }
+        if (live && !shade) fb.surf[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        // child rays: reflections into the first half of the next level, transmissions into the second
+        unsigned rslot = warp_alloc(fb.counters + C_NRAYS + level + 1, spawnR ? 1 : 0, child_half, overflow);
+        unsigned tslot = warp_alloc(fb.counters + C_NTRAYS + level + 1, spawnT ? 1 : 0, fb.cap - child_half, overflow);
+        if (spawnR && rslot != 0xffffffffu) {
+            nray_o[rslot] = make_float4(refRayOrig.x, refRayOrig.y, refRayOrig.z, __uint_as_float(pixel));
+            nray_d[rslot] = make_float4(reflectDir.x, reflectDir.y, reflectDir.z, __uint_as_float(path * 2u));
+            nb.y = __int_as_float((int)rslot);
+        }
+        if (spawnT && tslot != 0xffffffffu) {
+            unsigned c = child_half + tslot;
+            nray_o[c] = make_float4(traRayOrig.x, traRayOrig.y, traRayOrig.z, __uint_as_float(pixel));
+            nray_d[c] = make_float4(refractDir.x, refractDir.y, refractDir.z, __uint_as_float(path * 2u + 1u));
+            nb.z = __int_as_float((int)c);
         }
         // shadow requests: one per (shaded hit, light)
         unsigned pslot = warp_alloc(fb.counters + C_NPREQ + level, shade ? s.n_point_lights : 0, fb.preq_cap, overflow);
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
                 }
             }
         }
-        if (i < n) {
+        if (live) {
             fb.node_a[level][i] = na;
             fb.node_b[level][i] = nb;
         }
@@ -383,9 +408,11 @@ __global__ void __launch_bounds__(128) k_shadow_directional(DevScene s, FrameBuf
 // ---- K5: local shading, Renderer::blinnPhongShader ----
 #define WRT_MAX_LIGHTS_FAST 8
 __global__ void __launch_bounds__(256) k_shade(DevScene s, FrameBuffers fb, int level) {
-    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
+    const LevelSpan span = level_span(fb.counters, level, fb.cap);
+    const unsigned n = span.count();
     const float4* ray_o = fb.ray_o[level & 1];
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
+        const unsigned i = span.slot(item);
         const float4* sv = fb.surf + 3 * (size_t)i;
         float4 s0 = sv[0];
         if (__float_as_int(s0.w) < 0) continue;
@@ -401,8 +428,10 @@ __global__ void __launch_bounds__(256) k_shade(DevScene s, FrameBuffers fb, int 
 
 // ---- K6: bottom-up combine, Renderer.hpp:259 ----
 __global__ void __launch_bounds__(256) k_combine(FrameBuffers fb, int level) {
-    const unsigned n = queue_len(fb.counters, C_NRAYS + level, fb.cap);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const LevelSpan span = level_span(fb.counters, level, fb.cap);
+    const unsigned n = span.count();
+    for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
+        const unsigned i = span.slot(item);
         float4 nb = fb.node_b[level][i];
         if (nb.w == 0.f) continue;                       // miss / light avatar: returned as is
         float4 na = fb.node_a[level][i];

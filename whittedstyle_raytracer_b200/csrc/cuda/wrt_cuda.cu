@@ -3,6 +3,7 @@
 // with -fmad=false (see dev_math.cuh).  No CPU fallback exists in this library.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,8 +62,10 @@ struct WrtContext {
     float queue_factor = 2.0f;
     float prune_rel = 1e-3f;
     bool kernel_timing = false;
-    int refill = 8;                    // idle lanes that trigger a refill on deep ray-tree levels
-    int refill_soft = 16;
+    int refill = 16;                   // idle lanes that trigger a refill on deep ray-tree levels
+    int refill_soft = 24;
+    int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
+    int smem_rows_cap = 64;
     int trace_blocks_per_sm = 10;
 
     // frame buffers
@@ -259,7 +262,7 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
         {
             LaunchScope ls(c, st, F_TRACE);
-            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, d == 0 ? 32 : c->refill);
+            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, d == 0 ? c->refill0 : c->refill);
         }
         {
             LaunchScope ls(c, st, F_SURFACE);
@@ -268,7 +271,7 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         if (ds.n_point_lights > 0) {
             if (ds.shadow_type == 0) {
                 LaunchScope ls(c, st, F_SHADOW_HARD);
-                k_shadow_hard<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), d == 0 ? 32 : c->refill);
+                k_shadow_hard<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), d == 0 ? c->refill0 : c->refill);
             } else {
                 LaunchScope ls(c, st, F_SHADOW_SOFT);
                 k_shadow_soft<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft);
@@ -301,8 +304,8 @@ void add_batch_stats(WrtContext* c, const unsigned* cnt) {
     s.rays_per_depth[0] += cnt[wrt::C_VALID0];
     s.closest_rays += cnt[wrt::C_VALID0];
     for (int d = 1; d < WRT_MAX_DEPTH; d++) {
-        s.rays_per_depth[d] += cnt[wrt::C_NRAYS + d];
-        s.closest_rays += cnt[wrt::C_NRAYS + d];
+        s.rays_per_depth[d] += cnt[wrt::C_NRAYS + d] + cnt[wrt::C_NTRAYS + d];
+        s.closest_rays += cnt[wrt::C_NRAYS + d] + cnt[wrt::C_NTRAYS + d];
     }
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
         int64_t p = cnt[wrt::C_NPREQ + d], q = cnt[wrt::C_NDREQ + d];
@@ -439,6 +442,12 @@ int wrt_create(int device, WrtContext** out) {
         return fail("wrt_create: stream/event/pinned allocation failed");
     }
     memset(c->h_counters, 0, wrt::C_TOTAL * sizeof(unsigned));
+    // tuning overrides (development only; defaults are what bench.py measures)
+    if (const char* e = getenv("WRT_REFILL")) c->refill = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("WRT_REFILL_SOFT")) c->refill_soft = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("WRT_TRACE_BLOCKS")) c->trace_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));
     *out = c;
     return 0;
 }

@@ -188,7 +188,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -373,7 +373,7 @@ def run_cuda_arm(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     barrier()
     dr.close()
     if world > 1:
@@ -393,7 +393,21 @@ def profile_traffic(family):
     return None
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1
+    (NCCL's version banner, the reference's progress text) was rerouted to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

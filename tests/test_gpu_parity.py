@@ -268,6 +268,25 @@ def test_drop_in_executable(workdir):
     assert p.returncode == 255 and "ERROR: extraneous string in the input file" in p.stdout
 
 
+def test_reference_renderer_with_cuda_strategy(workdir):
+    """INTEGRATION.md level A: the reference's UNMODIFIED main.cpp / Renderer with
+    integration/CudaStrategy.hpp plugged in at IIntersectStrategy (built in the container by
+    `make -C oracle ref_cuda`) — every UpdateInter / getShadowCoeffi call of the reference's own
+    recursion runs on the GPU.  Its PPM must equal the stock reference executable's."""
+    strat, stock = ob.REF_EXE.parent / "whitted_ref_cuda_strategy", ob.REF_EXE
+    if not (strat.exists() and stock.exists()):
+        pytest.skip("oracle/_ref executables not built (needs /root/reference at build time)")
+    fixtures.write_config(workdir, "plug", fixtures.bunny_shadow_config(64, 48))
+    out = {}
+    for name, exe in (("stock", stock), ("cuda", strat)):
+        p = subprocess.run([str(exe), "plug.txt"], cwd=workdir, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        out[name] = read_ppm_p3(workdir / "plug.ppm")
+        (workdir / "plug.ppm").unlink()
+    d = image_diff(out["cuda"], out["stock"])
+    assert d["exact"] >= 0.999 * d["n"] and d["within1"] == d["n"], d
+
+
 # ---------------- BASELINE.json full sizes: size-independent properties ----------------
 
 FULL = [("bunny_shadow_4k", 17959375, 15256192), ("gla_bunny_tex_4k", 17959375, 14487729)]

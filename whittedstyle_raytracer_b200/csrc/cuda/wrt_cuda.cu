@@ -50,6 +50,7 @@ struct WrtContext {
     wrt::DevScene ds{};
     std::vector<void*> scene_allocs;
     bool has_scene = false;
+    bool textures_complete = true;
     int bvh_depth = 0;
     int stack_rows = 2;
 
@@ -319,6 +320,7 @@ int render_all(WrtContext* c, cudaStream_t st, uint8_t* d_image, uint8_t* d_pack
     if (!c->has_scene) return fail("wrt_render: no scene uploaded");
     if (!c->has_cam) return fail("wrt_render: no camera set");
     if (c->cam.width <= 0 || c->cam.height <= 0) return fail("wrt_render: empty image");
+    if (!c->textures_complete) return fail("wrt_render: a primitive references a texture / normal map that was not uploaded");
     const long long total = c->local_slots(c->rank, c->world);
     const long long max_batch = 1ll << 24;
     memset(&c->stats, 0, sizeof c->stats);
@@ -476,6 +478,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     free_scene(c);
     wrt::DevScene& ds = c->ds;
     memset(&ds, 0, sizeof ds);
+    c->textures_complete = true;
     const int np = s->n_prims;
     // nodes: identical 32-byte records, viewed as float4 pairs on the device
     static_assert(sizeof(WrtNode) == 32, "WrtNode must be 32 bytes");
@@ -506,8 +509,8 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         attr[4 * (size_t)p + 2] = make_float4(nn[6], nn[7], nn[8], uv[2]);
         attr[4 * (size_t)p + 3] = make_float4(uv[3], uv[4], uv[5], 0.f);
         ids[p] = make_int4(s->prim_material[p], s->prim_texture[p], s->prim_normalmap[p], s->prim_object[p]);
-        if (s->prim_texture[p] >= s->n_textures || s->prim_normalmap[p] >= s->n_normalmaps)
-            return fail("wrt_upload_scene: texture index out of range");
+        // the strategy queries never read texels; a frame render needs every referenced map present
+        if (s->prim_texture[p] >= s->n_textures || s->prim_normalmap[p] >= s->n_normalmaps) c->textures_complete = false;
     }
     std::vector<float4> mats(3 * (size_t)s->n_materials);
     for (int i = 0; i < s->n_materials; i++) {

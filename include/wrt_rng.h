@@ -54,13 +54,24 @@ WRT_HD float wrt_u01(uint32_t bits)
 
 /* u,v for soft-shadow sample `sample` of light `light` at ray-tree node
  * `path` (root = 1, reflection child = 2p, transmission child = 2p+1) of
- * global pixel `pixel` (y*width + x). */
+ * global pixel `pixel` (y*width + x).  One Philox block serves two samples:
+ * counter (pixel, path, light, sample >> 1); even samples take words x,y, odd
+ * samples words z,w. */
 WRT_HD void wrt_light_sample_uv(uint32_t seed, uint32_t pixel, uint32_t path,
                                 uint32_t light, uint32_t sample, float* u, float* v)
 {
-    WrtRand4 r = wrt_philox4x32_10(pixel, path, light, sample, seed, 0x57525421u);
-    *u = wrt_u01(r.x);
-    *v = wrt_u01(r.y);
+    WrtRand4 r = wrt_philox4x32_10(pixel, path, light, sample >> 1, seed, 0x57525421u);
+    if (sample & 1u) { *u = wrt_u01(r.z); *v = wrt_u01(r.w); }
+    else             { *u = wrt_u01(r.x); *v = wrt_u01(r.y); }
+}
+
+/* Both samples of a pair at once (what the CUDA kernel uses). */
+WRT_HD void wrt_light_sample_uv_pair(uint32_t seed, uint32_t pixel, uint32_t path, uint32_t light,
+                                     uint32_t pair, float* u0, float* v0, float* u1, float* v1)
+{
+    WrtRand4 r = wrt_philox4x32_10(pixel, path, light, pair, seed, 0x57525421u);
+    *u0 = wrt_u01(r.x); *v0 = wrt_u01(r.y);
+    *u1 = wrt_u01(r.z); *v1 = wrt_u01(r.w);
 }
 
 #endif /* WRT_RNG_H */

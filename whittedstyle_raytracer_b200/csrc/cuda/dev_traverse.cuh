@@ -15,6 +15,8 @@
 
 namespace wrt {
 
+#define WRT_INLINE_LIGHTS 4
+
 struct DevScene {
     const float4* nodes;      // reference-topology tree (host-built, BVH.hpp:49-125)
     const float4* fnodes;     // SAH tree over the same leaf boxes (fast_bvh.hpp), same record layout
@@ -24,6 +26,7 @@ struct DevScene {
     const int*    object_prim;
     const float4* materials;  // per material 3x float4: {Od.rgb, ka} {Os.rgb, kd} {ks, n, alpha, eta}
     const WrtLight* lights;
+    WrtLight lights_c[WRT_INLINE_LIGHTS];   // the first lights again, in the kernel-parameter constant bank
     const WrtTexture* textures;
     const WrtTexture* normalmaps;
     const float* texels;
@@ -326,7 +329,8 @@ __device__ __forceinline__ float directional_product(const DevScene& s, const Ra
 // bunny); refilling keeps the SIMD lanes occupied where fixed 32-ray batches do not.
 // Q provides: bool begin(item, cur, st)  — load + start; false = resolved without a walk
 //             bool step(cur, st)         — one traversal step; false = finished
-//             void end()                 — write the result
+//             bool finish(cur, st)       — a walk ended: write results, or start the item's next
+//                                          walk (soft-shadow sample pairs) and return true
 template <class Q>
 __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned long long* work, Stack& st, int refill) {
     const unsigned lane = threadIdx.x & 31;
@@ -345,7 +349,7 @@ __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned l
                 if (item < n) {
                     st.sp = 0;
                     active = q.begin(item, cur, st);
-                    if (!active) q.end();
+                    while (!active && q.finish(cur, st)) active = true;
                 }
             }
             if (base + cnt >= n) drained = true;
@@ -360,7 +364,7 @@ __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned l
         for (int k = 0; k < 4; k++) {
             if (active) {
                 active = q.step(cur, st);
-                if (!active) q.end();
+                if (!active) active = q.finish(cur, st);
             }
         }
     }

@@ -30,10 +30,17 @@
 
 namespace wrt {
 
+// min/max without libm calls (finite inputs: same values as fminf/fmaxf)
+static inline float fb_min(float a, float b) { return a < b ? a : b; }
+static inline float fb_max(float a, float b) { return a > b ? a : b; }
+
 struct FastBvhBuilder {
-    struct P { float mn[3], mx[3], c[3]; int prim; };
-    std::vector<P> prims;
+    struct P { float mn[3], mx[3], c[3]; };
+    std::vector<P> prims;          // indexed by primitive
+    std::vector<int> idx;          // permutation of primitive indices, partitioned in place
     std::vector<WrtNode> nodes;
+    std::vector<float> right_area; // scratch
+    std::vector<int> scratch;
     int max_depth = 0;
 
     static float half_area(const float* mn, const float* mx) {
@@ -41,94 +48,102 @@ struct FastBvhBuilder {
         return dx * dy + dy * dz + dz * dx;
     }
     static void grow(float* mn, float* mx, const P& p) {
-        for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], p.mn[k]); mx[k] = fmaxf(mx[k], p.mx[k]); }
+        for (int k = 0; k < 3; k++) { mn[k] = fb_min(mn[k], p.mn[k]); mx[k] = fb_max(mx[k], p.mx[k]); }
     }
     static void reset(float* mn, float* mx) {
         for (int k = 0; k < 3; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
     }
 
-    // Leaf boxes are taken from the reference tree's leaf records: prim_box[p] for every prim.
+    // Leaf boxes are taken from the reference tree's leaf records.
     void build(const WrtSceneDesc* s) {
         nodes.clear();
         max_depth = 0;
         const int n = s->n_prims;
         if (n == 0 || s->n_nodes == 0) return;
         prims.resize(n);
+        idx.resize(n);
+        right_area.resize(n);
         for (int i = 0; i < s->n_nodes; i++) {
             const WrtNode& nd = s->nodes[i];
-            if (nd.link >= 0 || i == 1) continue;            // record 1 is padding
-            if (i == 1) continue;
+            if (nd.link >= 0 || i == 1) continue;            // inner node / padding record
             int p = ~nd.link;
             if (p < 0 || p >= n) continue;
             P& q = prims[p];
-            q.prim = p;
             for (int k = 0; k < 3; k++) { q.mn[k] = nd.pmin[k]; q.mx[k] = nd.pmax[k]; q.c[k] = 0.5f * nd.pmin[k] + 0.5f * nd.pmax[k]; }
         }
+        for (int i = 0; i < n; i++) idx[i] = i;
+        nodes.reserve(2 * (size_t)n + 2);
         nodes.resize(2);
         memset(nodes.data(), 0, 2 * sizeof(WrtNode));
         nodes[1].link = ~0;
         rec_build(0, 0, n, 0);
     }
 
-    void set_leaf(int rec, const P& p) {
+    void set_leaf(int rec, int prim) {
         WrtNode& nd = nodes[rec];
+        const P& p = prims[prim];
         for (int k = 0; k < 3; k++) { nd.pmin[k] = p.mn[k]; nd.pmax[k] = p.mx[k]; }
-        nd.link = ~p.prim;
+        nd.link = ~prim;
     }
 
-    // chooses the split of prims[b,e); returns mid in (b,e) after partitioning
+    void sort_axis(int b, int e, int axis) {
+        const std::vector<P>& pr = prims;
+        std::sort(idx.begin() + b, idx.begin() + e, [&pr, axis](int x, int y) {
+            float cx = pr[x].c[axis], cy = pr[y].c[axis];
+            return cx < cy || (cx == cy && x < y);
+        });
+    }
+
+    // chooses the split of idx[b,e); returns mid in (b,e) after partitioning
     int split(int b, int e) {
         const int n = e - b;
         if (n == 2) return b + 1;
         float cmn[3], cmx[3];
         reset(cmn, cmx);
         for (int i = b; i < e; i++)
-            for (int k = 0; k < 3; k++) { cmn[k] = fminf(cmn[k], prims[i].c[k]); cmx[k] = fmaxf(cmx[k], prims[i].c[k]); }
+            for (int k = 0; k < 3; k++) { cmn[k] = fb_min(cmn[k], prims[idx[i]].c[k]); cmx[k] = fb_max(cmx[k], prims[idx[i]].c[k]); }
         float best_cost = INFINITY;
         int best_axis = -1, best_pos = -1;
-        if (n <= 256) {                                       // exact sweep
-            std::vector<float> right_area(n);
+        if (n <= 16) {                                        // exact sweep over the three axes
+            int sorted_axis = -1;
             for (int axis = 0; axis < 3; axis++) {
                 if (!(cmx[axis] > cmn[axis])) continue;
-                std::sort(prims.begin() + b, prims.begin() + e, [axis](const P& x, const P& y) {
-                    return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.prim < y.prim);
-                });
+                sort_axis(b, e, axis);
+                sorted_axis = axis;
                 float mn[3], mx[3];
                 reset(mn, mx);
-                for (int i = n - 1; i > 0; i--) { grow(mn, mx, prims[b + i]); right_area[i] = half_area(mn, mx); }
+                for (int i = n - 1; i > 0; i--) { grow(mn, mx, prims[idx[b + i]]); right_area[i] = half_area(mn, mx); }
                 reset(mn, mx);
                 for (int i = 1; i < n; i++) {
-                    grow(mn, mx, prims[b + i - 1]);
+                    grow(mn, mx, prims[idx[b + i - 1]]);
                     float cost = half_area(mn, mx) * i + right_area[i] * (n - i);
                     if (cost < best_cost) { best_cost = cost; best_axis = axis; best_pos = i; }
                 }
             }
             if (best_axis < 0) return b + n / 2;
-            const int axis = best_axis;
-            std::sort(prims.begin() + b, prims.begin() + e, [axis](const P& x, const P& y) {
-                return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.prim < y.prim);
-            });
+            if (sorted_axis != best_axis) sort_axis(b, e, best_axis);
             return b + best_pos;
         }
-        const int K = 64;
+        const int KMAX = 64, K = 64;                          // bins
         for (int axis = 0; axis < 3; axis++) {
             if (!(cmx[axis] > cmn[axis])) continue;
-            int cnt[K] = {0};
-            float bmn[K][3], bmx[K][3];
+            int cnt[KMAX] = {0};
+            float bmn[KMAX][3], bmx[KMAX][3];
             for (int j = 0; j < K; j++) reset(bmn[j], bmx[j]);
             const float scale = K / (cmx[axis] - cmn[axis]);
             for (int i = b; i < e; i++) {
-                int j = std::min(K - 1, std::max(0, (int)((prims[i].c[axis] - cmn[axis]) * scale)));
+                const P& p = prims[idx[i]];
+                int j = std::min(K - 1, std::max(0, (int)((p.c[axis] - cmn[axis]) * scale)));
                 cnt[j]++;
-                grow(bmn[j], bmx[j], prims[i]);
+                grow(bmn[j], bmx[j], p);
             }
-            float ra[K];
-            int rc[K];
+            float ra[KMAX];
+            int rc[KMAX];
             float mn[3], mx[3];
             reset(mn, mx);
             int c = 0;
             for (int j = K - 1; j > 0; j--) {
-                if (cnt[j]) { for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], bmn[j][k]); mx[k] = fmaxf(mx[k], bmx[j][k]); } }
+                if (cnt[j]) { for (int k = 0; k < 3; k++) { mn[k] = fb_min(mn[k], bmn[j][k]); mx[k] = fb_max(mx[k], bmx[j][k]); } }
                 c += cnt[j];
                 ra[j] = c ? half_area(mn, mx) : 0.f;
                 rc[j] = c;
@@ -136,7 +151,7 @@ struct FastBvhBuilder {
             reset(mn, mx);
             c = 0;
             for (int j = 1; j < K; j++) {
-                if (cnt[j - 1]) { for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], bmn[j - 1][k]); mx[k] = fmaxf(mx[k], bmx[j - 1][k]); } }
+                if (cnt[j - 1]) { for (int k = 0; k < 3; k++) { mn[k] = fb_min(mn[k], bmn[j - 1][k]); mx[k] = fb_max(mx[k], bmx[j - 1][k]); } }
                 c += cnt[j - 1];
                 if (c == 0 || rc[j] == 0) continue;
                 float cost = half_area(mn, mx) * c + ra[j] * rc[j];
@@ -148,18 +163,19 @@ struct FastBvhBuilder {
         const float scale = K / (cmx[axis] - cmn[axis]);
         const float lo = cmn[axis];
         const int pos = best_pos;
-        auto mid = std::partition(prims.begin() + b, prims.begin() + e, [=](const P& x) {
-            int j = std::min(K - 1, std::max(0, (int)((x.c[axis] - lo) * scale)));
+        const std::vector<P>& pr = prims;
+        auto mid = std::partition(idx.begin() + b, idx.begin() + e, [&pr, axis, scale, lo, pos](int x) {
+            int j = std::min(K - 1, std::max(0, (int)((pr[x].c[axis] - lo) * scale)));
             return j < pos;
         });
-        int m = (int)(mid - prims.begin());
+        int m = (int)(mid - idx.begin());
         if (m == b || m == e) return b + n / 2;
         return m;
     }
 
     void rec_build(int rec, int b, int e, int depth) {
         max_depth = std::max(max_depth, depth);
-        if (e - b == 1) { set_leaf(rec, prims[b]); return; }
+        if (e - b == 1) { set_leaf(rec, idx[b]); return; }
         int mid = split(b, e);
         int pair = (int)nodes.size();
         nodes.resize(pair + 2);
@@ -169,7 +185,7 @@ struct FastBvhBuilder {
         rec_build(pair + 1, mid, e, depth + 1);
         const WrtNode L = nodes[pair], R = nodes[pair + 1];
         WrtNode& nd = nodes[rec];
-        for (int k = 0; k < 3; k++) { nd.pmin[k] = fminf(L.pmin[k], R.pmin[k]); nd.pmax[k] = fmaxf(L.pmax[k], R.pmax[k]); }
+        for (int k = 0; k < 3; k++) { nd.pmin[k] = fb_min(L.pmin[k], R.pmin[k]); nd.pmax[k] = fb_max(L.pmax[k], R.pmax[k]); }
     }
 };
 

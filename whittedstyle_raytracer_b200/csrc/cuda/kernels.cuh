@@ -160,8 +160,9 @@ struct ClosestQuery {
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
         return traverse_step<true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
     }
-    __device__ __forceinline__ void end() {
+    __device__ __forceinline__ bool finish(int&, Stack&) {
         fb.hit[idx] = make_float4(cs.best.t, __int_as_float(cs.best.prim), cs.best.u, cs.best.v);
+        return false;
     }
 };
 
@@ -324,7 +325,7 @@ struct HardShadowQuery {
         bool more = traverse_step<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
         return more && res != 0.f;
     }
-    __device__ __forceinline__ void end() { fb.coeff[out] = res; }
+    __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[out] = res; return false; }
 };
 
 __global__ void __launch_bounds__(128) k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
@@ -340,6 +341,8 @@ __global__ void __launch_bounds__(128) k_shadow_hard(const __grid_constant__ Dev
 // Work item = (request, sample): consecutive items share the shading point, so a warp's
 // rays start at one or two origins and stay coherent.  Each lit sample adds 1.0f to the
 // request's coefficient (float atomics on small integers are exact and order-free).
+// (Tracing a sample pair per lane from one Philox block was tried: 16 % slower — register
+// pressure and a less coherent second walk; profiles/NOTES.md.)
 struct SoftShadowQuery {
     const DevScene& s;
     const FrameBuffers& fb;
@@ -356,12 +359,17 @@ struct SoftShadowQuery {
         unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
         float4 o4 = fb.preq_o[req];
         uint4 k = fb.preq_k[req];
-        const WrtLight* L = s.lights + k.x;
+        f3 v0, v1, v2;
+        if (k.x < WRT_INLINE_LIGHTS) {                 // kernel-parameter constant bank
+            const WrtLight& L = s.lights_c[k.x];
+            v0 = mk3(L.tri[0], L.tri[1], L.tri[2]); v1 = mk3(L.tri[3], L.tri[4], L.tri[5]); v2 = mk3(L.tri[6], L.tri[7], L.tri[8]);
+        } else {
+            const WrtLight* L = s.lights + k.x;
+            v0 = mk3(L->tri[0], L->tri[1], L->tri[2]); v1 = mk3(L->tri[3], L->tri[4], L->tri[5]); v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
+        }
         float u, v;
         wrt_light_sample_uv(seed, k.y, k.z, k.x, sample, &u, &v);
         // randomSampleTriangle, Triangle.hpp:139-145: (1-u-v)*v0 + u*v1 + v*v2
-        f3 v0 = mk3(L->tri[0], L->tri[1], L->tri[2]), v1 = mk3(L->tri[3], L->tri[4], L->tri[5]),
-           v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
         f3 lightPos = (1 - u - v) * v0 + u * v1 + v * v2;
         f3 orig = mk3(o4);
         f3 raydir = normalized(lightPos - orig);
@@ -376,8 +384,9 @@ struct SoftShadowQuery {
         bool more = traverse_step<true>(nodes, r, st, cur, never, [&](int p) { occluded_leaf(s, r, dis, p, occ); });
         return more && !occ;
     }
-    __device__ __forceinline__ void end() {
+    __device__ __forceinline__ bool finish(int&, Stack&) {
         if (!occ) atomicAdd(fb.coeff + out, 1.0f);
+        return false;
     }
 };
 

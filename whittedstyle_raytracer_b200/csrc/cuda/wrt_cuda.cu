@@ -3,6 +3,7 @@
 // with -fmad=false (see dev_math.cuh).  No CPU fallback exists in this library.
 #include <algorithm>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -49,6 +50,8 @@ struct WrtContext {
     // scene
     wrt::DevScene ds{};
     std::vector<void*> scene_allocs;
+    std::vector<size_t> scene_alloc_bytes;
+    size_t scene_slot = 0;
     bool has_scene = false;
     bool textures_complete = true;
     int bvh_depth = 0;
@@ -111,21 +114,30 @@ namespace {
 
 using wrt::FrameBuffers;
 
+// Scene arrays keep their device allocation across uploads when the new array fits
+// (re-uploading a scene of the same size costs copies only, no cudaMalloc/cudaFree).
 template <class T>
 int dev_upload(WrtContext* c, const T* src, size_t count, const T** dst) {
     *dst = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    void* p = nullptr;
-    CK(cudaMalloc(&p, bytes));
-    c->scene_allocs.push_back(p);
-    if (count) CK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    size_t slot = c->scene_slot++;
+    if (slot >= c->scene_allocs.size()) { c->scene_allocs.push_back(nullptr); c->scene_alloc_bytes.push_back(0); }
+    if (c->scene_alloc_bytes[slot] < bytes) {
+        if (c->scene_allocs[slot]) cudaFree(c->scene_allocs[slot]);
+        c->scene_allocs[slot] = nullptr; c->scene_alloc_bytes[slot] = 0;
+        CK(cudaMalloc(&c->scene_allocs[slot], bytes));
+        c->scene_alloc_bytes[slot] = bytes;
+    }
+    void* p = c->scene_allocs[slot];
+    if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->own_stream));
     *dst = (const T*)p;
     return 0;
 }
 
 void free_scene(WrtContext* c) {
-    for (void* p : c->scene_allocs) cudaFree(p);
+    for (void* p : c->scene_allocs) if (p) cudaFree(p);
     c->scene_allocs.clear();
+    c->scene_alloc_bytes.clear();
     c->has_scene = false;
 }
 
@@ -474,8 +486,9 @@ void wrt_destroy(WrtContext* c) {
 int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     if (!c || !s) return fail("wrt_upload_scene: null argument");
     CK(cudaSetDevice(c->device));
-    CK(cudaDeviceSynchronize());
-    free_scene(c);
+    CK(cudaDeviceSynchronize());                       // no frame may still read the old scene
+    c->has_scene = false;
+    c->scene_slot = 0;
     wrt::DevScene& ds = c->ds;
     memset(&ds, 0, sizeof ds);
     c->textures_complete = true;
@@ -485,7 +498,9 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     if (dev_upload(c, (const float4*)s->nodes, 2 * (size_t)s->n_nodes, &ds.nodes)) return 1;
     // SAH tree over the same leaf boxes (fast_bvh.hpp explains why results are identical)
     wrt::FastBvhBuilder fbvh;
+    auto t_sah0 = std::chrono::steady_clock::now();
     fbvh.build(s);
+    auto t_sah1 = std::chrono::steady_clock::now();
     if (fbvh.nodes.size() != (size_t)s->n_nodes) return fail("wrt_upload_scene: fast BVH build failed");
     if (dev_upload(c, (const float4*)fbvh.nodes.data(), 2 * fbvh.nodes.size(), &ds.fnodes)) return 1;
     std::vector<float4> geom(3 * (size_t)np), attr(4 * (size_t)np);
@@ -528,6 +543,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     if (dev_upload(c, s->textures, (size_t)s->n_textures, &ds.textures)) return 1;
     if (dev_upload(c, s->normalmaps, (size_t)s->n_normalmaps, &ds.normalmaps)) return 1;
     if (dev_upload(c, s->texels, 3 * (size_t)s->n_texels, &ds.texels)) return 1;
+    for (int i = 0; i < s->n_lights && i < WRT_INLINE_LIGHTS; i++) ds.lights_c[i] = s->lights[i];
     ds.n_nodes = s->n_nodes; ds.n_prims = np; ds.n_lights = s->n_lights;
     ds.n_point_lights = ds.n_dir_lights = 0;
     for (int i = 0; i < s->n_lights; i++) {
@@ -542,7 +558,11 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     c->bvh_depth = tree_depth(s);
     c->stack_rows = std::max(c->bvh_depth, fbvh.max_depth) + 2;
     if (c->stack_rows > 96) return fail("wrt_upload_scene: acceleration tree deeper than 94 levels");
+    CK(cudaStreamSynchronize(c->own_stream));          // host staging vectors go out of scope here
     c->has_scene = true;
+    if (getenv("WRT_VERBOSE"))
+        fprintf(stderr, "[wrt] upload: %d prims, reference tree depth %d, SAH tree depth %d (built in %.2f ms)\n", np,
+                c->bvh_depth, fbvh.max_depth, std::chrono::duration<double, std::milli>(t_sah1 - t_sah0).count());
     return 0;
 }
 
@@ -687,6 +707,16 @@ int wrt_render(WrtContext* c, uint8_t* rgb_host, WrtStats* stats) {
     if (c->world > 1) CK(cudaMemsetAsync(c->d_image, 0, bytes, st));
     if (render_all(c, st, c->d_image, nullptr)) return 1;
     if (finish_frame(c, c->d_image, nullptr)) return 1;
+    cudaPointerAttributes attr;
+    bool user_pinned = c->world == 1 && cudaPointerGetAttributes(&attr, rgb_host) == cudaSuccess &&
+                       attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (user_pinned) {                                 // caller's buffer is page-locked: no staging copy
+        CK(cudaMemcpyAsync(rgb_host, c->d_image, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (stats) *stats = c->stats;
+        return 0;
+    }
     CK(cudaMemcpyAsync(c->h_image, c->d_image, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (c->world == 1) memcpy(rgb_host, c->h_image, bytes);

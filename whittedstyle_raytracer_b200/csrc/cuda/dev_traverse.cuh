@@ -164,7 +164,11 @@ __device__ __forceinline__ bool traverse_step(const float4* __restrict__ nodes, 
     if (hr && linkR < 0) { leaf(~linkR); hr = false; }
     if (hl && hr) {
         bool right_first = NEAR_FIRST && (tr < tl);
-        st.push(right_first ? linkL : linkR);
+        int far_link = right_first ? linkL : linkR;
+        st.push(far_link);
+#ifdef WRT_PREFETCH_FAR
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + 2 * far_link));   // it will be popped later
+#endif
         cur = right_first ? linkR : linkL;
         return true;
     }

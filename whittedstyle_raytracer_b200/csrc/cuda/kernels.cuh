@@ -16,6 +16,10 @@
 #include "../../../include/wrt_rng.h"
 #include "../../../include/wrt_tiles.h"
 
+#ifndef WRT_MIN_BLOCKS
+#define WRT_MIN_BLOCKS 1
+#endif
+
 namespace wrt {
 
 enum CounterSlot {
@@ -166,7 +170,7 @@ struct ClosestQuery {
     }
 };
 
-__global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
+__global__ void __launch_bounds__(128, WRT_MIN_BLOCKS) k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
                                                        float prune_rel, int refill) {
     extern __shared__ int smem[];
     Stack st;
@@ -328,7 +332,7 @@ struct HardShadowQuery {
     __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[out] = res; return false; }
 };
 
-__global__ void __launch_bounds__(128) k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
+__global__ void __launch_bounds__(128, WRT_MIN_BLOCKS) k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
@@ -390,7 +394,7 @@ struct SoftShadowQuery {
     }
 };
 
-__global__ void __launch_bounds__(128) k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
+__global__ void __launch_bounds__(128, WRT_MIN_BLOCKS) k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
                                                      unsigned seed, int refill) {
     extern __shared__ int smem[];
     Stack st;

@@ -98,6 +98,7 @@ struct WrtContext {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaStream_t last_stream = nullptr;
     bool frame_pending = false;
+    bool has_frame = false;
 
     wrt::TileMap tilemap() const {
         wrt::TileMap tm;
@@ -339,6 +340,7 @@ int render_all(WrtContext* c, cudaStream_t st, uint8_t* d_image, uint8_t* d_pack
     c->timed.clear();
     c->event_next = 0;
     c->last_stream = st;
+    c->has_frame = true;
     CK(cudaEventRecord(c->ev_begin, st));
     if (total > 0) {
         unsigned want = (unsigned)std::min(total, max_batch);
@@ -746,7 +748,7 @@ int wrt_render_device(WrtContext* c, void* d_rgb_tiles, void* cuda_stream) {
 int wrt_finish_device(WrtContext* c, WrtStats* stats) {
     if (!c) return fail("wrt_finish_device: null context");
     CK(cudaSetDevice(c->device));
-    if (!c->last_stream && !c->frame_pending) return fail("wrt_finish_device: no frame in flight");
+    if (!c->has_frame) return fail("wrt_finish_device: no frame in flight");
     // the packed pointer is only needed again if an overflowed frame must be re-rendered
     if (c->frame_pending && c->h_counters) {
         CK(cudaStreamSynchronize(c->last_stream));

@@ -223,7 +223,8 @@ def run_cuda_arm(args):
 
     workdir = Path(tempfile.mkdtemp(prefix=f"wrt_bench_{rank}_"))
     scene, glass = prepare_scene(args.workload, workdir)
-    dr = DistributedRenderer(scene, rank, world, local)
+    tile = tuple(int(x) for x in os.environ.get("WRT_TILE", "8x4").split("x"))
+    dr = DistributedRenderer(scene, rank, world, local, tile=tile)
     ctx = dr.renderer.ctx
     w, h = scene.width, scene.height
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
@@ -238,28 +239,40 @@ def run_cuda_arm(args):
     barrier()
     rays_local = stats["rays"]
     rays_t = torch.tensor([rays_local, stats["closest_rays"], stats["shadow_rays"]], dtype=torch.int64, device="cuda")
+    per_rank_rays = torch.zeros(world, dtype=torch.int64, device="cuda")
+    per_rank_rays[rank] = rays_local
     if world > 1:
         dist.all_reduce(rays_t)
+        dist.all_reduce(per_rank_rays)
     rays_frame, closest_frame, shadow_frame = (int(x) for x in rays_t.tolist())
 
     # ---- timed: device-resident scene, CUDA events on the launching (current) stream ----
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ctx.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
     barrier()
     t_wall0 = time.time()
     for k in range(args.steps):
         l2_flush()
         if world > 1:
             dist.barrier()
+        dr.render_done = ev[k][2]
         ev[k][0].record()
         dr.frame()
         ev[k][1].record()
         dr.finish()
+    dr.render_done = None
     barrier()
     t_wall1 = time.time()
     launches = ctx.launches - launches0
-    ms_local = sum(a.elapsed_time(b) for a, b in ev)
+    ms_local = sum(a.elapsed_time(b) for a, b, _ in ev)
+    render_local = sum(a.elapsed_time(c) for a, _, c in ev) / args.steps      # this rank's tiles only, no gather
+    rr = torch.zeros(world, dtype=torch.float64, device="cuda")
+    rr[rank] = render_local
+    if world > 1:
+        dist.all_reduce(rr)
+    per_rank_render_ms = [round(float(x), 4) for x in rr.tolist()]
     ms_t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -362,13 +375,15 @@ def run_cuda_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "width": w, "height": h, "rays_per_frame": rays_frame,
                        "closest_hit_rays": closest_frame, "shadow_rays": shadow_frame,
-                       "parallelism": f"tiles32x16-interleaved x{world}" + ("+nccl-gather" if world > 1 else ""),
+                       "parallelism": f"tiles{tile[0]}x{tile[1]}-interleaved x{world}" + ("+nccl-gather" if world > 1 else ""),
                        "traversal": "pruned", "l2": "flushed between timed steps (256 MiB write)",
                        "scene_bytes": scene.upload_bytes, "image_checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": int(scene.upload_bytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": fam_ms,
+            "per_rank_render_ms": per_rank_render_ms,
+            "per_rank_rays": [int(x) for x in per_rank_rays.tolist()],
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -4,7 +4,7 @@
  * The reference renders pixels in one serial loop (Renderer.hpp:104-131); every
  * pixel is independent, so the frame shards as interleaved tiles.  The image is
  * cut into tile_w x tile_h tiles (multiples of the 8 x 4 pixel block a warp
- * traces).  Rank r owns the tile sequence k = r, r + world, r + 2*world, ...;
+ * traces; the default tile IS that block).  Rank r owns the tile sequence k = r, r + world, r + 2*world, ...;
  * sequence number k maps to image tile (k * perm_mul) % n_tiles with perm_mul
  * coprime to n_tiles, which scatters each rank's tiles over the whole image
  * (the bunny covers ~7 % of the pixels but spawns about half of the rays, so

@@ -16,8 +16,12 @@
 #include "../../../include/wrt_rng.h"
 #include "../../../include/wrt_tiles.h"
 
-#ifndef WRT_MIN_BLOCKS
-#define WRT_MIN_BLOCKS 1
+// Traversal kernels: 128-thread CTAs; ptxas settles at 54-56 registers (9 CTAs per SM).  Forcing more
+// CTAs per SM through a minimum-blocks bound spills and is slower (profiles/NOTES.md).
+#ifdef WRT_MIN_BLOCKS
+#define WRT_TRACE_BOUNDS WRT_TRACE_BOUNDS
+#else
+#define WRT_TRACE_BOUNDS __launch_bounds__(128)
 #endif
 
 namespace wrt {
@@ -170,7 +174,7 @@ struct ClosestQuery {
     }
 };
 
-__global__ void __launch_bounds__(128, WRT_MIN_BLOCKS) k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
+__global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
                                                        float prune_rel, int refill) {
     extern __shared__ int smem[];
     Stack st;
@@ -332,7 +336,7 @@ struct HardShadowQuery {
     __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[out] = res; return false; }
 };
 
-__global__ void __launch_bounds__(128, WRT_MIN_BLOCKS) k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
+__global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
@@ -394,7 +398,7 @@ struct SoftShadowQuery {
     }
 };
 
-__global__ void __launch_bounds__(128, WRT_MIN_BLOCKS) k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
+__global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
                                                      unsigned seed, int refill) {
     extern __shared__ int smem[];
     Stack st;

@@ -60,7 +60,7 @@ struct WrtContext {
     // camera / tiling / options
     WrtCamera cam{};
     bool has_cam = false;
-    int tile_w = 32, tile_h = 16, rank = 0, world = 1;
+    int tile_w = 8, tile_h = 4, rank = 0, world = 1;   // one warp-sized 8x4 block per tile: finest interleave
     int traversal = WRT_TRAVERSAL_PRUNED;
     uint32_t seed = WRT_DEFAULT_SEED;
     float queue_factor = 2.0f;

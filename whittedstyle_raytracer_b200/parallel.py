@@ -16,7 +16,7 @@ from . import cabi
 from .renderer import Renderer
 from .scene import Scene
 
-TILE_W, TILE_H = 32, 16
+TILE_W, TILE_H = 8, 4      # one warp-sized pixel block per tile: finest interleave, best balance
 
 
 def tile_slot_count(width, height, rank, world, tile=(TILE_W, TILE_H)) -> int:
@@ -90,11 +90,14 @@ class DistributedRenderer:
         self.packed = self.tg.new_buffer(dev)
         self.gathered = torch.empty((world, self.tg.stride), dtype=torch.uint8, device=dev) if rank == 0 else None
         self.image = torch.zeros((cam.height, cam.width, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
+        self.render_done = None                        # optional torch.cuda.Event recorded after the render kernels
 
     def frame(self):
         """Enqueues render -> gather -> scatter on torch's current stream (asynchronous)."""
         stream = self.torch.cuda.current_stream().cuda_stream
         self.renderer.render_device(self.packed.data_ptr(), stream)
+        if self.render_done is not None:
+            self.render_done.record()                  # this rank's own tiles are finished here
         g = self.tg.gather(self.packed, self.gathered)
         if self.rank == 0:
             self.renderer.scatter_tiles(g.data_ptr(), self.world, self.tg.stride, self.image.data_ptr(), stream)

@@ -75,7 +75,7 @@ class Context:
     def set_camera(self, scene: Scene):
         self._check(self.lib.wrt_set_camera(self.h, scene.camera_ptr))
 
-    def set_tiles(self, tile_w=32, tile_h=16, rank=0, world=1):
+    def set_tiles(self, tile_w=8, tile_h=4, rank=0, world=1):
         self._check(self.lib.wrt_set_tiles(self.h, tile_w, tile_h, rank, world))
 
     def set_options(self, traversal=TRAVERSAL_PRUNED, seed=cabi.WRT_DEFAULT_SEED, queue_factor=0.0):

@@ -232,6 +232,7 @@ def run_cuda_arm(args):
     def l2_flush():
         flush.fill_(rank + 1)
 
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to emit
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
         dr.frame()
@@ -247,7 +248,6 @@ def run_cuda_arm(args):
     rays_frame, closest_frame, shadow_frame = (int(x) for x in rays_t.tolist())
 
     # ---- timed: device-resident scene, CUDA events on the launching (current) stream ----
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]

@@ -42,13 +42,14 @@ def main():
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
     res = []
     for r in rows[2:]:
         d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0]}
         for k, name in WANT.items():
             if k in hdr:
-                d[name] = r[hdr.index(k)]
+                u = units[hdr.index(k)]
+                d[name] = r[hdr.index(k)] + (f" {u}" if u else "")
         stalls = {}
         for i, h in enumerate(hdr):
             if h.startswith(STALL) and h.endswith("_per_issue_active.ratio"):

@@ -47,14 +47,16 @@ struct FrameBuffers {
     float4* ray_o[2];            // {o.xyz, pixel id}
     float4* ray_d[2];            // {d.xyz, path id}
     float4* hit;                 // {t, prim, b1, b2}
-    float4* surf;                // 3 per node: {pos, prim} {nDir, material} {Od, -}
+    float4* surf[2];             // by level parity, 4 per node: {pos, prim} {nDir, material} {Od, -} {ray origin, -}
     float4* node_a[WRT_MAX_DEPTH];   // {local.rgb -> colour.rgb, fr}
     float4* node_b[WRT_MAX_DEPTH];   // {kT, childR, childT, composite flag}
-    float4* preq_o;              // point-light request: {shadow ray origin, node}
-    uint4*  preq_k;              //                      {light, pixel, path, -}
-    float4* dreq_o;              // directional request: {pos, node}
-    uint4*  dreq_k;              //                      {light, self prim, -, -}
-    float*  coeff;               // [node * n_lights + light]
+    // shadow requests and coefficients are double-buffered by level parity so that the shadow + shade
+    // kernels of level d (side stream) overlap the closest-hit + surface kernels of level d+1
+    float4* preq_o[2];           // point-light request: {shadow ray origin, node}
+    uint4*  preq_k[2];           //                      {light, pixel, path, -}
+    float4* dreq_o[2];           // directional request: {pos, node}
+    uint4*  dreq_k[2];           //                      {light, self prim, -, -}
+    float*  coeff[2];            // [node * n_lights + light]
     unsigned* counters;
     unsigned cap;                // capacity of every per-level array
     unsigned preq_cap, dreq_cap;
@@ -225,10 +227,11 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
                         Od = texture_at(s, s.textures + sf.textureIndex, sf.u, sf.v);      // :176-180
                     if (sf.normalMapIndex != -1) sf.nDir = change_normal_dir(s, sf);        // :182-184
                     pos = sf.pos; nDir = sf.nDir;
-                    float4* sv = fb.surf + 3 * (size_t)i;
+                    float4* sv = fb.surf[level & 1] + 4 * (size_t)i;
                     sv[0] = make_float4(pos.x, pos.y, pos.z, __int_as_float(prim));
                     sv[1] = make_float4(nDir.x, nDir.y, nDir.z, __int_as_float(sf.material));
                     sv[2] = make_float4(Od.x, Od.y, Od.z, 0.f);
+                    sv[3] = make_float4(org.x, org.y, org.z, 0.f);          // p_eye_dir needs the ray origin, :267
                     // ---- reflection / transmission, :194-257 ----
                     refRayOrig = pos; traRayOrig = pos;
                     N = normalized(nDir);
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
                 }
             }
         }
-        if (live && !shade) fb.surf[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (live && !shade) fb.surf[level & 1][4 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         // child rays: reflections into the first half of the next level, transmissions into the second
         unsigned rslot = warp_alloc(fb.counters + C_NRAYS + level + 1, spawnR ? 1 : 0, child_half, overflow);
         unsigned tslot = warp_alloc(fb.counters + C_NTRAYS + level + 1, spawnT ? 1 : 0, fb.cap - child_half, overflow);
@@ -279,15 +282,15 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
         if (shade) {
             f3 sorig = pos + 0.0005f * nDir;                               // BVHStrategy.hpp:15, Renderer.hpp:349
             for (int li = 0; li < s.n_lights; li++) {
-                fb.coeff[(size_t)i * s.n_lights + li] = 0.f;
+                fb.coeff[level & 1][(size_t)i * s.n_lights + li] = 0.f;
                 bool point = float_equal(s.lights[li].pos[3], 1.f);
                 if (point && pslot != 0xffffffffu) {
-                    fb.preq_o[pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(i));
-                    fb.preq_k[pslot] = make_uint4((unsigned)li, pixel, path, 0u);
+                    fb.preq_o[level & 1][pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(i));
+                    fb.preq_k[level & 1][pslot] = make_uint4((unsigned)li, pixel, path, 0u);
                     ++pslot;
                 } else if (!point && dslot != 0xffffffffu) {
-                    fb.dreq_o[dslot] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(i));
-                    fb.dreq_k[dslot] = make_uint4((unsigned)li, (unsigned)prim, 0u, 0u);
+                    fb.dreq_o[level & 1][dslot] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(i));
+                    fb.dreq_k[level & 1][dslot] = make_uint4((unsigned)li, (unsigned)prim, 0u, 0u);
                     ++dslot;
                 }
             }
@@ -307,10 +310,12 @@ struct HardShadowQuery {
     const float4* nodes;
     float dis, res;
     unsigned out;
-    __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_) : s(s_), fb(fb_) {}
+    int par;
+    __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int level)
+        : s(s_), fb(fb_), par(level & 1) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
-        float4 o4 = fb.preq_o[item];
-        uint4 k = fb.preq_k[item];
+        float4 o4 = fb.preq_o[par][item];
+        uint4 k = fb.preq_k[par][item];
         const WrtLight* L = s.lights + k.x;
         f3 orig = mk3(o4);
         f3 lightPos = mk3(L->pos[0], L->pos[1], L->pos[2]);
@@ -333,7 +338,7 @@ struct HardShadowQuery {
         bool more = traverse_step<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
         return more && res != 0.f;
     }
-    __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[out] = res; return false; }
+    __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[par][out] = res; return false; }
 };
 
 __global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
@@ -341,7 +346,7 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene 
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned n = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    HardShadowQuery q(s, fb);
+    HardShadowQuery q(s, fb, level);
     run_queue(q, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
 }
 
@@ -360,13 +365,14 @@ struct SoftShadowQuery {
     float dis;
     bool occ;
     unsigned out;
-    __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_)
-        : s(s_), fb(fb_), seed(seed_) {}
+    int par;
+    __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_, int level)
+        : s(s_), fb(fb_), seed(seed_), par(level & 1) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack& st) {
         unsigned req = (unsigned)(item / WRT_SOFT_SAMPLES);
         unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
-        float4 o4 = fb.preq_o[req];
-        uint4 k = fb.preq_k[req];
+        float4 o4 = fb.preq_o[par][req];
+        uint4 k = fb.preq_k[par][req];
         f3 v0, v1, v2;
         if (k.x < WRT_INLINE_LIGHTS) {                 // kernel-parameter constant bank
             const WrtLight& L = s.lights_c[k.x];
@@ -393,7 +399,7 @@ struct SoftShadowQuery {
         return more && !occ;
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
-        if (!occ) atomicAdd(fb.coeff + out, 1.0f);
+        if (!occ) atomicAdd(fb.coeff[par] + out, 1.0f);
         return false;
     }
 };
@@ -404,7 +410,7 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    SoftShadowQuery q(s, fb, seed);
+    SoftShadowQuery q(s, fb, seed, level);
     run_queue(q, (unsigned long long)nreq * WRT_SOFT_SAMPLES, reinterpret_cast<unsigned long long*>(fb.counters + work_slot),
               st, refill);
 }
@@ -413,12 +419,12 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 __global__ void __launch_bounds__(128) k_shadow_directional(DevScene s, FrameBuffers fb, int level) {
     const unsigned n = queue_len(fb.counters, C_NDREQ + level, fb.dreq_cap);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o4 = fb.dreq_o[i];
-        uint4 k = fb.dreq_k[i];
+        float4 o4 = fb.dreq_o[level & 1][i];
+        uint4 k = fb.dreq_k[level & 1][i];
         const WrtLight* L = s.lights + k.x;
         f3 negDir = mk3(-L->pos[0], -L->pos[1], -L->pos[2]);
         Ray r = make_ray(mk3(o4), normalized(negDir));
-        fb.coeff[(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product(s, r, (int)k.y);
+        fb.coeff[level & 1][(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product(s, r, (int)k.y);
     }
 }
 
@@ -427,16 +433,15 @@ __global__ void __launch_bounds__(128) k_shadow_directional(DevScene s, FrameBuf
 __global__ void __launch_bounds__(256) k_shade(DevScene s, FrameBuffers fb, int level) {
     const LevelSpan span = level_span(fb.counters, level, fb.cap);
     const unsigned n = span.count();
-    const float4* ray_o = fb.ray_o[level & 1];
     for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
         const unsigned i = span.slot(item);
-        const float4* sv = fb.surf + 3 * (size_t)i;
+        const float4* sv = fb.surf[level & 1] + 4 * (size_t)i;
         float4 s0 = sv[0];
         if (__float_as_int(s0.w) < 0) continue;
-        float4 s1 = sv[1], s2 = sv[2];
+        float4 s1 = sv[1], s2 = sv[2], s3 = sv[3];
         Mtl m = load_material(s, __float_as_int(s1.w));
         m.diffuse = mk3(s2);
-        f3 local = blinn_phong(s, mk3(ray_o[i]), mk3(s0), mk3(s1), m, fb.coeff + (size_t)i * s.n_lights);
+        f3 local = blinn_phong(s, mk3(s3), mk3(s0), mk3(s1), m, fb.coeff[level & 1] + (size_t)i * s.n_lights);
         float4 na = fb.node_a[level][i];
         na.x = local.x; na.y = local.y; na.z = local.z;
         fb.node_a[level][i] = na;

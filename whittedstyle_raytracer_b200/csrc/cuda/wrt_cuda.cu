@@ -46,6 +46,9 @@ struct WrtContext {
     int device = 0;
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;       // shadow + shade kernels of level d, concurrent with level d+1
+    cudaEvent_t ev_surface[WRT_MAX_DEPTH] = {}, ev_shade[WRT_MAX_DEPTH] = {};
+    bool overlap = true;
 
     // scene
     wrt::DevScene ds{};
@@ -193,16 +196,18 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
         if (frame_alloc(c, &fb.ray_d[k], cap)) return 1;
     }
     if (frame_alloc(c, &fb.hit, cap)) return 1;
-    if (frame_alloc(c, &fb.surf, 3 * (size_t)cap)) return 1;
+    for (int k = 0; k < 2; k++) if (frame_alloc(c, &fb.surf[k], 4 * (size_t)cap)) return 1;
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
         if (frame_alloc(c, &fb.node_a[d], cap)) return 1;
         if (frame_alloc(c, &fb.node_b[d], cap)) return 1;
     }
-    if (frame_alloc(c, &fb.preq_o, ds.n_point_lights ? fb.preq_cap : 1)) return 1;
-    if (frame_alloc(c, &fb.preq_k, ds.n_point_lights ? fb.preq_cap : 1)) return 1;
-    if (frame_alloc(c, &fb.dreq_o, ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
-    if (frame_alloc(c, &fb.dreq_k, ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
-    if (frame_alloc(c, &fb.coeff, (size_t)cap * std::max(1, ds.n_lights))) return 1;
+    for (int k = 0; k < 2; k++) {
+        if (frame_alloc(c, &fb.preq_o[k], ds.n_point_lights ? fb.preq_cap : 1)) return 1;
+        if (frame_alloc(c, &fb.preq_k[k], ds.n_point_lights ? fb.preq_cap : 1)) return 1;
+        if (frame_alloc(c, &fb.dreq_o[k], ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
+        if (frame_alloc(c, &fb.dreq_k[k], ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
+        if (frame_alloc(c, &fb.coeff[k], (size_t)cap * std::max(1, ds.n_lights))) return 1;
+    }
     if (frame_alloc(c, &fb.counters, wrt::C_TOTAL)) return 1;
     c->batch_slots = slots;
     c->fb_lights = ds.n_lights; c->fb_point = ds.n_point_lights; c->fb_dir = ds.n_dir_lights;
@@ -273,7 +278,13 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         LaunchScope ls(c, st, F_RAYGEN);
         k_raygen<<<wide_grid, 256, 0, st>>>(c->cam, tm, slot0, n, fb);
     }
+    // Level d: closest hit + surface on the caller's stream; its shadow + shade kernels on the side
+    // stream, overlapping level d+1's closest hit + surface (they only need surface(d)'s output, and
+    // the request / coefficient / surface buffers alternate by level parity).
+    const bool overlap = c->overlap && !c->kernel_timing;
+    cudaStream_t ss = overlap ? c->side_stream : st;
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
+        if (overlap && d >= 2) CK(cudaStreamWaitEvent(st, c->ev_shade[d - 2], 0));   // parity buffers free again
         {
             LaunchScope ls(c, st, F_TRACE);
             k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, d == 0 ? c->refill0 : c->refill);
@@ -282,23 +293,32 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
             LaunchScope ls(c, st, F_SURFACE);
             k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, d);
         }
+        if (overlap) {
+            CK(cudaEventRecord(c->ev_surface[d], st));
+            CK(cudaStreamWaitEvent(ss, c->ev_surface[d], 0));
+        }
         if (ds.n_point_lights > 0) {
             if (ds.shadow_type == 0) {
-                LaunchScope ls(c, st, F_SHADOW_HARD);
-                k_shadow_hard<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), d == 0 ? c->refill0 : c->refill);
+                LaunchScope ls(c, ss, F_SHADOW_HARD);
+                k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), d == 0 ? c->refill0 : c->refill);
             } else {
-                LaunchScope ls(c, st, F_SHADOW_SOFT);
-                k_shadow_soft<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft);
+                LaunchScope ls(c, ss, F_SHADOW_SOFT);
+                k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft);
             }
         }
         if (ds.n_dir_lights > 0) {
-            LaunchScope ls(c, st, F_SHADOW_DIR);
-            k_shadow_directional<<<wide_grid, TB, 0, st>>>(ds, fb, d);
+            LaunchScope ls(c, ss, F_SHADOW_DIR);
+            k_shadow_directional<<<wide_grid, TB, 0, ss>>>(ds, fb, d);
         }
         {
-            LaunchScope ls(c, st, F_SHADE);
-            k_shade<<<wide_grid, 256, 0, st>>>(ds, fb, d);
+            LaunchScope ls(c, ss, F_SHADE);
+            k_shade<<<wide_grid, 256, 0, ss>>>(ds, fb, d);
         }
+        if (overlap) CK(cudaEventRecord(c->ev_shade[d], ss));
+    }
+    if (overlap) {
+        CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - 2], 0));
+        CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - 1], 0));
     }
     for (int d = WRT_MAX_DEPTH - 1; d >= 0; d--) {
         LaunchScope ls(c, st, F_COMBINE);
@@ -451,7 +471,11 @@ int wrt_create(int device, WrtContext** out) {
     WrtContext* c = new WrtContext();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    bool ev_ok = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int d = 0; d < WRT_MAX_DEPTH && ev_ok; d++)
+        ev_ok = cudaEventCreateWithFlags(&c->ev_surface[d], cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&c->ev_shade[d], cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_counters, wrt::C_TOTAL * sizeof(unsigned)) != cudaSuccess) {
         delete c;
@@ -462,6 +486,7 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_REFILL")) c->refill = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_REFILL_SOFT")) c->refill_soft = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_TRACE_BLOCKS")) c->trace_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("WRT_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));
     *out = c;
@@ -481,6 +506,11 @@ void wrt_destroy(WrtContext* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
+        if (c->ev_surface[d]) cudaEventDestroy(c->ev_surface[d]);
+        if (c->ev_shade[d]) cudaEventDestroy(c->ev_shade[d]);
+    }
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

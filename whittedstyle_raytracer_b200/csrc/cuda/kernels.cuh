@@ -12,6 +12,8 @@
 // Every queue length lives in device memory (Counters); kernels read it there, so
 // the host enqueues the whole frame without synchronising.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "dev_shade.cuh"
 #include "../../../include/wrt_rng.h"
 #include "../../../include/wrt_tiles.h"
@@ -448,8 +450,10 @@ __global__ void __launch_bounds__(256) k_shade(DevScene s, FrameBuffers fb, int 
     }
 }
 
-// ---- K6: bottom-up combine, Renderer.hpp:259 ----
-__global__ void __launch_bounds__(256) k_combine(FrameBuffers fb, int level) {
+// ---- K6 + K7: bottom-up combine (Renderer.hpp:259) and 8-bit resolve (Renderer.hpp:128-130) ----
+// One cooperative launch walks the levels 8 -> 0 with a grid-wide barrier between them (each
+// level reads the finished colours of the level below), then quantises level 0.
+__device__ __forceinline__ void combine_level(const FrameBuffers& fb, int level) {
     const LevelSpan span = level_span(fb.counters, level, fb.cap);
     const unsigned n = span.count();
     for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(256) k_combine(FrameBuffers fb, int level) {
         f3 R = mk3(0.f, 0.f, 0.f), T = R;
         if (cR >= 0) R = mk3(fb.node_a[level + 1][cR]);
         if (cT >= 0) T = mk3(fb.node_a[level + 1][cT]);
-        f3 c = mk3(na) + na.w * R + nb.x * T;
+        f3 c = mk3(na) + na.w * R + nb.x * T;            // blinnPhongRes + fr * R_lambda + (1-fr)(1-alpha) * T_lambda
         fb.node_a[level][i] = make_float4(c.x, c.y, c.z, na.w);
     }
 }
@@ -472,9 +476,14 @@ __device__ __forceinline__ unsigned char quantize(float c) {   // int(255 * std:
     return (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
-// ---- K7: 8-bit resolve.  image != nullptr: row-major image; else tile-order pack ----
-__global__ void __launch_bounds__(256) k_resolve(FrameBuffers fb, TileMap tm, long long slot0, unsigned n,
-                                                 unsigned char* image, unsigned char* packed) {
+// image != nullptr: row-major image; packed != nullptr: tile-order buffer (multi-GPU gather)
+__global__ void __launch_bounds__(256) k_combine_resolve(const __grid_constant__ FrameBuffers fb, const __grid_constant__ TileMap tm,
+                                                         long long slot0, unsigned n, unsigned char* image, unsigned char* packed) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int level = WRT_MAX_DEPTH - 1; level >= 0; level--) {
+        combine_level(fb, level);
+        grid.sync();
+    }
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 c = fb.node_a[0][i];
         unsigned char r = quantize(c.x), g = quantize(c.y), b = quantize(c.z);

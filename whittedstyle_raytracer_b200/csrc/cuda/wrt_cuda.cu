@@ -93,6 +93,7 @@ struct WrtContext {
     // bookkeeping
     int64_t launches = 0;
     int work_seq = 0;
+    int coop_grid = 0;                 // co-resident CTAs of k_combine_resolve (cooperative launch)
     WrtStats stats{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -320,13 +321,10 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - 2], 0));
         CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - 1], 0));
     }
-    for (int d = WRT_MAX_DEPTH - 1; d >= 0; d--) {
-        LaunchScope ls(c, st, F_COMBINE);
-        k_combine<<<wide_grid, 256, 0, st>>>(fb, d);
-    }
     {
-        LaunchScope ls(c, st, F_RESOLVE);
-        k_resolve<<<wide_grid, 256, 0, st>>>(fb, tm, slot0, n, d_image, d_packed);
+        LaunchScope ls(c, st, F_COMBINE);
+        void* args[] = {(void*)&fb, (void*)&tm, (void*)&slot0, (void*)&n, (void*)&d_image, (void*)&d_packed};
+        CK(cudaLaunchCooperativeKernel((const void*)k_combine_resolve, dim3(c->coop_grid), dim3(256), args, 0, st));
     }
     CK(cudaGetLastError());
     return 0;
@@ -482,6 +480,14 @@ int wrt_create(int device, WrtContext** out) {
         return fail("wrt_create: stream/event/pinned allocation failed");
     }
     memset(c->h_counters, 0, wrt::C_TOTAL * sizeof(unsigned));
+    {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrt::k_combine_resolve, 256, 0) != cudaSuccess || per_sm < 1) {
+            wrt_destroy(c);
+            return fail("wrt_create: cooperative launch of k_combine_resolve is not possible on this device");
+        }
+        c->coop_grid = c->num_sms * std::min(per_sm, 4);
+    }
     // tuning overrides (development only; defaults are what bench.py measures)
     if (const char* e = getenv("WRT_REFILL")) c->refill = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_REFILL_SOFT")) c->refill_soft = std::max(1, std::min(32, atoi(e)));

@@ -42,7 +42,14 @@ WORKLOAD_DESC = {
 # Reference traversal work per ray: box tests, triangle tests -> FLOPs at 21 / 61 per test
 ALGO_TESTS = {"config": (75.1, 4.11), "bunny_shadow_4k": (77.5, 4.28), "gla_bunny_tex_4k": (69.5, 4.30),
               "water_bunny_tex_soft_4k": (48.6, 2.86), "glass_bunny_soft_8k": (48.6, 2.86)}
-ALGO_BYTES_PER_RAY = 112      # wavefront queue traffic (ray 40 B + hit 16 B) x (write + read)
+# Algorithmic HBM bytes per unit of each traversal kernel: what one launch must move
+# at minimum.  (SURVEY.md section 8d's 112 B/ray is the whole pipeline's queue traffic per closest-hit ray.)
+ALGO_BYTES = {
+    "trace_closest": 48.0,                 # ray 2 x float4 read + hit float4 written, per ray
+    "shadow_hard": 36.0,                   # request 32 B read + coefficient 4 B written, per ray
+    "shadow_soft": 36.0 / 50.0,            # one 32 B request + one 4 B coefficient serve 50 sample rays
+    "shadow_directional": 36.0,
+}
 
 
 def flops_per_ray(workload):
@@ -347,13 +354,16 @@ def run_cuda_arm(args):
     dom_s = fam_ms[dom] * 1e-3
     fma_tf, muladd_tf = ctx.measure_fp32_peak()
     fpr = flops_per_ray(args.workload)
+    bpu = ALGO_BYTES.get(dom, 112.0)
     roofline = {
         "kernel": f"k_{dom}", "share_of_step": dom_share, "launches_per_step": dom_launches,
         "avg_launch_ms": fam_ms[dom] / dom_launches, "units_per_step": dom_units,
-        "bound": "hbm", "achieved": dom_units * ALGO_BYTES_PER_RAY / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": dom_units * ALGO_BYTES_PER_RAY / dom_s / 1e9 / hbm_peak, "peak_source": peak_src,
-        "algorithmic_bytes_per_ray": ALGO_BYTES_PER_RAY, "traffic": profile_traffic(dom),
-        "binding_bound": "fp32-issue/latency (divergent BVH traversal; working set L1/L2-resident) — neither HBM nor tensor",
+        "bound": "hbm", "achieved": dom_units * bpu / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": dom_units * bpu / dom_s / 1e9 / hbm_peak, "peak_source": peak_src,
+        "algorithmic_bytes_per_unit": bpu, "algorithmic_bytes_per_launch": dom_units * bpu / dom_launches,
+        "traffic": profile_traffic(dom),
+        "binding_bound": "NOT hbm and not tensor: FP32 issue rate (deep levels: SM throughput 84 %, IPC 3.3/4) and L1 load "
+                         "latency (level 0); `bound` says hbm only because the schema offers hbm|tensor — see `fp32` and DESIGN.md section 6",
         "fp32": {"algorithmic_flops_per_ray": fpr, "achieved_tflops": dom_units * fpr / dom_s / 1e12,
                  "peak_tflops_fma_measured": fma_tf, "peak_tflops_fmul_fadd_measured": muladd_tf,
                  "frac_of_fma_peak": dom_units * fpr / dom_s / 1e12 / max(fma_tf, 1e-9),

@@ -2,12 +2,14 @@
 // the path is divergent traversal, not a dense contraction).
 //
 // One frame = for each ray-tree level d = 0..8 (Renderer.hpp:25 MAX_DEPTH 9):
-//   k_trace_closest   rays[d]  -> hits              (persistent warps, smem stacks)
+//   k_trace_closest   rays[d]  -> hits              (persistent warps, lane refill, smem stacks)
 //   k_surface_spawn   hits     -> surface records, shadow requests, child rays[d+1], node[d].{fr,kT,children}
 //   k_shadow_*        requests -> coeff[node, light]  (hard product / soft 50-sample count / directional)
 //   k_shade           surface + coeff -> node[d].local
-// then bottom-up k_combine(d = 8..0): colour = local + fr*R + (1-fr)(1-alpha)*T in the
-// reference's own association (Renderer.hpp:259), and k_resolve: int(255*min(c,1)) (Renderer.hpp:128-130).
+// (shadow + shade of level d run on a side stream beside closest-hit + surface of level d+1), then
+//   k_combine_resolve bottom-up colour = local + fr*R + (1-fr)(1-alpha)*T in the reference's own
+//                     association (Renderer.hpp:259) and int(255*min(c,1)) (Renderer.hpp:128-130),
+//                     one cooperative launch.
 //
 // Every queue length lives in device memory (Counters); kernels read it there, so
 // the host enqueues the whole frame without synchronising.

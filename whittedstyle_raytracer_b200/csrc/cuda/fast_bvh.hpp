@@ -173,6 +173,31 @@ struct FastBvhBuilder {
         return m;
     }
 
+    // Copy of the tree whose leaf boxes are grown by rel * (largest extent, largest |coordinate|) + abs
+    // on every side and whose inner boxes are the unions of those: a conservative culling structure
+    // for queries the reference answers without boxes.
+    std::vector<WrtNode> dilated(float rel, float abs_pad) const {
+        std::vector<WrtNode> d = nodes;
+        for (size_t i = 0; i < d.size(); i++) {
+            if (d[i].link >= 0 || i == 1) continue;
+            float ext = 0.f;
+            for (int k = 0; k < 3; k++) {
+                ext = fb_max(ext, d[i].pmax[k] - d[i].pmin[k]);
+                ext = fb_max(ext, fb_max(fabsf(d[i].pmin[k]), fabsf(d[i].pmax[k])) * 1e-2f);
+            }
+            float pad = rel * ext + abs_pad;
+            for (int k = 0; k < 3; k++) { d[i].pmin[k] -= pad; d[i].pmax[k] += pad; }
+        }
+        // inner boxes bottom-up: children always have larger indices than their parent
+        for (size_t i = d.size(); i-- > 0;) {
+            if (d[i].link < 0) continue;
+            const WrtNode& L = d[d[i].link];
+            const WrtNode& R = d[d[i].link + 1];
+            for (int k = 0; k < 3; k++) { d[i].pmin[k] = fb_min(L.pmin[k], R.pmin[k]); d[i].pmax[k] = fb_max(L.pmax[k], R.pmax[k]); }
+        }
+        return d;
+    }
+
     void rec_build(int rec, int b, int e, int depth) {
         max_depth = std::max(max_depth, depth);
         if (e - b == 1) { set_leaf(rec, idx[b]); return; }

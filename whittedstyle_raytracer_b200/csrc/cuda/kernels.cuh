@@ -23,7 +23,7 @@
 // Traversal kernels: 128-thread CTAs; ptxas settles at 54-56 registers (9 CTAs per SM).  Forcing more
 // CTAs per SM through a minimum-blocks bound spills and is slower (profiles/NOTES.md).
 #ifdef WRT_MIN_BLOCKS
-#define WRT_TRACE_BOUNDS WRT_TRACE_BOUNDS
+#define WRT_TRACE_BOUNDS __launch_bounds__(128, WRT_MIN_BLOCKS)
 #else
 #define WRT_TRACE_BOUNDS __launch_bounds__(128)
 #endif
@@ -419,8 +419,12 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
               st, refill);
 }
 
-// ---- K4c: directional-light shadows, Renderer.hpp:381-400 ----
-__global__ void __launch_bounds__(128) k_shadow_directional(DevScene s, FrameBuffers fb, int level) {
+// ---- K4c: directional-light shadows, Renderer.hpp:381-400 (dilated-tree culling, dev_traverse.cuh) ----
+__global__ void __launch_bounds__(128) k_shadow_directional(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
+                                                            int level) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
     const unsigned n = queue_len(fb.counters, C_NDREQ + level, fb.dreq_cap);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 o4 = fb.dreq_o[level & 1][i];
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(128) k_shadow_directional(DevScene s, FrameBuf
         const WrtLight* L = s.lights + k.x;
         f3 negDir = mk3(-L->pos[0], -L->pos[1], -L->pos[2]);
         Ray r = make_ray(mk3(o4), normalized(negDir));
-        fb.coeff[level & 1][(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product(s, r, (int)k.y);
+        fb.coeff[level & 1][(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product_bvh(s, r, (int)k.y, st);
     }
 }
 
@@ -569,15 +573,19 @@ __global__ void __launch_bounds__(128) k_batch_shadow(DevScene s, const float* p
     }
 }
 
-__global__ void __launch_bounds__(128) k_batch_shadow_directional(DevScene s, const float* pos, const int* self_object,
-                                                                  const float* lightdir4, long long n, float* out) {
+__global__ void __launch_bounds__(128) k_batch_shadow_directional(const __grid_constant__ DevScene s, const float* pos,
+                                                                  const int* self_object, const float* lightdir4,
+                                                                  long long n, float* out, int literal) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         f3 p = mk3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
         f3 negDir = mk3(-lightdir4[4 * i], -lightdir4[4 * i + 1], -lightdir4[4 * i + 2]);
         int so = self_object[i];
         int self_prim = (so >= 0 && so < s.n_prims) ? __ldg(s.object_prim + so) : -1;
         Ray r = make_ray(p, normalized(negDir));
-        out[i] = directional_product(s, r, self_prim);
+        out[i] = literal ? directional_product(s, r, self_prim) : directional_product_bvh(s, r, self_prim, st);
     }
 }
 

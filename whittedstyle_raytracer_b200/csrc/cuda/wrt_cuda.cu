@@ -309,7 +309,7 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         }
         if (ds.n_dir_lights > 0) {
             LaunchScope ls(c, ss, F_SHADOW_DIR);
-            k_shadow_directional<<<wide_grid, TB, 0, ss>>>(ds, fb, d);
+            k_shadow_directional<<<wide_grid, TB, sb, ss>>>(ds, fb, d);
         }
         {
             LaunchScope ls(c, ss, F_SHADE);
@@ -541,6 +541,9 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     auto t_sah1 = std::chrono::steady_clock::now();
     if (fbvh.nodes.size() != (size_t)s->n_nodes) return fail("wrt_upload_scene: fast BVH build failed");
     if (dev_upload(c, (const float4*)fbvh.nodes.data(), 2 * fbvh.nodes.size(), &ds.fnodes)) return 1;
+    // dilated copy for the directional-shadow loop, which the reference runs without any box test
+    std::vector<WrtNode> dil = fbvh.dilated(1e-3f, 1e-4f);
+    if (dev_upload(c, (const float4*)dil.data(), 2 * dil.size(), &ds.dnodes)) return 1;
     std::vector<float4> geom(3 * (size_t)np), attr(4 * (size_t)np);
     std::vector<int4> ids(np);
     int has_light = 0;
@@ -595,7 +598,8 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     ds.amin = s->amin; ds.amax = s->amax; ds.distmin = s->distmin; ds.distmax = s->distmax;
     c->bvh_depth = tree_depth(s);
     c->stack_rows = std::max(c->bvh_depth, fbvh.max_depth) + 2;
-    if (c->stack_rows > 96) return fail("wrt_upload_scene: acceleration tree deeper than 94 levels");
+    if (c->stack_rows > 90)     // 90 rows x 128 threads x 4 B = 45 KB of dynamic shared memory per CTA
+        return fail("wrt_upload_scene: acceleration tree deeper than 88 levels (degenerate geometry?)");
     CK(cudaStreamSynchronize(c->own_stream));          // host staging vectors go out of scope here
     c->has_scene = true;
     if (getenv("WRT_VERBOSE"))
@@ -713,8 +717,9 @@ int wrt_shadow_directional(WrtContext* c, const float* pos, const int32_t* self_
     CK(cudaMemcpyAsync(c->d_scratch[2], lightdir4, (size_t)n * 16, cudaMemcpyHostToDevice, st));
     int grid = (int)std::min<int64_t>((n + 127) / 128, grid_for(c, 8));
     ++c->launches;
-    wrt::k_batch_shadow_directional<<<grid, 128, 0, st>>>(c->ds, (const float*)c->d_scratch[0], (const int*)c->d_scratch[1],
-                                                          (const float*)c->d_scratch[2], n, (float*)c->d_scratch[3]);
+    wrt::k_batch_shadow_directional<<<grid, 128, stack_bytes(c, 128), st>>>(
+        c->ds, (const float*)c->d_scratch[0], (const int*)c->d_scratch[1], (const float*)c->d_scratch[2], n,
+        (float*)c->d_scratch[3], c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(coeff, c->d_scratch[3], (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

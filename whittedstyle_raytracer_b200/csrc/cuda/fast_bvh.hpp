@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../../include/wrt_scene.h"
@@ -39,8 +40,6 @@ struct FastBvhBuilder {
     std::vector<P> prims;          // indexed by primitive
     std::vector<int> idx;          // permutation of primitive indices, partitioned in place
     std::vector<WrtNode> nodes;
-    std::vector<float> right_area; // scratch
-    std::vector<int> scratch;
     int max_depth = 0;
 
     static float half_area(const float* mn, const float* mx) {
@@ -62,7 +61,6 @@ struct FastBvhBuilder {
         if (n == 0 || s->n_nodes == 0) return;
         prims.resize(n);
         idx.resize(n);
-        right_area.resize(n);
         for (int i = 0; i < s->n_nodes; i++) {
             const WrtNode& nd = s->nodes[i];
             if (nd.link >= 0 || i == 1) continue;            // inner node / padding record
@@ -72,11 +70,12 @@ struct FastBvhBuilder {
             for (int k = 0; k < 3; k++) { q.mn[k] = nd.pmin[k]; q.mx[k] = nd.pmax[k]; q.c[k] = 0.5f * nd.pmin[k] + 0.5f * nd.pmax[k]; }
         }
         for (int i = 0; i < n; i++) idx[i] = i;
-        nodes.reserve(2 * (size_t)n + 2);
-        nodes.resize(2);
-        memset(nodes.data(), 0, 2 * sizeof(WrtNode));
+        // A subtree over k primitives occupies exactly 2k-2 records below its root, so every subtree's
+        // record range is known before it is built: sibling subtrees are built by independent threads
+        // into disjoint ranges of one preallocated array (layout = depth-first, pairs adjacent).
+        nodes.assign(2 * (size_t)n, WrtNode{});
         nodes[1].link = ~0;
-        rec_build(0, 0, n, 0);
+        max_depth = rec_build(0, 0, n, 2, 0);
     }
 
     void set_leaf(int rec, int prim) {
@@ -105,6 +104,7 @@ struct FastBvhBuilder {
         float best_cost = INFINITY;
         int best_axis = -1, best_pos = -1;
         if (n <= 16) {                                        // exact sweep over the three axes
+            float right_area[16];
             int sorted_axis = -1;
             for (int axis = 0; axis < 3; axis++) {
                 if (!(cmx[axis] > cmn[axis])) continue;
@@ -198,19 +198,28 @@ struct FastBvhBuilder {
         return d;
     }
 
-    void rec_build(int rec, int b, int e, int depth) {
-        max_depth = std::max(max_depth, depth);
-        if (e - b == 1) { set_leaf(rec, idx[b]); return; }
+    // Builds the subtree over idx[b,e) into record `rec`; its descendants use records [free, free + 2(e-b) - 2).
+    // Returns the depth of the deepest leaf below (root = `depth`).
+    int rec_build(int rec, int b, int e, int free, int depth) {
+        if (e - b == 1) { set_leaf(rec, idx[b]); return depth; }
         int mid = split(b, e);
-        int pair = (int)nodes.size();
-        nodes.resize(pair + 2);
-        memset(&nodes[pair], 0, 2 * sizeof(WrtNode));
+        const int pair = free;
         nodes[rec].link = pair;
-        rec_build(pair, b, mid, depth + 1);
-        rec_build(pair + 1, mid, e, depth + 1);
+        const int nl = mid - b;
+        const int free_l = pair + 2, free_r = free_l + (2 * nl - 2);
+        int dl = 0, dr = 0;
+        if (e - b >= 2048 && depth < 4) {                      // big subtrees: build the halves concurrently
+            std::thread t([&] { dl = rec_build(pair, b, mid, free_l, depth + 1); });
+            dr = rec_build(pair + 1, mid, e, free_r, depth + 1);
+            t.join();
+        } else {
+            dl = rec_build(pair, b, mid, free_l, depth + 1);
+            dr = rec_build(pair + 1, mid, e, free_r, depth + 1);
+        }
         const WrtNode L = nodes[pair], R = nodes[pair + 1];
         WrtNode& nd = nodes[rec];
         for (int k = 0; k < 3; k++) { nd.pmin[k] = fb_min(L.pmin[k], R.pmin[k]); nd.pmax[k] = fb_max(L.pmax[k], R.pmax[k]); }
+        return dl > dr ? dl : dr;
     }
 };
 

@@ -1,7 +1,10 @@
 // host_api.cpp — C ABI over the host front-end (see include/wrt_host.h).
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <memory>
+#include <thread>
+#include <vector>
 
 #include "../../../include/wrt_host.h"
 #include "../../../include/wrt_tiles.h"
@@ -122,31 +125,50 @@ int wrt_scatter_tiles_host(int width, int height, int tile_w, int tile_h, int wo
 }
 
 // PPMGenerator::writeHeader / writePixel (include/PPMGenerator.hpp:631-646):
-// "P3\nW\nH\n255\n" then "r g b\n" per pixel, row-major.
+// "P3\nW\nH\n255\n" then "r g b\n" per pixel, row-major — byte-identical to `fout << int`.
+// The reference's timer includes this write (src/main.cpp:59-64); at 4K it is 89 MB of text, so the
+// formatter uses a 256-entry digit table and formats row bands on several threads.
 int wrt_write_ppm_p3(const char* path, int width, int height, const uint8_t* rgb) {
     FILE* f = fopen(path, "wb");
     if (!f) { g_err = std::string("cannot open ") + path; return 1; }
-    static const char digits[] = "0123456789";
-    std::vector<char> buf;
-    buf.reserve((size_t)1 << 22);
+    struct Lut { char txt[256][4]; unsigned char len[256]; };
+    static const Lut lut = [] {
+        Lut l;
+        for (int v = 0; v < 256; v++) l.len[v] = (unsigned char)snprintf(l.txt[v], 4, "%d", v);
+        return l;
+    }();
     char hdr[64];
     int hl = snprintf(hdr, sizeof hdr, "P3\n%d\n%d\n255\n", width, height);
-    buf.insert(buf.end(), hdr, hdr + hl);
-    size_t n = (size_t)width * height;
-    for (size_t i = 0; i < n; i++) {
-        for (int k = 0; k < 3; k++) {
-            unsigned v = rgb[i * 3 + k];
-            if (v >= 100) { buf.push_back(digits[v / 100]); v %= 100; buf.push_back(digits[v / 10]); buf.push_back(digits[v % 10]); }
-            else if (v >= 10) { buf.push_back(digits[v / 10]); buf.push_back(digits[v % 10]); }
-            else buf.push_back(digits[v]);
-            buf.push_back(k == 2 ? '\n' : ' ');
+    bool ok = fwrite(hdr, 1, (size_t)hl, f) == (size_t)hl;
+    const size_t npx = (size_t)width * height;
+    const size_t band = (size_t)1 << 20;                        // pixels per task (<= 12 MB of text)
+    const unsigned nthreads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    std::vector<std::vector<char>> bufs(nthreads);
+    for (size_t base = 0; base < npx && ok; base += band * nthreads) {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; t++) {
+            size_t p0 = base + (size_t)t * band, p1 = std::min(npx, p0 + band);
+            bufs[t].clear();
+            if (p0 >= p1) continue;
+            pool.emplace_back([&, t, p0, p1] {
+                std::vector<char>& out = bufs[t];
+                out.resize((p1 - p0) * 12);
+                char* w = out.data();
+                for (size_t i = p0; i < p1; i++) {
+                    for (int k = 0; k < 3; k++) {
+                        unsigned v = rgb[i * 3 + k];
+                        memcpy(w, lut.txt[v], 4);               // copies up to 3 digits (+1 byte overwritten next)
+                        w += lut.len[v];
+                        *w++ = k == 2 ? '\n' : ' ';
+                    }
+                }
+                out.resize((size_t)(w - out.data()));
+            });
         }
-        if (buf.size() > ((size_t)1 << 22) - 16) {
-            if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); g_err = "short write"; return 1; }
-            buf.clear();
-        }
+        for (auto& th : pool) th.join();
+        for (unsigned t = 0; t < nthreads && ok; t++)
+            if (!bufs[t].empty()) ok = fwrite(bufs[t].data(), 1, bufs[t].size(), f) == bufs[t].size();
     }
-    bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
     ok = (fclose(f) == 0) && ok;
     if (!ok) { g_err = "short write"; return 1; }
     return 0;

@@ -23,6 +23,7 @@ struct DevScene {
     const float4* dnodes;     // the SAH tree with every box dilated: conservative culling for the box-free
                               // directional-shadow loop (Renderer.hpp:381-400)
     const float4* geom;
+    const float4* prim_box;   // per prim {pMin.xyz, 0} {pMax.xyz, 0}: the primitive's own (leaf) box, for the occluder cache
     const float4* attr;       // per prim 4x float4: {n0,uv0.x} {n1,uv0.y} {n2,uv1.x} {uv1.y,uv2.x,uv2.y,0}
     const int4*   ids;        // per prim {material, texture, normalmap, object}
     const int*    object_prim;
@@ -298,6 +299,17 @@ __device__ __forceinline__ bool occluded_begin(const DevScene& s, const float4* 
 __device__ __forceinline__ void occluded_leaf(const DevScene& s, const Ray& r, float dis, int p, bool& occ) {
     PrimHit h; float oma; unsigned fl;
     if (prim_test(s, p, r, h, oma, fl) && h.t < dis) occ = true;
+}
+
+// Occluder cache: the primitive that blocked this lane's previous shadow ray is tried first.  The
+// any-hit answer is an OR over primitives of (own box hit && intersection accepted && t < dis), so
+// testing one of them early is only a reordering; the own-box test keeps the predicate exact.
+__device__ __forceinline__ bool occluder_cache_hit(const DevScene& s, const Ray& r, float dis, int p) {
+    float te;
+    const float4* b = s.prim_box + 2 * (size_t)p;
+    if (!slab(ldg4(b), ldg4(b + 1), r, te)) return false;
+    PrimHit h; float oma; unsigned fl;
+    return prim_test(s, p, r, h, oma, fl) && h.t < dis;
 }
 
 __device__ __forceinline__ bool occluded(const DevScene& s, const float4* nodes, const Ray& r, float dis, Stack& st) {

@@ -370,8 +370,10 @@ struct SoftShadowQuery {
     bool occ;
     unsigned out;
     int par;
-    __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_, int level)
-        : s(s_), fb(fb_), seed(seed_), par(level & 1) {}
+    int last_occ;              // occluder cache: primitive that blocked this lane's previous ray, or -1
+    bool use_cache;
+    __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_, int level, bool cache)
+        : s(s_), fb(fb_), seed(seed_), par(level & 1), last_occ(-1), use_cache(cache && !s_.has_light_prims) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack& st) {
         unsigned req = (unsigned)(item / WRT_SOFT_SAMPLES);
         unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
@@ -394,12 +396,20 @@ struct SoftShadowQuery {
         dis = norm(lightPos - orig);
         r = make_ray(orig, raydir);
         out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
-        nodes = degenerate_dir(raydir) ? s.nodes : s.fnodes;
+        const bool degenerate = degenerate_dir(raydir);
+        nodes = degenerate ? s.nodes : s.fnodes;
+        if (use_cache && last_occ >= 0 && !degenerate) {
+            if (occluder_cache_hit(s, r, dis, last_occ)) { occ = true; return false; }
+            last_occ = -1;                                   // stale: do not pay for it again
+        }
         return occluded_begin(s, nodes, r, dis, st, cur, occ);
     }
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
         const float never = INFINITY;
-        bool more = traverse_step<true>(nodes, r, st, cur, never, [&](int p) { occluded_leaf(s, r, dis, p, occ); });
+        bool more = traverse_step<true>(nodes, r, st, cur, never, [&](int p) {
+            occluded_leaf(s, r, dis, p, occ);
+            if (occ) last_occ = p;
+        });
         return more && !occ;
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
@@ -409,12 +419,12 @@ struct SoftShadowQuery {
 };
 
 __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
-                                                     unsigned seed, int refill) {
+                                               unsigned seed, int refill, int occluder_cache) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    SoftShadowQuery q(s, fb, seed, level);
+    SoftShadowQuery q(s, fb, seed, level, occluder_cache != 0);
     run_queue(q, (unsigned long long)nreq * WRT_SOFT_SAMPLES, reinterpret_cast<unsigned long long*>(fb.counters + work_slot),
               st, refill);
 }

@@ -71,6 +71,7 @@ struct WrtContext {
     bool kernel_timing = false;
     int refill = 16;                   // idle lanes that trigger a refill on deep ray-tree levels
     int refill_soft = 24;
+    int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
     int smem_rows_cap = 64;
     int trace_blocks_per_sm = 10;
@@ -304,7 +305,8 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
                 k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), d == 0 ? c->refill0 : c->refill);
             } else {
                 LaunchScope ls(c, ss, F_SHADOW_SOFT);
-                k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft);
+                k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft,
+                                                          d >= c->cache_from_level ? 1 : 0);
             }
         }
         if (ds.n_dir_lights > 0) {
@@ -493,6 +495,7 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_REFILL_SOFT")) c->refill_soft = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_TRACE_BLOCKS")) c->trace_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_OVERLAP")) c->overlap = atoi(e) != 0;
+    if (const char* e = getenv("WRT_CACHE_FROM")) c->cache_from_level = atoi(e);
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));
     *out = c;
@@ -575,6 +578,16 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         mats[3 * (size_t)i + 1] = make_float4(m.specular[0], m.specular[1], m.specular[2], m.kd);
         mats[3 * (size_t)i + 2] = make_float4(m.ks, m.n, m.alpha, m.eta);
     }
+    std::vector<float4> pbox(2 * (size_t)np, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < s->n_nodes; i++) {
+        const WrtNode& nd = s->nodes[i];
+        if (nd.link >= 0 || i == 1) continue;
+        int p = ~nd.link;
+        if (p < 0 || p >= np) continue;
+        pbox[2 * (size_t)p] = make_float4(nd.pmin[0], nd.pmin[1], nd.pmin[2], 0.f);
+        pbox[2 * (size_t)p + 1] = make_float4(nd.pmax[0], nd.pmax[1], nd.pmax[2], 0.f);
+    }
+    if (dev_upload(c, pbox.data(), pbox.size(), &ds.prim_box)) return 1;
     if (dev_upload(c, geom.data(), geom.size(), &ds.geom)) return 1;
     if (dev_upload(c, attr.data(), attr.size(), &ds.attr)) return 1;
     if (dev_upload(c, ids.data(), ids.size(), &ds.ids)) return 1;

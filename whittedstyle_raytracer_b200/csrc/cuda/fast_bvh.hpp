@@ -173,6 +173,27 @@ struct FastBvhBuilder {
         return m;
     }
 
+    // Eight copies of the tree, one per ray-direction octant (bit 0: d.x < 0, bit 1: d.y < 0, bit 2: d.z < 0),
+    // with each record's planes pre-swapped into {entry planes}{exit planes} for that octant.
+    std::vector<WrtNode> octant_copies() const { return octant_copies_of(nodes.data(), nodes.size()); }
+    static std::vector<WrtNode> octant_copies_of(const WrtNode* nodes, size_t n_nodes) {
+        struct View { const WrtNode* p; size_t n; size_t size() const { return n; } const WrtNode& operator[](size_t i) const { return p[i]; } };
+        View nodes_v{nodes, n_nodes};
+        return octant_copies_impl(nodes_v);
+    }
+    template <class NodesT>
+    static std::vector<WrtNode> octant_copies_impl(const NodesT& nodes) {
+        std::vector<WrtNode> o(8 * nodes.size());
+        for (int oct = 0; oct < 8; oct++)
+            for (size_t i = 0; i < nodes.size(); i++) {
+                WrtNode nd = nodes[i];
+                for (int k = 0; k < 3; k++)
+                    if (oct & (1 << k)) { float t = nd.pmin[k]; nd.pmin[k] = nd.pmax[k]; nd.pmax[k] = t; }
+                o[(size_t)oct * nodes.size() + i] = nd;
+            }
+        return o;
+    }
+
     // Copy of the tree whose leaf boxes are grown by rel * (largest extent, largest |coordinate|) + abs
     // on every side and whose inner boxes are the unions of those: a conservative culling structure
     // for queries the reference answers without boxes.

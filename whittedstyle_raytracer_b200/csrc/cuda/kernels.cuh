@@ -167,12 +167,19 @@ struct ClosestQuery {
         if (s.n_nodes == 0) return false;
         r = make_ray(mk3(o), mk3(d));
         float prune = prune_cfg;
-        nodes = pick_tree(s, r.d, prune);
+        const bool ref_tree = prune < 0.f || degenerate_dir(r.d);       // literal walk / axis-degenerate ray
+        if (ref_tree) prune = -1.f;
+        nodes = (ref_tree ? s.ronodes : s.onodes) + (size_t)ray_octant(r.d) * 2 * (size_t)s.n_nodes;
         cs.prune_rel = prune;
-        return cs.begin(s, nodes, 0, r, cur);
+        float te;
+        float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
+        if (!slab_presorted(lo, hi, r, te)) return false;
+        cur = __float_as_int(lo.w);
+        if (cur < 0) { cs.leaf(s, r, ~cur); return false; }
+        return true;
     }
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
-        return traverse_step<true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
+        return traverse_step<true, true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
         fb.hit[idx] = make_float4(cs.best.t, __int_as_float(cs.best.prim), cs.best.u, cs.best.v);
@@ -329,17 +336,17 @@ struct HardShadowQuery {
         out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
         res = 1.f;
         if (s.n_nodes == 0) return false;
-        nodes = degenerate_dir(raydir) ? s.nodes : s.fnodes;
+        nodes = (degenerate_dir(raydir) ? s.ronodes : s.onodes) + (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
         float te;
         float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
-        if (!slab(lo, hi, r, te)) return false;
+        if (!slab_presorted(lo, hi, r, te)) return false;
         cur = __float_as_int(lo.w);
         if (cur < 0) { shadow_leaf(s, r, dis, ~cur, res); return false; }
         return true;
     }
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
         const float never = INFINITY;
-        bool more = traverse_step<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
+        bool more = traverse_step<false, true>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
         return more && res != 0.f;
     }
     __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[par][out] = res; return false; }
@@ -397,7 +404,9 @@ struct SoftShadowQuery {
         r = make_ray(orig, raydir);
         out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
         const bool degenerate = degenerate_dir(raydir);
-        nodes = degenerate ? s.nodes : s.fnodes;
+        // octant copy: ray_octant() uses `d < 0` exactly like the reference's swap, so +-0 components pick the
+        // unswapped planes and the presorted slab test equals BoundBox::IntersectRay for every ray
+        nodes = (degenerate ? s.ronodes : s.onodes) + (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
         if (use_cache && last_occ >= 0 && !degenerate) {
             if (occluder_cache_hit(s, r, dis, last_occ)) { occ = true; return false; }
             last_occ = -1;                                   // stale: do not pay for it again
@@ -406,10 +415,11 @@ struct SoftShadowQuery {
     }
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
         const float never = INFINITY;
-        bool more = traverse_step<true>(nodes, r, st, cur, never, [&](int p) {
+        auto leaf = [&](int p) {
             occluded_leaf(s, r, dis, p, occ);
             if (occ) last_occ = p;
-        });
+        };
+        bool more = traverse_step<true, true>(nodes, r, st, cur, never, leaf);
         return more && !occ;
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {

@@ -544,6 +544,12 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     auto t_sah1 = std::chrono::steady_clock::now();
     if (fbvh.nodes.size() != (size_t)s->n_nodes) return fail("wrt_upload_scene: fast BVH build failed");
     if (dev_upload(c, (const float4*)fbvh.nodes.data(), 2 * fbvh.nodes.size(), &ds.fnodes)) return 1;
+    {
+        std::vector<WrtNode> oct = fbvh.octant_copies();
+        if (dev_upload(c, (const float4*)oct.data(), 2 * oct.size(), &ds.onodes)) return 1;
+        oct = wrt::FastBvhBuilder::octant_copies_of(s->nodes, (size_t)s->n_nodes);
+        if (dev_upload(c, (const float4*)oct.data(), 2 * oct.size(), &ds.ronodes)) return 1;
+    }
     // dilated copy for the directional-shadow loop, which the reference runs without any box test
     std::vector<WrtNode> dil = fbvh.dilated(1e-3f, 1e-4f);
     if (dev_upload(c, (const float4*)dil.data(), 2 * dil.size(), &ds.dnodes)) return 1;

@@ -131,11 +131,13 @@ def load_cuda() -> C.CDLL:
     """Loads the CUDA render core.  Raises when it is not built — there is no fallback."""
     global _cuda
     if _cuda is None:
-        if not CUDA_LIB.exists():
+        import os
+        lib_path = Path(os.environ.get("WRT_CUDA_LIB", CUDA_LIB))      # A/B builds during development
+        if not lib_path.exists():
             raise RuntimeError(
                 f"{CUDA_LIB} is not built (nvcc -gencode arch=compute_100a,code=sm_100a); "
                 "this package has no CPU fallback — run __graft_entry__.build()")
-        lib = C.CDLL(str(CUDA_LIB))
+        lib = C.CDLL(str(lib_path))
         vp, i32, i64, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32
         lib.wrt_create.argtypes = [i32, C.POINTER(vp)]
         lib.wrt_destroy.argtypes = [vp]

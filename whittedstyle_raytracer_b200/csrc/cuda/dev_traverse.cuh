@@ -415,17 +415,27 @@ __device__ __forceinline__ float directional_product_bvh(const DevScene& s, cons
 //             bool step(cur, st)         — one traversal step; false = finished
 //             bool finish(cur, st)       — a walk ended: write results, or start the item's next
 //                                          walk (soft-shadow sample pairs) and return true
+#ifndef WRT_CHUNK_MIN_PER
+#define WRT_CHUNK_MIN_PER 256
+#endif
+
 template <class Q>
-__device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned long long* work, Stack& st, int refill) {
+__device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned long long* work, Stack& st, int refill_cfg) {
+    const int refill = refill_cfg & 0xff;
+    const unsigned chunk_div = (unsigned)(refill_cfg >> 8);     // 0: one claim per refill; k: chunks of n / (warps * k)
+
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     // Work is claimed from the global counter in chunks and handed out to idle lanes from the warp's
     // private range: one atomic per `chunk` items instead of one per refill.  (ncu, v5: 27 % of the
     // level-0 stall samples sat on the SHFL behind this atomic — 13 M single-address atomics per frame.)
-    // Small queues keep 32-item chunks so every warp still gets work.
+
     unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
-    unsigned long long per = n / (warps * 16ull);      // >= 16 chunks per warp: the tail stays below ~3 %
-    const unsigned chunk = per >= 256 ? 256u : (per >= 32 ? (unsigned)(per & ~31ull) : 32u);
+    unsigned long long per = chunk_div ? n / (warps * (unsigned long long)chunk_div) : 0;
+    // Short queues claim exactly what a refill needs (A/B on one rank's 1/8 share of the 4K frame:
+    // 6.5 ms vs 7.1 ms with chunks — chunk tails dominate there); long ones claim 256 items at a time
+    // (full frame: 45.1 ms vs 47.7 ms without chunks — the claim atomic was the limiter).
+    const bool chunked = per >= (unsigned long long)WRT_CHUNK_MIN_PER;
     unsigned long long loc_next = 0, loc_end = 0;      // warp-uniform private range
     bool active = false, drained = false;
     int cur = 0;
@@ -437,11 +447,12 @@ __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned l
             unsigned long long first = loc_next, second = 0;   // items [first, first+avail) then [second, ...)
             if (avail < cnt) {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(work, (unsigned long long)chunk);
+                const unsigned claim = chunked ? 256u : cnt - (unsigned)avail;
+                if (lane == 0) base = atomicAdd(work, (unsigned long long)claim);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 second = base;
                 loc_next = base + (cnt - avail);
-                loc_end = base + chunk;
+                loc_end = base + claim;
                 if (base >= n) drained = true;           // nothing left behind this chunk either
             } else {
                 loc_next += cnt;

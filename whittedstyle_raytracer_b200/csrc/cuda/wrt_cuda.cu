@@ -72,6 +72,7 @@ struct WrtContext {
     int refill = 16;                   // idle lanes that trigger a refill on deep ray-tree levels
     int refill_soft = 24;
     int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
+    int chunk_div = 16;                // work claiming: 0 = one atomic per refill, k = chunks of n/(warps*k) items
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
     int smem_rows_cap = 64;
     int trace_blocks_per_sm = 10;
@@ -289,7 +290,7 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         if (overlap && d >= 2) CK(cudaStreamWaitEvent(st, c->ev_shade[d - 2], 0));   // parity buffers free again
         {
             LaunchScope ls(c, st, F_TRACE);
-            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, d == 0 ? c->refill0 : c->refill);
+            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8));
         }
         {
             LaunchScope ls(c, st, F_SURFACE);
@@ -302,10 +303,10 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         if (ds.n_point_lights > 0) {
             if (ds.shadow_type == 0) {
                 LaunchScope ls(c, ss, F_SHADOW_HARD);
-                k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), d == 0 ? c->refill0 : c->refill);
+                k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8));
             } else {
                 LaunchScope ls(c, ss, F_SHADOW_SOFT);
-                k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft,
+                k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
                                                           d >= c->cache_from_level ? 1 : 0);
             }
         }
@@ -496,6 +497,7 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_TRACE_BLOCKS")) c->trace_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("WRT_CACHE_FROM")) c->cache_from_level = atoi(e);
+    if (const char* e = getenv("WRT_CHUNK_DIV")) c->chunk_div = std::max(0, std::min(255, atoi(e)));
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));
     *out = c;

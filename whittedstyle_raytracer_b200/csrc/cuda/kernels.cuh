@@ -47,20 +47,26 @@ struct TileMap : WrtTileMap {     // include/wrt_tiles.h
     }
 };
 
+#ifndef WRT_SIDE_STREAMS
+#define WRT_SIDE_STREAMS 2
+#endif
+#define WRT_SETS (WRT_SIDE_STREAMS + 1)
+
 struct FrameBuffers {
     float4* ray_o[2];            // {o.xyz, pixel id}
     float4* ray_d[2];            // {d.xyz, path id}
     float4* hit;                 // {t, prim, b1, b2}
-    float4* surf[2];             // by level parity, 4 per node: {pos, prim} {nDir, material} {Od, -} {ray origin, -}
+    float4* surf[WRT_SETS];      // by level % WRT_SETS, 4 per node: {pos, prim} {nDir, material} {Od, -} {ray origin, -}
     float4* node_a[WRT_MAX_DEPTH];   // {local.rgb -> colour.rgb, fr}
     float4* node_b[WRT_MAX_DEPTH];   // {kT, childR, childT, composite flag}
-    // shadow requests and coefficients are double-buffered by level parity so that the shadow + shade
-    // kernels of level d (side stream) overlap the closest-hit + surface kernels of level d+1
-    float4* preq_o[2];           // point-light request: {shadow ray origin, node}
-    uint4*  preq_k[2];           //                      {light, pixel, path, -}
-    float4* dreq_o[2];           // directional request: {pos, node}
-    uint4*  dreq_k[2];           //                      {light, self prim, -, -}
-    float*  coeff[2];            // [node * n_lights + light]
+    // Shadow requests, coefficients and surface records exist in WRT_SETS copies indexed by level % WRT_SETS:
+    // shadow + shade of level d run on side stream d % WRT_SIDE_STREAMS, beside closest-hit + surface of level d+1 (main
+    // stream) and beside the straggling long rays of level d-1's shadow kernel (the other side stream).
+    float4* preq_o[WRT_SETS];    // point-light request: {shadow ray origin, node}
+    uint4*  preq_k[WRT_SETS];    //                      {light, pixel, path, -}
+    float4* dreq_o[WRT_SETS];    // directional request: {pos, node}
+    uint4*  dreq_k[WRT_SETS];    //                      {light, self prim, -, -}
+    float*  coeff[WRT_SETS];     // [node * n_lights + light]
     unsigned* counters;
     unsigned cap;                // capacity of every per-level array
     unsigned preq_cap, dreq_cap;
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
                         Od = texture_at(s, s.textures + sf.textureIndex, sf.u, sf.v);      // :176-180
                     if (sf.normalMapIndex != -1) sf.nDir = change_normal_dir(s, sf);        // :182-184
                     pos = sf.pos; nDir = sf.nDir;
-                    float4* sv = fb.surf[level & 1] + 4 * (size_t)i;
+                    float4* sv = fb.surf[level % WRT_SETS] + 4 * (size_t)i;
                     sv[0] = make_float4(pos.x, pos.y, pos.z, __int_as_float(prim));
                     sv[1] = make_float4(nDir.x, nDir.y, nDir.z, __int_as_float(sf.material));
                     sv[2] = make_float4(Od.x, Od.y, Od.z, 0.f);
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
                 }
             }
         }
-        if (live && !shade) fb.surf[level & 1][4 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (live && !shade) fb.surf[level % WRT_SETS][4 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         // child rays: reflections into the first half of the next level, transmissions into the second
         unsigned rslot = warp_alloc(fb.counters + C_NRAYS + level + 1, spawnR ? 1 : 0, child_half, overflow);
         unsigned tslot = warp_alloc(fb.counters + C_NTRAYS + level + 1, spawnT ? 1 : 0, fb.cap - child_half, overflow);
@@ -293,15 +299,15 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
         if (shade) {
             f3 sorig = pos + 0.0005f * nDir;                               // BVHStrategy.hpp:15, Renderer.hpp:349
             for (int li = 0; li < s.n_lights; li++) {
-                fb.coeff[level & 1][(size_t)i * s.n_lights + li] = 0.f;
+                fb.coeff[level % WRT_SETS][(size_t)i * s.n_lights + li] = 0.f;
                 bool point = float_equal(s.lights[li].pos[3], 1.f);
                 if (point && pslot != 0xffffffffu) {
-                    fb.preq_o[level & 1][pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(i));
-                    fb.preq_k[level & 1][pslot] = make_uint4((unsigned)li, pixel, path, 0u);
+                    fb.preq_o[level % WRT_SETS][pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(i));
+                    fb.preq_k[level % WRT_SETS][pslot] = make_uint4((unsigned)li, pixel, path, 0u);
                     ++pslot;
                 } else if (!point && dslot != 0xffffffffu) {
-                    fb.dreq_o[level & 1][dslot] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(i));
-                    fb.dreq_k[level & 1][dslot] = make_uint4((unsigned)li, (unsigned)prim, 0u, 0u);
+                    fb.dreq_o[level % WRT_SETS][dslot] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(i));
+                    fb.dreq_k[level % WRT_SETS][dslot] = make_uint4((unsigned)li, (unsigned)prim, 0u, 0u);
                     ++dslot;
                 }
             }
@@ -323,7 +329,7 @@ struct HardShadowQuery {
     unsigned out;
     int par;
     __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int level)
-        : s(s_), fb(fb_), par(level & 1) {}
+        : s(s_), fb(fb_), par(level % WRT_SETS) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
         float4 o4 = fb.preq_o[par][item];
         uint4 k = fb.preq_k[par][item];
@@ -380,7 +386,7 @@ struct SoftShadowQuery {
     int last_occ;              // occluder cache: primitive that blocked this lane's previous ray, or -1
     bool use_cache;
     __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_, int level, bool cache)
-        : s(s_), fb(fb_), seed(seed_), par(level & 1), last_occ(-1), use_cache(cache && !s_.has_light_prims) {}
+        : s(s_), fb(fb_), seed(seed_), par(level % WRT_SETS), last_occ(-1), use_cache(cache && !s_.has_light_prims) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack& st) {
         unsigned req = (unsigned)(item / WRT_SOFT_SAMPLES);
         unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
@@ -447,12 +453,12 @@ __global__ void __launch_bounds__(128) k_shadow_directional(const __grid_constan
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned n = queue_len(fb.counters, C_NDREQ + level, fb.dreq_cap);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o4 = fb.dreq_o[level & 1][i];
-        uint4 k = fb.dreq_k[level & 1][i];
+        float4 o4 = fb.dreq_o[level % WRT_SETS][i];
+        uint4 k = fb.dreq_k[level % WRT_SETS][i];
         const WrtLight* L = s.lights + k.x;
         f3 negDir = mk3(-L->pos[0], -L->pos[1], -L->pos[2]);
         Ray r = make_ray(mk3(o4), normalized(negDir));
-        fb.coeff[level & 1][(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product_bvh(s, r, (int)k.y, st);
+        fb.coeff[level % WRT_SETS][(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product_bvh(s, r, (int)k.y, st);
     }
 }
 
@@ -463,13 +469,13 @@ __global__ void __launch_bounds__(256) k_shade(DevScene s, FrameBuffers fb, int 
     const unsigned n = span.count();
     for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
         const unsigned i = span.slot(item);
-        const float4* sv = fb.surf[level & 1] + 4 * (size_t)i;
+        const float4* sv = fb.surf[level % WRT_SETS] + 4 * (size_t)i;
         float4 s0 = sv[0];
         if (__float_as_int(s0.w) < 0) continue;
         float4 s1 = sv[1], s2 = sv[2], s3 = sv[3];
         Mtl m = load_material(s, __float_as_int(s1.w));
         m.diffuse = mk3(s2);
-        f3 local = blinn_phong(s, mk3(s3), mk3(s0), mk3(s1), m, fb.coeff[level & 1] + (size_t)i * s.n_lights);
+        f3 local = blinn_phong(s, mk3(s3), mk3(s0), mk3(s1), m, fb.coeff[level % WRT_SETS] + (size_t)i * s.n_lights);
         float4 na = fb.node_a[level][i];
         na.x = local.x; na.y = local.y; na.z = local.z;
         fb.node_a[level][i] = na;

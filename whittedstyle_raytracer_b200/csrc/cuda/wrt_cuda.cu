@@ -46,7 +46,7 @@ struct WrtContext {
     int device = 0;
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
-    cudaStream_t side_stream = nullptr;       // shadow + shade kernels of level d, concurrent with level d+1
+    cudaStream_t side_stream[WRT_SIDE_STREAMS] = {};    // shadow + shade kernels of level d run on side_stream[d % WRT_SIDE_STREAMS]
     cudaEvent_t ev_surface[WRT_MAX_DEPTH] = {}, ev_shade[WRT_MAX_DEPTH] = {};
     bool overlap = true;
 
@@ -199,12 +199,12 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
         if (frame_alloc(c, &fb.ray_d[k], cap)) return 1;
     }
     if (frame_alloc(c, &fb.hit, cap)) return 1;
-    for (int k = 0; k < 2; k++) if (frame_alloc(c, &fb.surf[k], 4 * (size_t)cap)) return 1;
+    for (int k = 0; k < WRT_SETS; k++) if (frame_alloc(c, &fb.surf[k], 4 * (size_t)cap)) return 1;
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
         if (frame_alloc(c, &fb.node_a[d], cap)) return 1;
         if (frame_alloc(c, &fb.node_b[d], cap)) return 1;
     }
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < WRT_SETS; k++) {
         if (frame_alloc(c, &fb.preq_o[k], ds.n_point_lights ? fb.preq_cap : 1)) return 1;
         if (frame_alloc(c, &fb.preq_k[k], ds.n_point_lights ? fb.preq_cap : 1)) return 1;
         if (frame_alloc(c, &fb.dreq_o[k], ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
@@ -281,13 +281,16 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         LaunchScope ls(c, st, F_RAYGEN);
         k_raygen<<<wide_grid, 256, 0, st>>>(c->cam, tm, slot0, n, fb);
     }
-    // Level d: closest hit + surface on the caller's stream; its shadow + shade kernels on the side
-    // stream, overlapping level d+1's closest hit + surface (they only need surface(d)'s output, and
-    // the request / coefficient / surface buffers alternate by level parity).
+    // Level d: closest hit + surface on the caller's stream; its shadow + shade kernels on side stream
+    // d % WRT_SIDE_STREAMS.  They overlap level d+1's closest hit + surface (which only need surface(d)'s output) and the
+    // tail of level d-1's shadow kernel on the other side stream: a persistent traversal kernel ends with
+    // its longest ray (hundreds of node steps along the bunny's silhouette, ~150 us measured per launch),
+    // during which the SMs would otherwise idle.  Request / coefficient / surface buffers rotate over
+    // WRT_SETS levels.
     const bool overlap = c->overlap && !c->kernel_timing;
-    cudaStream_t ss = overlap ? c->side_stream : st;
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
-        if (overlap && d >= 2) CK(cudaStreamWaitEvent(st, c->ev_shade[d - 2], 0));   // parity buffers free again
+        cudaStream_t ss = overlap ? c->side_stream[d % WRT_SIDE_STREAMS] : st;
+        if (overlap && d >= WRT_SETS) CK(cudaStreamWaitEvent(st, c->ev_shade[d - WRT_SETS], 0));   // buffer set free again
         {
             LaunchScope ls(c, st, F_TRACE);
             k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8));
@@ -320,10 +323,8 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         }
         if (overlap) CK(cudaEventRecord(c->ev_shade[d], ss));
     }
-    if (overlap) {
-        CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - 2], 0));
-        CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - 1], 0));
-    }
+    if (overlap)
+        for (int k = 1; k <= WRT_SIDE_STREAMS; k++) CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - k], 0));
     {
         LaunchScope ls(c, st, F_COMBINE);
         void* args[] = {(void*)&fb, (void*)&tm, (void*)&slot0, (void*)&n, (void*)&d_image, (void*)&d_packed};
@@ -472,7 +473,9 @@ int wrt_create(int device, WrtContext** out) {
     WrtContext* c = new WrtContext();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    bool ev_ok = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) == cudaSuccess;
+    bool ev_ok = true;
+    for (int k = 0; k < WRT_SIDE_STREAMS && ev_ok; k++)
+        ev_ok = cudaStreamCreateWithFlags(&c->side_stream[k], cudaStreamNonBlocking) == cudaSuccess;
     for (int d = 0; d < WRT_MAX_DEPTH && ev_ok; d++)
         ev_ok = cudaEventCreateWithFlags(&c->ev_surface[d], cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&c->ev_shade[d], cudaEventDisableTiming) == cudaSuccess;
@@ -521,7 +524,7 @@ void wrt_destroy(WrtContext* c) {
         if (c->ev_surface[d]) cudaEventDestroy(c->ev_surface[d]);
         if (c->ev_shade[d]) cudaEventDestroy(c->ev_shade[d]);
     }
-    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    for (int k = 0; k < WRT_SIDE_STREAMS; k++) if (c->side_stream[k]) cudaStreamDestroy(c->side_stream[k]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

@@ -328,8 +328,9 @@ struct HardShadowQuery {
     float dis, res;
     unsigned out;
     int par;
-    __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int level)
-        : s(s_), fb(fb_), par(level % WRT_SETS) {}
+    bool literal;              // WRT_TRAVERSAL_EXHAUSTIVE: walk the reference-topology tree (its left-to-right product order)
+    __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int level, bool literal_)
+        : s(s_), fb(fb_), par(level % WRT_SETS), literal(literal_) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
         float4 o4 = fb.preq_o[par][item];
         uint4 k = fb.preq_k[par][item];
@@ -342,7 +343,7 @@ struct HardShadowQuery {
         out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
         res = 1.f;
         if (s.n_nodes == 0) return false;
-        nodes = (degenerate_dir(raydir) ? s.ronodes : s.onodes) + (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
+        nodes = ((literal || degenerate_dir(raydir)) ? s.ronodes : s.onodes) + (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
         float te;
         float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
         if (!slab_presorted(lo, hi, r, te)) return false;
@@ -358,12 +359,13 @@ struct HardShadowQuery {
     __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[par][out] = res; return false; }
 };
 
-__global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill) {
+__global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill,
+                                                     int literal) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned n = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    HardShadowQuery q(s, fb, level);
+    HardShadowQuery q(s, fb, level, literal != 0);
     run_queue(q, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
 }
 

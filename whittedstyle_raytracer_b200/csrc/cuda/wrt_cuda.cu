@@ -306,7 +306,8 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         if (ds.n_point_lights > 0) {
             if (ds.shadow_type == 0) {
                 LaunchScope ls(c, ss, F_SHADOW_HARD);
-                k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8));
+                k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8),
+                                                          c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
             } else {
                 LaunchScope ls(c, ss, F_SHADOW_SOFT);
                 k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),

@@ -269,6 +269,28 @@ def test_directional_light_on_bunny(workdir):
     assert 0.02 < (want < 1).mean() < 0.98
 
 
+def test_large_triangle_soup(workdir):
+    """60 000 random triangles (12x the bunny): thread-parallel SAH build, deeper trees and stacks.
+    GPU image == oracle (which walks the reference-topology tree exhaustively, ~250 box tests per ray)."""
+    rng = np.random.default_rng(5)
+    n = 60000
+    c = rng.uniform(-8, 8, (n, 3))
+    c[:, 2] -= 6
+    lines = ["imsize 200 150", "eye 0 1 10", "viewdir 0 -0.1 -1", "hfov 60", "updir 0 1 0", "bkgcolor 0.2 0.3 0.5 1.0",
+             "light 5 20 10 1 1 1 1", "mtlcolor 0.7 0.6 0.5 1 1 1 0.2 0.7 0.3 20 0.6 1.3"]
+    tri = c[:, None, :] + rng.uniform(-0.12, 0.12, (n, 3, 3))
+    lines += ["v %.4f %.4f %.4f" % tuple(q) for q in tri.reshape(-1, 3)]
+    lines += ["f %d %d %d" % (3 * i + 1, 3 * i + 2, 3 * i + 3) for i in range(n)]
+    scene = Scene(text="\n".join(lines) + "\n", asset_dir=workdir)
+    assert scene.n_prims == n
+    ref, ost = ob.OracleScene(scene).render()
+    for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
+        img, st = gpu_render(scene, traversal)
+        d = image_diff(img, ref)
+        assert d["exact"] >= 0.999 * d["n"] and d["within1"] >= 0.9999 * d["n"], (traversal, d)
+        assert st["closest_rays"] == ost.closest_rays and st["shadow_rays"] == ost.shadow_rays
+
+
 def test_render_is_deterministic_and_reusable(workdir):
     scene, _ = load_golden_scene(workdir, "water_small")
     r = Renderer(scene)

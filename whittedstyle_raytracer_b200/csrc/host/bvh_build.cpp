@@ -26,6 +26,8 @@ struct Builder {
     HostScene& s;
     std::vector<int> order;      // object indices, permuted in place
     std::vector<int> leaf_objs;  // objects in DFS leaf order
+    std::vector<float> cen;      // box centroids, 3 per object (same floats the reference recomputes in its comparator)
+    std::vector<float> box;      // pMin, pMax per object, 6 floats: keeps the union loops out of the 200-byte Object records
     int max_depth = 0;
 
     explicit Builder(HostScene& hs) : s(hs) {}
@@ -49,14 +51,13 @@ struct Builder {
             return;
         }
         if (n > 2) {
-            V3 mn = s.objList[order[b]].bmin, mx = s.objList[order[b]].bmax;
-            unite(mn, mx, s.objList[order[b + 1]]);
-            for (int i = b + 2; i < e; i++) unite(mn, mx, s.objList[order[i]]);
+            const float* b0 = &box[6 * (size_t)order[b]];
+            V3 mn(b0[0], b0[1], b0[2]), mx(b0[3], b0[4], b0[5]);
+            for (int i = b + 1; i < e; i++) unite(mn, mx, &box[6 * (size_t)order[i]]);
             V3 d = mx - mn;                                        // BoundBox.hpp:41-50
             int axis = (d.x > d.y && d.x > d.z) ? 0 : (d.y > d.z ? 1 : 2);
-            const std::vector<Object>& objs = s.objList;
-            std::sort(order.begin() + b, order.begin() + e,
-                      [&objs, axis](int a, int c) { return centroid(objs[a], axis) < centroid(objs[c], axis); });
+            const float* cp = cen.data() + axis;
+            std::sort(order.begin() + b, order.begin() + e, [cp](int a, int c) { return cp[3 * a] < cp[3 * c]; });
         }
         int mid = (n == 2) ? b + 1 : b + n / 2;
         int pair = (int)s.nodes.size();
@@ -79,9 +80,9 @@ struct Builder {
         nd.pmin[0] = mn.x; nd.pmin[1] = mn.y; nd.pmin[2] = mn.z;
         nd.pmax[0] = mx.x; nd.pmax[1] = mx.y; nd.pmax[2] = mx.z;
     }
-    static void unite(V3& mn, V3& mx, const Object& o) {
-        V3 lo(fminf(mn.x, o.bmin.x), fminf(mn.y, o.bmin.y), fminf(mn.z, o.bmin.z));
-        V3 hi(fmaxf(mx.x, o.bmax.x), fmaxf(mx.y, o.bmax.y), fmaxf(mx.z, o.bmax.z));
+    static void unite(V3& mn, V3& mx, const float* o) {
+        V3 lo(fminf(mn.x, o[0]), fminf(mn.y, o[1]), fminf(mn.z, o[2]));
+        V3 hi(fmaxf(mx.x, o[3]), fmaxf(mx.y, o[4]), fmaxf(mx.z, o[5]));
         mn = V3(fminf(lo.x, hi.x), fminf(lo.y, hi.y), fminf(lo.z, hi.z));
         mx = V3(fmaxf(lo.x, hi.x), fmaxf(lo.y, hi.y), fmaxf(lo.z, hi.z));
     }
@@ -109,7 +110,16 @@ void HostScene::buildAndFlatten() {
     Builder b(*this);
     if (n > 0) {
         b.order.resize(n);
-        for (int i = 0; i < n; i++) b.order[i] = i;
+        b.cen.resize(3 * (size_t)n);
+        b.box.resize(6 * (size_t)n);
+        for (int i = 0; i < n; i++) {
+            b.order[i] = i;
+            for (int k = 0; k < 3; k++) b.cen[3 * (size_t)i + k] = Builder::centroid(objList[i], k);
+            const V3 &mn = objList[i].bmin, &mx = objList[i].bmax;
+            float* bx = &b.box[6 * (size_t)i];
+            bx[0] = mn.x; bx[1] = mn.y; bx[2] = mn.z; bx[3] = mx.x; bx[4] = mx.y; bx[5] = mx.z;
+        }
+        nodes.reserve(2 * (size_t)n);
         nodes.resize(2);
         memset(nodes.data(), 0, 2 * sizeof(WrtNode));
         nodes[1].link = ~0;       // padding record, never referenced

@@ -12,7 +12,6 @@
 //     prints it directly and the text starts with "ERROR:"); the CLI turns that
 //     into the same console line + exit(-1).
 #include <fstream>
-#include <regex>
 #include <sstream>
 
 #include "host_scene.hpp"
@@ -164,41 +163,59 @@ struct Parser {
         V3 normal = normalized(cross(e1, e2));
         t.n0 = t.n1 = t.n2 = normal;
     }
+    // Which of the reference's four corner forms a token is (std::regex_match against "[0-9]+", "[0-9]+//[0-9]+",
+    // "[0-9]+/[0-9]+", "[0-9]+/[0-9]+/[0-9]+", PPMGenerator.hpp:289-292), without std::regex: 0 = none.
+    enum FaceForm { FORM_NONE = 0, FORM_FLAT, FORM_SMOOTH, FORM_FLAT_TEXT, FORM_SMOOTH_TEXT };
+    static FaceForm classify(const std::string& s, size_t& p, size_t& q) {
+        size_t i = 0, n = s.size();
+        auto digits = [&]() { size_t b = i; while (i < n && s[i] >= '0' && s[i] <= '9') ++i; return i > b; };
+        if (!digits()) return FORM_NONE;
+        if (i == n) return FORM_FLAT;
+        if (s[i] != '/') return FORM_NONE;
+        p = i++;
+        if (i < n && s[i] == '/') {                       // v//n
+            q = i++;
+            if (!digits() || i != n) return FORM_NONE;
+            return FORM_SMOOTH;
+        }
+        if (!digits()) return FORM_NONE;
+        if (i == n) return FORM_FLAT_TEXT;                // v/t
+        if (s[i] != '/') return FORM_NONE;
+        q = i++;
+        if (!digits() || i != n) return FORM_NONE;
+        return FORM_SMOOTH_TEXT;                          // v/t/n
+    }
     void processFace(const std::string tok[3], Object& t) {
-        static const std::regex flat("[0-9]+"), smooth("[0-9]+//[0-9]+"), flat_text("[0-9]+/[0-9]+"),
-            smooth_text("[0-9]+/[0-9]+/[0-9]+");
-        auto all = [&](const std::regex& r) {
-            return std::regex_match(tok[0], r) && std::regex_match(tok[1], r) && std::regex_match(tok[2], r);
-        };
+        size_t p[3] = {0, 0, 0}, q[3] = {0, 0, 0};
+        FaceForm f0 = classify(tok[0], p[0], q[0]), f1 = classify(tok[1], p[1], q[1]), f2 = classify(tok[2], p[2], q[2]);
+        // all three corners must have the same form (the reference tests the forms in the order
+        // flat, smooth, smooth_text, flat_text; the forms are mutually exclusive, so order is irrelevant)
+        if (f0 == FORM_NONE || f0 != f1 || f0 != f2) throw ParseError("f face information is not valid");
         V3* vs[3] = {&t.v0, &t.v1, &t.v2};
         V3* ns[3] = {&t.n0, &t.n1, &t.n2};
         V2* ts[3] = {&t.uv0, &t.uv1, &t.uv2};
-        if (all(flat)) {
-            for (int i = 0; i < 3; i++) *vs[i] = vertexAt(to_int(tok[i]) - 1);
-            flatNormal(t);
-        } else if (all(smooth)) {
-            for (int i = 0; i < 3; i++) {
-                size_t p = tok[i].find("//");
-                *vs[i] = vertexAt(to_int(tok[i].substr(0, p)) - 1);
-                *ns[i] = normalAt(to_int(tok[i].substr(p + 2)) - 1);
+        for (int i = 0; i < 3; i++) {
+            const std::string& s = tok[i];
+            switch (f0) {
+            case FORM_FLAT:
+                *vs[i] = vertexAt(to_int(s) - 1);
+                break;
+            case FORM_SMOOTH:
+                *vs[i] = vertexAt(to_int(s.substr(0, p[i])) - 1);
+                *ns[i] = normalAt(to_int(s.substr(q[i] + 1)) - 1);
+                break;
+            case FORM_FLAT_TEXT:
+                *vs[i] = vertexAt(to_int(s.substr(0, p[i])) - 1);
+                *ts[i] = uvAt(to_int(s.substr(p[i] + 1)) - 1);
+                break;
+            default:
+                *vs[i] = vertexAt(to_int(s.substr(0, p[i])) - 1);
+                *ts[i] = uvAt(to_int(s.substr(p[i] + 1, q[i] - p[i] - 1)) - 1);
+                *ns[i] = normalAt(to_int(s.substr(q[i] + 1)) - 1);
+                break;
             }
-        } else if (all(smooth_text)) {
-            for (int i = 0; i < 3; i++) {
-                size_t p = tok[i].find('/'), q = tok[i].find('/', p + 1);
-                *vs[i] = vertexAt(to_int(tok[i].substr(0, p)) - 1);
-                *ts[i] = uvAt(to_int(tok[i].substr(p + 1, q - p - 1)) - 1);
-                *ns[i] = normalAt(to_int(tok[i].substr(q + 1)) - 1);
-            }
-        } else if (all(flat_text)) {
-            for (int i = 0; i < 3; i++) {
-                size_t p = tok[i].find('/');
-                *vs[i] = vertexAt(to_int(tok[i].substr(0, p)) - 1);
-                *ts[i] = uvAt(to_int(tok[i].substr(p + 1)) - 1);
-            }
-            flatNormal(t);
-        } else {
-            throw ParseError("f face information is not valid");
         }
+        if (f0 == FORM_FLAT || f0 == FORM_FLAT_TEXT) flatNormal(t);
     }
 
     void applyTextureState(Object& s) {               // :256-266, :322-331

@@ -145,3 +145,32 @@ def test_bunny_loader_matches_main_cpp(workdir):
     assert any(abs(g.materials[i].eta - 1.33) < 1e-6 and g.materials[i].ks == np.float32(0.2) for i in range(2))
     # no bunny.obj in the cwd -> silently skipped (main.cpp:47)
     assert Scene.from_workdir(workdir, "bl", bunny=False).n_prims == 2
+
+
+FACE_FORMS = [r"[0-9]+", r"[0-9]+//[0-9]+", r"[0-9]+/[0-9]+", r"[0-9]+/[0-9]+/[0-9]+"]    # PPMGenerator.hpp:289-292
+FACE_TOKENS = ["1", "01", "1/1", "1//1", "1/1/1", "", "/", "//", "1/", "1//", "/1", "//1", "1/1/", "1//1/1", "1/1//1",
+               "1/1/1/1", "a", "1a", "1/a", "-1", "+1", "1.0", "1 ", "1///1", "1/ /1", "9999999999"]
+
+
+@pytest.mark.parametrize("tok", FACE_TOKENS)
+def test_face_token_forms_match_reference_regexes(tok, workdir):
+    """processFace accepts a face iff all three corners fullmatch the SAME one of the reference's four regexes;
+    the hand-written matcher in config_parser.cpp must agree token by token."""
+    import re
+    if any(c.isspace() for c in tok) or tok == "":
+        pytest.skip("not a single >>-token")
+    form = next((i for i, f in enumerate(FACE_FORMS) if re.fullmatch(f, tok)), None)
+    body = HEADER + "mtlcolor 1 1 1 1 1 1 0.2 0.6 0.2 10 1 1\nv 0 0 -3\nv 1 0 -3\nv 0 1 -3\nvn 0 0 1\nvt 0 0\n"
+    txt = body + f"f {tok} {tok} {tok}\n"
+    if form is None or tok in ("9999999999",):
+        with pytest.raises(SceneError):
+            Scene(text=txt, asset_dir=workdir)
+    elif tok == "01":
+        assert Scene(text=txt, asset_dir=workdir).n_prims == 1
+    else:
+        assert Scene(text=txt, asset_dir=workdir).n_prims == 1
+        # mixing it with a different valid form is rejected like the reference's per-form triple match
+        other = "1//1" if tok != "1//1" else "1"
+        with pytest.raises(SceneError) as e:
+            Scene(text=body + f"f {tok} {other} {tok}\n", asset_dir=workdir)
+        assert "f face information is not valid" in str(e.value)

@@ -246,13 +246,19 @@ def run_cuda_arm(args):
         stats = dr.finish()
     barrier()
     rays_local = stats["rays"]
-    rays_t = torch.tensor([rays_local, stats["closest_rays"], stats["shadow_rays"]], dtype=torch.int64, device="cuda")
+    rays_t = torch.tensor([rays_local, stats["closest_rays"], stats["shadow_rays"], stats["shaft_culled_requests"],
+                           stats["unlit_skipped_requests"], stats["shadow_rays_traced"]], dtype=torch.int64, device="cuda")
     per_rank_rays = torch.zeros(world, dtype=torch.int64, device="cuda")
     per_rank_rays[rank] = rays_local
     if world > 1:
         dist.all_reduce(rays_t)
         dist.all_reduce(per_rank_rays)
-    rays_frame, closest_frame, shadow_frame = (int(x) for x in rays_t.tolist())
+    rays_frame, closest_frame, shadow_frame, culled_frame, unlit_frame, shadow_traced_frame = (int(x) for x in rays_t.tolist())
+    # Shadow requests that provably cannot change the image are answered without tracing:
+    # an empty shaft to the area light = 50 lit samples; a light whose shading factors are exactly 0 = coefficient
+    # unused.  `value` counts the frame's rays the way the reference counts them (it traces all of them, SURVEY.md
+    # section 8d: "the reference's own traversal counts are the canonical algorithmic work"); the traced subset
+    # is reported beside it.
 
     # ---- timed: device-resident scene, CUDA events on the launching (current) stream ----
     launches0 = ctx.launches
@@ -345,7 +351,7 @@ def run_cuda_arm(args):
     dom_share = fam_ms[dom] / max(1e-9, sum(fam_ms.values()))
     # units the dominant family processes in one frame on this rank
     if dom.startswith("shadow"):
-        dom_units = stats["shadow_rays"]
+        dom_units = stats["shadow_rays_traced"]                  # rays the kernel really traces
     elif dom == "trace_closest":
         dom_units = stats["closest_rays"]
     else:
@@ -385,6 +391,14 @@ def run_cuda_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "width": w, "height": h, "rays_per_frame": rays_frame,
                        "closest_hit_rays": closest_frame, "shadow_rays": shadow_frame,
+                       "shadow_rays_traced": shadow_traced_frame,
+                       "request_culling": {"shaft_empty_requests": culled_frame, "unlit_light_requests": unlit_frame,
+                                           "note": "shadow requests answered without tracing: whole shaft to the area light "
+                                                   "misses every leaf box (=50 lit samples) / light's diffuse+specular factors "
+                                                   "exactly 0 (coefficient unused); bit-identical image; rays_per_frame counts "
+                                                   "them like the reference, which traces them; WRT_SHAFT_CULL=0 "
+                                                   "WRT_UNLIT_CULL=0 disable"},
+                       "traced_mrays_per_s": (closest_frame + shadow_traced_frame) / (ms_per_step * 1e-3) / 1e6,
                        "parallelism": f"tiles{tile[0]}x{tile[1]}-interleaved x{world}" + ("+nccl-gather" if world > 1 else ""),
                        "traversal": "pruned", "l2": "flushed between timed steps (256 MiB write)",
                        "scene_bytes": scene.upload_bytes, "image_checksum": checksum},

@@ -143,6 +143,11 @@ typedef struct WrtStats {
     int32_t pad;
     float   gpu_ms;               /* device time of the last wrt_render* call */
     float   pad2;
+    /* CUDA path only.  Shadow requests answered without tracing; they stay counted in shadow_requests /
+     * shadow_rays, which follow the reference's definition (it traces them): */
+    int64_t shaft_culled_requests;  /* soft shadows: the whole shaft to the area light misses every leaf box => 50 lit */
+    int64_t unlit_skipped_requests; /* the light's diffuse and specular factors are exactly 0 => coefficient unused */
+    int64_t shadow_rays_traced;     /* shadow rays the kernels really traced */
 } WrtStats;
 
 #define WRT_MAX_DEPTH 9           /* Renderer.hpp:25 */

@@ -1,0 +1,137 @@
+// TEST INFRASTRUCTURE (built and run by tests/test_shaft_cull.py).
+// Runs the product's shaft test (csrc/cuda/shaft_cull.h — the same source k_surface_spawn compiles)
+// on the CPU and checks every "empty" verdict by brute force: for many (u, v) samples, corner
+// extremes included, the sample ray — built with the kernel's own float operations — must miss
+// the own box of EVERY primitive under the exact BoundBox::IntersectRay arithmetic.  Also checks
+// that each sample's 1/d lies inside the shaft's bounds.  Prints one JSON line.
+//
+// usage: shaft_cull_check <config.txt> <bunny.obj|-> <asset_dir> <n_requests> <seed>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../include/wrt_host.h"
+#include "../include/wrt_rng.h"
+#include "../include/wrt_scene.h"
+#include "../whittedstyle_raytracer_b200/csrc/cuda/fast_bvh.hpp"
+#include "../whittedstyle_raytracer_b200/csrc/cuda/shaft_cull.h"
+
+struct V { float x, y, z; };
+
+static uint64_t g_state;
+static uint32_t rnd() { g_state = g_state * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(g_state >> 32); }
+static float unif() { return (float)(rnd() >> 8) * (1.0f / 16777216.0f); }
+
+// BoundBox::IntersectRay (BoundBox.hpp:53-85) on a natural-order box
+static bool slab(const float* mn, const float* mx, V o, V d, V inv) {
+    float ax = (mn[0] - o.x) * inv.x, bx = (mx[0] - o.x) * inv.x;
+    float ay = (mn[1] - o.y) * inv.y, by = (mx[1] - o.y) * inv.y;
+    float az = (mn[2] - o.z) * inv.z, bz = (mx[2] - o.z) * inv.z;
+    float tminx = d.x < 0 ? bx : ax, tmaxx = d.x < 0 ? ax : bx;
+    float tminy = d.y < 0 ? by : ay, tmaxy = d.y < 0 ? ay : by;
+    float tminz = d.z < 0 ? bz : az, tmaxz = d.z < 0 ? az : bz;
+    float te = fmaxf(tminx, fmaxf(tminy, tminz)), tx = fminf(tmaxx, fminf(tmaxy, tmaxz));
+    return te <= tx && tx >= 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 6) { fprintf(stderr, "usage\n"); return 2; }
+    WrtScene* sc = nullptr;
+    if (wrt_scene_load(argv[1], strcmp(argv[2], "-") ? argv[2] : nullptr, argv[3], 0, &sc) != 0) {
+        fprintf(stderr, "load failed: %s\n", wrt_host_last_error());
+        return 2;
+    }
+    const WrtSceneDesc* S = wrt_scene_desc(sc);
+    const int n_req = atoi(argv[4]);
+    g_state = strtoull(argv[5], nullptr, 10) * 2654435761ull + 12345;
+    wrt::FastBvhBuilder fb;
+    fb.build(S);
+    std::vector<WrtNode> oct = fb.octant_copies();
+    std::vector<float4> onodes(2 * oct.size());
+    static_assert(sizeof(WrtNode) == 2 * sizeof(float4), "record = two float4");
+    memcpy(onodes.data(), oct.data(), oct.size() * sizeof(WrtNode));
+    const int np = S->n_prims, nn = (int)fb.nodes.size();
+    std::vector<float> box(6 * (size_t)np);
+    float smin[3] = {INFINITY, INFINITY, INFINITY}, smax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < S->n_nodes; i++) {
+        const WrtNode& nd = S->nodes[i];
+        if (nd.link >= 0 || i == 1) continue;
+        int p = ~nd.link;
+        for (int k = 0; k < 3; k++) {
+            box[6 * (size_t)p + k] = nd.pmin[k]; box[6 * (size_t)p + 3 + k] = nd.pmax[k];
+            smin[k] = fminf(smin[k], nd.pmin[k]); smax[k] = fmaxf(smax[k], nd.pmax[k]);
+        }
+    }
+    long long empty = 0, nonempty = 0, gave_up = 0, violations = 0, bound_violations = 0, rays_checked = 0;
+    const float top = 1.0f - 1.0f / 16777216.0f;
+    for (int r = 0; r < n_req; r++) {
+        // origin: a point on a random primitive pushed off along +-normal like BVHStrategy.hpp:15, or a free point
+        float o[3];
+        int mode = rnd() % 4;
+        if (mode < 3 && np > 0) {
+            int p = rnd() % np;
+            const float* g = S->prim_geom + 12 * (size_t)p;
+            if ((S->prim_flags[p] & WRT_PRIM_KIND_MASK) == WRT_PRIM_TRIANGLE) {
+                float a = unif(), b = unif();
+                if (a + b > 1) { a = 1 - a; b = 1 - b; }
+                V e1{g[4], g[5], g[6]}, e2{g[8], g[9], g[10]};
+                V n{e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x};
+                float len = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+                float sgn = (rnd() & 1) ? 0.0005f : -0.0005f;
+                if (len > 0) { n.x /= len; n.y /= len; n.z /= len; }
+                o[0] = g[0] + a * e1.x + b * e2.x + sgn * n.x;
+                o[1] = g[1] + a * e1.y + b * e2.y + sgn * n.y;
+                o[2] = g[2] + a * e1.z + b * e2.z + sgn * n.z;
+            } else {
+                V n{unif() - 0.5f, unif() - 0.5f, unif() - 0.5f};
+                float len = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z) + 1e-20f;
+                float rr = g[3] + 0.0005f;
+                o[0] = g[0] + rr * n.x / len; o[1] = g[1] + rr * n.y / len; o[2] = g[2] + rr * n.z / len;
+            }
+        } else {
+            for (int k = 0; k < 3; k++) o[k] = smin[k] + (smax[k] - smin[k]) * (unif() * 1.4f - 0.2f);
+        }
+        for (int li = 0; li < S->n_lights; li++) {
+            const WrtLight& L = S->lights[li];
+            if (fabsf(L.pos[3] - 1.f) >= 0.00001f) continue;
+            WrtShaft sh;
+            const bool made = wrt_shaft_make(o, L.tri, &sh);
+            const bool is_empty = wrt_shaft_is_empty(onodes.data(), nn, o, L.tri);
+            if (!made) { gave_up++; if (is_empty) violations++; continue; }
+            if (is_empty) empty++; else nonempty++;
+            V v0{L.tri[0], L.tri[1], L.tri[2]}, v1{L.tri[3], L.tri[4], L.tri[5]}, v2{L.tri[6], L.tri[7], L.tri[8]};
+            const int ns = is_empty ? 40 : 12;
+            for (int s = 0; s < ns; s++) {
+                float u, v;
+                if (s < 4) { u = (s & 1) ? top : 0.f; v = (s & 2) ? top : 0.f; }
+                else if (s < 8) { u = (s & 1) ? top : 0.f; v = unif(); if (s & 2) { float t = u; u = v; v = t; } }
+                else wrt_light_sample_uv(WRT_DEFAULT_SEED, rnd(), 1u + rnd() % 511u, (uint32_t)li, (uint32_t)s, &u, &v);
+                // SoftShadowQuery::begin (kernels.cuh) / area_light_shadow (oracle): same operations, same order
+                float a = 1 - u - v;
+                V lp{a * v0.x + u * v1.x + v * v2.x, a * v0.y + u * v1.y + v * v2.y, a * v0.z + u * v1.z + v * v2.z};
+                V dl{lp.x - o[0], lp.y - o[1], lp.z - o[2]};
+                float mag = sqrtf(dl.x * dl.x + dl.y * dl.y + dl.z * dl.z);
+                V d = dl;
+                if (mag > 0) { float mi = 1 / mag; d = V{dl.x * mi, dl.y * mi, dl.z * mi}; }
+                V inv{1 / d.x, 1 / d.y, 1 / d.z};
+                const float iv[3] = {inv.x, inv.y, inv.z}, dv[3] = {d.x, d.y, d.z};
+                for (int k = 0; k < 3; k++) {
+                    bool neg = dv[k] < 0;
+                    if (!(iv[k] >= sh.ilo[k] && iv[k] <= sh.ihi[k]) || neg != (((sh.octant >> k) & 1) != 0) || dv[k] == 0) bound_violations++;
+                }
+                if (!is_empty) continue;
+                rays_checked++;
+                V ov{o[0], o[1], o[2]};
+                for (int p = 0; p < np; p++)
+                    if (slab(&box[6 * (size_t)p], &box[6 * (size_t)p + 3], ov, d, inv)) { violations++; break; }
+            }
+        }
+    }
+    printf("{\"prims\": %d, \"empty\": %lld, \"nonempty\": %lld, \"gave_up\": %lld, \"rays_checked\": %lld, "
+           "\"violations\": %lld, \"bound_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked, violations, bound_violations);
+    wrt_scene_free(sc);
+    return (violations || bound_violations) ? 1 : 0;
+}

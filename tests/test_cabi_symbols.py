@@ -37,7 +37,7 @@ def test_struct_layouts_match_headers():
     assert C.sizeof(cabi.WrtLight) == 80
     assert C.sizeof(cabi.WrtHit) == 60
     assert C.sizeof(cabi.WrtCamera) == 4 * (7 * 3 + 1 + 3)
-    assert C.sizeof(cabi.WrtStats) == 8 * 14 + 16
+    assert C.sizeof(cabi.WrtStats) == 8 * 14 + 16 + 24
 
 
 def test_cuda_library_is_sm100a_only():

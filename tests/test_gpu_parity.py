@@ -387,3 +387,35 @@ def test_4k_soft_shadow_config(workdir):
     d = image_diff(img[::40, ::48], sample[::40, ::48])
     assert d["exact"] >= 0.999 * d["n"] and d["max"] <= 1, d
     r.ctx.close()
+
+
+def test_request_culling_changes_the_work_not_the_result(workdir, monkeypatch):
+    """Shadow requests that cannot change the image are answered without tracing: soft-shadow requests
+    whose whole shaft to the area light misses every leaf box (50 lit samples, shaft_cull.h) and lights
+    whose diffuse and specular factors are exactly 0 at the point (dev_shade.cuh).  Same image, same ray
+    counts (the reference traces those rays, so they are counted), and the oracle — which traces all of
+    them — agrees.  Soft and hard shadows."""
+    for soft in (True, False):
+        name = f"cull_640_{int(soft)}"
+        fixtures.write_config(workdir, name, fixtures.water_bunny_tex_config(640, 360, soft=soft))
+        scene = Scene.from_workdir(workdir, name)
+        on, st_on = gpu_render(scene)
+        monkeypatch.setenv("WRT_SHAFT_CULL", "0")           # read by wrt_create
+        monkeypatch.setenv("WRT_UNLIT_CULL", "0")
+        off, st_off = gpu_render(scene)
+        monkeypatch.delenv("WRT_SHAFT_CULL")
+        monkeypatch.delenv("WRT_UNLIT_CULL")
+        assert np.array_equal(on, off)
+        assert st_off["shaft_culled_requests"] == 0 and st_off["unlit_skipped_requests"] == 0
+        assert st_off["shadow_rays_traced"] == st_off["shadow_rays"]
+        assert st_on["unlit_skipped_requests"] > 0.02 * st_on["shadow_requests"]
+        if soft:
+            assert st_on["shaft_culled_requests"] > 0.25 * st_on["shadow_requests"]
+        per = 50 if soft else 1
+        assert st_on["shadow_rays_traced"] == st_on["shadow_rays"] - per * (st_on["shaft_culled_requests"] + st_on["unlit_skipped_requests"])
+        for k in ("closest_rays", "shadow_rays", "shadow_requests", "rays_per_depth"):
+            assert st_on[k] == st_off[k], k
+        ref, ost = ob.OracleScene(scene).render()
+        d = image_diff(on, ref)
+        assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+        assert st_on["shadow_rays"] == ost.shadow_rays

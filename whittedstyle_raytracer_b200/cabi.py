@@ -69,7 +69,9 @@ class WrtHit(C.Structure):
 class WrtStats(C.Structure):
     _fields_ = [("closest_rays", C.c_int64), ("shadow_rays", C.c_int64), ("rays_per_depth", C.c_int64 * 9),
                 ("shadow_requests", C.c_int64), ("box_tests", C.c_int64), ("prim_tests", C.c_int64),
-                ("overflow_retries", C.c_int32), ("pad", C.c_int32), ("gpu_ms", C.c_float), ("pad2", C.c_float)]
+                ("overflow_retries", C.c_int32), ("pad", C.c_int32), ("gpu_ms", C.c_float), ("pad2", C.c_float),
+                ("shaft_culled_requests", C.c_int64), ("unlit_skipped_requests", C.c_int64),
+                ("shadow_rays_traced", C.c_int64)]
 
 
 # numpy view of WrtHit (same layout, 60 bytes)

@@ -152,6 +152,35 @@ __device__ __forceinline__ f3 refraction_dir(f3 incident, f3 normal, float eta_i
     return cos_theta_t * (-N) + (eta_i / eta_t) * (cos_theta_i * N - I);
 }
 
+// The two geometric factors of one light's Blinn-Phong terms (Renderer.hpp:290-296, :320-326):
+// mx = max(L.N, 0) and pw = pow(max(H.N, 0), n).  One function for k_shade and for the request
+// culling in k_surface_spawn, so both see bit-identical values.  LAZY: pw is only evaluated when
+// mx == 0 (the only case the culling asks about); otherwise it is returned as 1.
+template <bool LAZY>
+__device__ __forceinline__ void light_factors(const WrtLight* L, f3 p_eye_dir, f3 pos, f3 nDir, float n_exp, float& mx, float& pw) {
+    f3 p_light_dir;
+    if (float_equal(L->pos[3], 1.f)) p_light_dir = normalized(mk3(L->pos[0], L->pos[1], L->pos[2]) - pos);
+    else p_light_dir = normalized(mk3(-L->pos[0], -L->pos[1], -L->pos[2]));
+    float ndl = dot(p_light_dir, normalized(nDir));
+    mx = (ndl < 0.f) ? 0.f : ndl;
+    pw = 1.f;
+    if (LAZY && mx != 0.f) return;
+    f3 h = normalized(p_light_dir + p_eye_dir);
+    float hn = dot(h, nDir);
+    float mh = (hn < 0.f) ? 0.f : hn;
+    pw = ref_powf(mh, n_exp);
+}
+
+// True when light L adds exactly the same value to the pixel whatever its shadow coefficient is: both
+// factors are 0, so the diffuse and the specular term are (finite, sign fixed by the colours) * 0 for
+// every coefficient in [0, 1] — the light faces the back of the surface.  The reference still traces
+// these shadow rays (Renderer.hpp:283-287 runs before the max()); their result is multiplied by 0.
+__device__ __forceinline__ bool light_terms_vanish(const WrtLight* L, f3 p_eye_dir, f3 pos, f3 nDir, float n_exp) {
+    float mx, pw;
+    light_factors<true>(L, p_eye_dir, pos, nDir, n_exp, mx, pw);
+    return mx == 0.f && pw == 0.f;
+}
+
 // Renderer::blinnPhongShader, Renderer.hpp:265-341.  `shadow[l]` holds the
 // coefficient the shadow kernels produced for light l (hard: product; soft:
 // number of unoccluded samples, divided by 50 here; directional: product).
@@ -164,29 +193,19 @@ __device__ __forceinline__ f3 blinn_phong(const DevScene& s, f3 rayOrig, f3 pos,
         const WrtLight* L = s.lights + li;
         f3 lcolor = mk3(L->color[0], L->color[1], L->color[2]);
         float sh = shadow[li];
+        float mx, pw;
+        light_factors<false>(L, p_eye_dir, pos, nDir, m.n, mx, pw);
         if (float_equal(L->pos[3], 1.f)) {
             f3 lightPos = mk3(L->pos[0], L->pos[1], L->pos[2]);
             float d_p_light = norm(lightPos - pos);
             float attenuation = 1.f;
             if (L->c1 >= 0.f) attenuation = 1.f / (L->c1 + L->c2 * d_p_light + L->c3 * d_p_light * d_p_light);
-            f3 p_light_dir = normalized(lightPos - pos);
             if (s.shadow_type != 0) sh = sh / (float)WRT_SOFT_SAMPLES;     // sum / sampleNum, Renderer.hpp:413
-            float ndl = dot(p_light_dir, normalized(nDir));
-            float mx = (ndl < 0.f) ? 0.f : ndl;
             diffuse = diffuse + (((((sh * lcolor) * m.kd) * m.diffuse) * attenuation) * mx);
-            f3 h = normalized(p_light_dir + p_eye_dir);
-            float hn = dot(h, nDir);
-            float mh = (hn < 0.f) ? 0.f : hn;
-            specular = specular + (((((sh * lcolor) * m.ks) * m.specular) * attenuation) * ref_powf(mh, m.n));
+            specular = specular + (((((sh * lcolor) * m.ks) * m.specular) * attenuation) * pw);
         } else {
-            f3 p_light_dir = normalized(mk3(-L->pos[0], -L->pos[1], -L->pos[2]));
-            float ndl = dot(p_light_dir, normalized(nDir));
-            float mx = (ndl < 0.f) ? 0.f : ndl;
             diffuse = diffuse + ((((sh * lcolor) * m.kd) * m.diffuse) * mx);
-            f3 h = normalized(p_light_dir + p_eye_dir);
-            float hn = dot(h, nDir);
-            float mh = (hn < 0.f) ? 0.f : hn;
-            specular = specular + ((((sh * lcolor) * m.ks) * m.specular) * ref_powf(mh, m.n));
+            specular = specular + ((((sh * lcolor) * m.ks) * m.specular) * pw);
         }
     }
     f3 res = ambient + diffuse + specular;

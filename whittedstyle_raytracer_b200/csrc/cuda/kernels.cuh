@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include "dev_shade.cuh"
+#include "shaft_cull.h"
 #include "../../../include/wrt_rng.h"
 #include "../../../include/wrt_tiles.h"
 
@@ -38,6 +39,9 @@ enum CounterSlot {
     C_VALID0 = 48,               // valid (non-padding) primary rays
     C_OVERFLOW = 49,             // set when a queue append was dropped
     C_WORK = 64,                 // work-distribution counters, one per persistent launch
+    C_NCULL = 128,               // [9] soft-shadow requests answered by the shaft test (shaft_cull.h), never queued
+    C_NSKIP = 144,               // [9] point-light requests whose light terms vanish (dev_shade.cuh), never queued
+    C_NDSKIP = 160,              // [9] the same for directional lights
     C_TOTAL = 256
 };
 
@@ -204,7 +208,15 @@ __global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScen
 }
 
 // ---- K3: hit -> surface, shadow requests, child rays (Renderer.hpp:170-257) ----
-__global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers fb, int level) {
+// `cull`: shadow requests that provably cannot change the image are answered here and never queued.
+//   WRT_CULL_UNLIT  the light's diffuse AND specular factors at this point are exactly 0 (dev_shade.cuh,
+//                   light_terms_vanish): whatever the coefficient, the light adds +-0;
+//   WRT_CULL_SHAFT  (soft shadows) the whole shaft origin -> area light misses every leaf box: all 50
+//                   samples are lit, coefficient = 50 (shaft_cull.h).
+// The reference traces these rays; WrtStats keeps counting them and reports how many were answered this way.
+#define WRT_CULL_UNLIT 1
+#define WRT_CULL_SHAFT 2
+__global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers fb, int level, int cull) {
     const LevelSpan span = level_span(fb.counters, level, fb.cap);
     const unsigned n = span.count();
     const unsigned child_half = fb.cap / 2;
@@ -225,6 +237,8 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
         f3 refractDir = org, reflectDir = org, refRayOrig = org, traRayOrig = org;
         unsigned pixel = 0, path = 0;
         int prim = -1;
+        float shade_n = 0.f;                                   // Phong exponent of the shaded material
+        unsigned lit_mask = 0, skip_mask = 0;                  // lights (< 32) answered without a request
         if (live) {
             float4 o4 = ray_o[i], d4 = ray_d[i], h = fb.hit[i];
             org = mk3(o4); dir = mk3(d4);
@@ -239,6 +253,7 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
                     na = make_float4(m.diffuse.x, m.diffuse.y, m.diffuse.z, 0.f); // light avatar, :172
                 } else {
                     shade = true;
+                    shade_n = m.n;
                     f3 Od = m.diffuse;
                     if (!float_equal(-1.f, (float)sf.textureIndex) && !float_equal(-1.f, sf.u) && !float_equal(-1.f, sf.v))
                         Od = texture_at(s, s.textures + sf.textureIndex, sf.u, sf.v);      // :176-180
@@ -291,15 +306,43 @@ __global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers 
             nray_d[c] = make_float4(refractDir.x, refractDir.y, refractDir.z, __uint_as_float(path * 2u + 1u));
             nb.z = __int_as_float((int)c);
         }
-        // shadow requests: one per (shaded hit, light)
-        unsigned pslot = warp_alloc(fb.counters + C_NPREQ + level, shade ? s.n_point_lights : 0, fb.preq_cap, overflow);
+        // shadow requests: one per (shaded hit, light) — minus the ones that cannot change the image
+        const f3 sorig = pos + 0.0005f * nDir;                             // BVHStrategy.hpp:15, Renderer.hpp:349
+        int n_preq = shade ? s.n_point_lights : 0, n_dreq = shade ? s.n_dir_lights : 0;
+        if (shade && cull) {
+            const float so[3] = {sorig.x, sorig.y, sorig.z};
+            const f3 p_eye_dir = normalized(org - pos);                    // as blinn_phong() will compute it
+            for (int li = 0; li < s.n_lights && li < 32; li++) {
+                const WrtLight* L = s.lights + li;
+                const bool point = float_equal(L->pos[3], 1.f);
+                if ((cull & WRT_CULL_UNLIT) && light_terms_vanish(L, p_eye_dir, pos, nDir, shade_n)) {
+                    skip_mask |= 1u << li;                                 // coefficient is multiplied by 0 twice
+                    if (point) --n_preq; else --n_dreq;
+                } else if ((cull & WRT_CULL_SHAFT) && point) {
+                    float tri[9];
+                    for (int k = 0; k < 9; k++) tri[k] = L->tri[k];
+                    if (wrt_shaft_is_empty(s.onodes, s.n_nodes, so, tri)) { lit_mask |= 1u << li; --n_preq; }
+                }
+            }
+        }
+        unsigned pslot = warp_alloc(fb.counters + C_NPREQ + level, n_preq, fb.preq_cap, overflow);
         unsigned dslot = 0xffffffffu;
-        if (s.n_dir_lights > 0)
-            dslot = warp_alloc(fb.counters + C_NDREQ + level, shade ? s.n_dir_lights : 0, fb.dreq_cap, overflow);
+        if (s.n_dir_lights > 0) dslot = warp_alloc(fb.counters + C_NDREQ + level, n_dreq, fb.dreq_cap, overflow);
+        if (cull) {                                                        // statistics: the reference traces these rays
+            unsigned n_lit = __reduce_add_sync(0xffffffffu, (unsigned)__popc(lit_mask));
+            unsigned n_skip_p = __reduce_add_sync(0xffffffffu, (unsigned)((shade ? s.n_point_lights : 0) - n_preq - __popc(lit_mask)));
+            unsigned n_skip_d = __reduce_add_sync(0xffffffffu, (unsigned)((shade ? s.n_dir_lights : 0) - n_dreq));
+            if ((threadIdx.x & 31) == 0) {
+                if (n_lit) atomicAdd(fb.counters + C_NCULL + level, n_lit);
+                if (n_skip_p) atomicAdd(fb.counters + C_NSKIP + level, n_skip_p);
+                if (n_skip_d) atomicAdd(fb.counters + C_NDSKIP + level, n_skip_d);
+            }
+        }
         if (shade) {
-            f3 sorig = pos + 0.0005f * nDir;                               // BVHStrategy.hpp:15, Renderer.hpp:349
             for (int li = 0; li < s.n_lights; li++) {
-                fb.coeff[level % WRT_SETS][(size_t)i * s.n_lights + li] = 0.f;
+                const bool lit = li < 32 && ((lit_mask >> li) & 1u), skip = li < 32 && ((skip_mask >> li) & 1u);
+                fb.coeff[level % WRT_SETS][(size_t)i * s.n_lights + li] = lit ? (float)WRT_SOFT_SAMPLES : 0.f;
+                if (lit || skip) continue;
                 bool point = float_equal(s.lights[li].pos[3], 1.f);
                 if (point && pslot != 0xffffffffu) {
                     fb.preq_o[level % WRT_SETS][pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(i));

@@ -71,6 +71,8 @@ struct WrtContext {
     bool kernel_timing = false;
     int refill = 16;                   // idle lanes that trigger a refill on deep ray-tree levels
     int refill_soft = 24;
+    bool shaft_cull = true;            // soft shadows: answer requests whose light shaft is empty without tracing (shaft_cull.h)
+    bool unlit_cull = true;            // drop shadow requests of lights whose shading terms are exactly 0 at the point
     int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
     int chunk_div = 16;                // work claiming: 0 = one atomic per refill, k = chunks of n/(warps*k) items
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
@@ -297,7 +299,13 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
         }
         {
             LaunchScope ls(c, st, F_SURFACE);
-            k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, d);
+            // request culling belongs to the pruned mode; WRT_TRAVERSAL_EXHAUSTIVE traces every ray the reference traces
+            int cull = 0;
+            if (c->traversal == WRT_TRAVERSAL_PRUNED) {
+                if (c->unlit_cull) cull |= WRT_CULL_UNLIT;
+                if (c->shaft_cull && ds.shadow_type != 0) cull |= WRT_CULL_SHAFT;
+            }
+            k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, d, cull);
         }
         if (overlap) {
             CK(cudaEventRecord(c->ev_surface[d], st));
@@ -345,9 +353,15 @@ void add_batch_stats(WrtContext* c, const unsigned* cnt) {
         s.closest_rays += cnt[wrt::C_NRAYS + d] + cnt[wrt::C_NTRAYS + d];
     }
     for (int d = 0; d < WRT_MAX_DEPTH; d++) {
-        int64_t p = cnt[wrt::C_NPREQ + d], q = cnt[wrt::C_NDREQ + d];
+        // requests answered without tracing count like the reference counts them (it traces them)
+        int64_t culled = cnt[wrt::C_NCULL + d], skip_p = cnt[wrt::C_NSKIP + d], skip_d = cnt[wrt::C_NDSKIP + d];
+        int64_t p = cnt[wrt::C_NPREQ + d] + culled + skip_p, q = cnt[wrt::C_NDREQ + d] + skip_d;
+        const int64_t per = ds.shadow_type ? WRT_SOFT_SAMPLES : 1;
         s.shadow_requests += p + q;
-        s.shadow_rays += p * (ds.shadow_type ? WRT_SOFT_SAMPLES : 1) + q;
+        s.shadow_rays += p * per + q;
+        s.shaft_culled_requests += culled;
+        s.unlit_skipped_requests += skip_p + skip_d;
+        s.shadow_rays_traced += cnt[wrt::C_NPREQ + d] * per + cnt[wrt::C_NDREQ + d];
     }
 }
 
@@ -501,6 +515,8 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_TRACE_BLOCKS")) c->trace_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("WRT_CACHE_FROM")) c->cache_from_level = atoi(e);
+    if (const char* e = getenv("WRT_SHAFT_CULL")) c->shaft_cull = atoi(e) != 0;
+    if (const char* e = getenv("WRT_UNLIT_CULL")) c->unlit_cull = atoi(e) != 0;
     if (const char* e = getenv("WRT_CHUNK_DIV")) c->chunk_div = std::max(0, std::min(255, atoi(e)));
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));

@@ -40,6 +40,10 @@ def stats_dict(st: cabi.WrtStats) -> dict:
         "rays_per_depth": [int(x) for x in st.rays_per_depth],
         "shadow_requests": int(st.shadow_requests), "overflow_retries": int(st.overflow_retries),
         "gpu_ms": float(st.gpu_ms),
+        # shadow requests answered without tracing (include/wrt_scene.h); shadow_rays keeps the reference's count
+        "shaft_culled_requests": int(st.shaft_culled_requests),
+        "unlit_skipped_requests": int(st.unlit_skipped_requests),
+        "shadow_rays_traced": int(st.shadow_rays_traced),
     }
 
 

@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
             smin[k] = fminf(smin[k], nd.pmin[k]); smax[k] = fmaxf(smax[k], nd.pmax[k]);
         }
     }
-    long long empty = 0, nonempty = 0, gave_up = 0, violations = 0, bound_violations = 0, rays_checked = 0;
+    long long empty = 0, nonempty = 0, gave_up = 0, violations = 0, bound_violations = 0, rays_checked = 0, degenerate_rays = 0;
     const float top = 1.0f - 1.0f / 16777216.0f;
     for (int r = 0; r < n_req; r++) {
         // origin: a point on a random primitive pushed off along +-normal like BVHStrategy.hpp:15, or a free point
@@ -94,6 +94,13 @@ int main(int argc, char** argv) {
         } else {
             for (int k = 0; k < 3; k++) o[k] = smin[k] + (smax[k] - smin[k]) * (unif() * 1.4f - 0.2f);
         }
+        // a quarter of the origins share a coordinate with a light corner: that axis is dropped by the shaft
+        // test, and when the coordinate is 0 every sample is axis-degenerate there (d_k == 0: the inf / NaN
+        // paths of BoundBox::IntersectRay, which slab() below takes exactly like the kernels do)
+        if (S->n_lights > 0 && rnd() % 4 == 0) {
+            int k = rnd() % 3;
+            o[k] = S->lights[rnd() % S->n_lights].tri[k + 3 * (rnd() % 3)];
+        }
         for (int li = 0; li < S->n_lights; li++) {
             const WrtLight& L = S->lights[li];
             if (fabsf(L.pos[3] - 1.f) >= 0.00001f) continue;
@@ -119,9 +126,11 @@ int main(int argc, char** argv) {
                 V inv{1 / d.x, 1 / d.y, 1 / d.z};
                 const float iv[3] = {inv.x, inv.y, inv.z}, dv[3] = {d.x, d.y, d.z};
                 for (int k = 0; k < 3; k++) {
+                    if (!((sh.use >> k) & 1)) continue;                   // dropped axis: nothing is claimed about it
                     bool neg = dv[k] < 0;
                     if (!(iv[k] >= sh.ilo[k] && iv[k] <= sh.ihi[k]) || neg != (((sh.octant >> k) & 1) != 0) || dv[k] == 0) bound_violations++;
                 }
+                if (dv[0] == 0 || dv[1] == 0 || dv[2] == 0) degenerate_rays++;
                 if (!is_empty) continue;
                 rays_checked++;
                 V ov{o[0], o[1], o[2]};
@@ -131,7 +140,8 @@ int main(int argc, char** argv) {
         }
     }
     printf("{\"prims\": %d, \"empty\": %lld, \"nonempty\": %lld, \"gave_up\": %lld, \"rays_checked\": %lld, "
-           "\"violations\": %lld, \"bound_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked, violations, bound_violations);
+           "\"degenerate_rays\": %lld, \"violations\": %lld, \"bound_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked,
+           degenerate_rays, violations, bound_violations);
     wrt_scene_free(sc);
     return (violations || bound_violations) ? 1 : 0;
 }

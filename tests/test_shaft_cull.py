@@ -44,6 +44,11 @@ CASES = {
                    "light 300 0.01 0.01 1 1 1 1\nlight 0.5 0.2 -0.5 1 1 1 1\n" + fixtures._WALL_VERTS +
                    "\nmtlcolor 1 1 1 1 1 1 0.2 0.6 0.2 10 1 1\nf 1 2 3\nf 1 4 2\nsphere 0 0 -1 0.4\nsphere 1 1 -2 0.3\n",
                    True, 3000),
+    # lights whose corners have a 0 coordinate: origins that share it make every sample axis-degenerate there
+    "axis_degenerate": (lambda: fixtures._CAMERA.format(w=32, h=24) + "\nshadow soft\nlight 0 0 60 1 1 1 1\n"
+                        "light 50 0 0 1 1 1 1\nv -1 -2 -4\nv 1 -2 -4\nv 0 -2 -6\n"
+                        "mtlcolor 1 1 1 1 1 1 0.2 0.6 0.2 10 1 1\nf 1 2 3\nsphere 0 0 -1 0.4\nsphere 1 0 2 0.3\n"
+                        "sphere -2 0.5 1 0.5\nsphere 0 -1 3 0.25\nsphere 4 0 -3 0.6\nsphere -3 2 -2 0.5\n", False, 8000),
 }
 
 
@@ -60,3 +65,5 @@ def test_empty_shaft_verdicts_hold_by_brute_force(name, checker, workdir):
     assert r["empty"] + r["nonempty"] + r["gave_up"] > 0
     if name in ("water_bunny_tex", "bunny_shadow"):
         assert r["empty"] > 0 and r["nonempty"] > 0          # the test exercises both verdicts
+    if name == "axis_degenerate":
+        assert r["degenerate_rays"] > 1000 and r["empty"] > 0

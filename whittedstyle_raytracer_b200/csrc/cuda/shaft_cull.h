@@ -12,20 +12,27 @@
 //  1. Bounds.  Per axis, D_k = lightPos_k - o_k of every sample lies between the extremes over the
 //     four parallelogram corners (linear in u, v), up to float rounding of the reference's
 //     evaluation order (<= 1e-6 * M, M = largest |coordinate| involved).  The ranges are padded by
-//     1e-5 * M; a padded range that touches 0 gives up (returns false), so below every sample ray
-//     has the same, non-zero direction signs: one octant, never axis-degenerate.
-//     |D| lies in [dmin, dmax] (dmax: farthest corner, convexity; dmin: the box lower bound
-//     sqrt(sum min|D_k|^2)), and inv_k = 1 / (D_k / |D|) = |D| / D_k up to 3 roundings (4e-7),
-//     so inv_k is inside [dmin/hi_k, dmax/lo_k] (signs handled), widened by 1e-5 relative.
+//     1e-5 * M.  An axis whose padded range excludes 0 is "definite": every sample direction has
+//     the same non-zero sign there.  |D| lies in [dmin, dmax] (dmax: farthest corner, convexity;
+//     dmin: the box lower bound sqrt(sum min|D_k|^2)), and inv_k = 1 / (D_k * (1/|D|)) = |D| / D_k
+//     up to 4 roundings (< 5e-7), so on a definite axis inv_k is inside [dmin/hi_k, dmax/lo_k]
+//     (signs handled), widened by 1e-5 relative.
+//     An axis whose range touches 0 is DROPPED from the test (no constraint).  That stays exact even
+//     for samples that are axis-degenerate there (d_k == 0: 1/0 = inf, 0*inf = NaN in
+//     BoundBox.hpp:55-84): with fmaxf/fminf the exact t_enter is >= the maximum over the other axes
+//     and t_exit <= their minimum (a NaN operand is ignored, +-inf only tightens), so a box that
+//     fails on the remaining axes fails the exact test.  At least one axis must be definite.
 //  2. Interval slab test.  All rays share the origin, so a = plane - o_k is the SAME float in
 //     every ray's BoundBox::IntersectRay (BoundBox.hpp:53-85); t = a * inv_k is monotonic in inv_k
 //     under round-to-nearest, hence t_near_k >= min(a*ilo_k, a*ihi_k) and t_far_k <= max(...)
 //     hold for the rounded values.  If max_k(lower) > min_k(upper) or min_k(upper) < 0, the exact
 //     test fails for every ray of the shaft.
-//  3. Inner boxes are exact unions of their children, so a failed test at an inner node implies
-//     a failed own-box test for every primitive below it (the same monotonicity argument the
-//     traversal kernels rely on, fast_bvh.hpp).
-// Any doubt (sign not definite, stack overflow, single-primitive scene whose root is tested
+//  3. Inner boxes are exact unions of their children and the interval bounds are monotonic under box
+//     inclusion (a sub-box is entered later and left earlier; rounding is monotonic), so a failed
+//     interval test at an inner node implies a failed one — hence a failed exact own-box test for
+//     every ray — at every leaf below it.  A primitive is only ever tested after its own (leaf) box
+//     passed, in the SAH tree and in the reference-topology tree that axis-degenerate rays walk.
+// Any doubt (no definite axis, stack overflow, single-primitive scene whose root is tested
 // without a box, BVH.hpp:166-172) answers "not empty" and the request is traced as before.
 //
 // The function is host/device so that tests/ can run the SAME source on the CPU against a
@@ -53,8 +60,9 @@
 
 struct WrtShaft {
     float o[3];
-    float ilo[3], ihi[3];      // bounds of 1/d per axis (same sign, finite)
+    float ilo[3], ihi[3];      // bounds of 1/d per definite axis (same sign, finite)
     int octant;                // bit k set: every sample direction is negative on axis k
+    int use;                   // bit k set: axis k is definite and takes part in the test
 };
 
 // Builds the bounds of step 1.  tri = the light's tv0, tv1, tv2 (9 floats).  false = give up.
@@ -75,20 +83,26 @@ WRT_SHAFT_HD bool wrt_shaft_make(const float o[3], const float tri[9], WrtShaft*
         dmax = fmaxf(dmax, sqrtf(dx * dx + dy * dy + dz * dz));
     }
     sh->octant = 0;
+    sh->use = 0;
     for (int k = 0; k < 3; k++) {
         float l = c[0][k] - o[k], h = l;
         for (int j = 1; j < 4; j++) { float d = c[j][k] - o[k]; l = fminf(l, d); h = fmaxf(h, d); }
         l -= pad; h += pad;
-        if (!(l > 0.f) && !(h < 0.f)) return false;                       // sign not definite (or NaN)
+        sh->o[k] = o[k];
         lo[k] = l; hi[k] = h;
+        if (!(l == l) || !(h == h)) return false;                         // NaN
+        if (!(l > 0.f) && !(h < 0.f)) continue;                           // sign not definite: axis dropped, |D_k| >= 0
+        sh->use |= 1 << k;
         float m = fminf(fabsf(l), fabsf(h));
         mn2 += m * m;
         if (h < 0.f) sh->octant |= 1 << k;
-        sh->o[k] = o[k];
     }
+    if (sh->use == 0) return false;
     const float dmin = sqrtf(mn2) * (1.f - WRT_SHAFT_PAD_REL);
     dmax = dmax * (1.f + WRT_SHAFT_PAD_REL) + 4.f * pad;
     for (int k = 0; k < 3; k++) {
+        sh->ilo[k] = 0.f; sh->ihi[k] = 0.f;
+        if (!((sh->use >> k) & 1)) continue;
         float a, b;                                                       // inv = |D| / D_k
         if (lo[k] > 0.f) { a = dmin / hi[k]; b = dmax / lo[k]; }          // positive: smallest |D| over largest D_k ...
         else             { a = dmax / hi[k]; b = dmin / lo[k]; }          // negative: hi is the one closest to 0
@@ -107,6 +121,9 @@ WRT_SHAFT_HD bool wrt_shaft_may_hit(const WrtShaft* sh, const float4 nearp, cons
     float lx = fminf(ax * sh->ilo[0], ax * sh->ihi[0]), ux = fmaxf(bx * sh->ilo[0], bx * sh->ihi[0]);
     float ly = fminf(ay * sh->ilo[1], ay * sh->ihi[1]), uy = fmaxf(by * sh->ilo[1], by * sh->ihi[1]);
     float lz = fminf(az * sh->ilo[2], az * sh->ihi[2]), uz = fmaxf(bz * sh->ilo[2], bz * sh->ihi[2]);
+    if (!(sh->use & 1)) { lx = -INFINITY; ux = INFINITY; }                // dropped axes do not constrain
+    if (!(sh->use & 2)) { ly = -INFINITY; uy = INFINITY; }
+    if (!(sh->use & 4)) { lz = -INFINITY; uz = INFINITY; }
     float lb = fmaxf(lx, fmaxf(ly, lz)), ub = fminf(ux, fminf(uy, uz));
     return lb <= ub && ub >= 0.f;
 }

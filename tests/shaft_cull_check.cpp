@@ -3,7 +3,9 @@
 // on the CPU and checks every "empty" verdict by brute force: for many (u, v) samples, corner
 // extremes included, the sample ray — built with the kernel's own float operations — must miss
 // the own box of EVERY primitive under the exact BoundBox::IntersectRay arithmetic.  Also checks
-// that each sample's 1/d lies inside the shaft's bounds.  Prints one JSON line.
+// that each sample's 1/d lies inside the shaft's bounds, and that the shaft's candidate list
+// (wrt_shaft_candidates, phase 1 of k_shadow_soft_list) contains every primitive whose own box a
+// sample ray hits.  Prints one JSON line.
 //
 // usage: shaft_cull_check <config.txt> <bunny.obj|-> <asset_dir> <n_requests> <seed>
 #include <cmath>
@@ -65,7 +67,8 @@ int main(int argc, char** argv) {
             smin[k] = fminf(smin[k], nd.pmin[k]); smax[k] = fmaxf(smax[k], nd.pmax[k]);
         }
     }
-    long long empty = 0, nonempty = 0, gave_up = 0, violations = 0, bound_violations = 0, rays_checked = 0, degenerate_rays = 0;
+    long long empty = 0, nonempty = 0, gave_up = 0, violations = 0, bound_violations = 0, rays_checked = 0, degenerate_rays = 0,
+              lists = 0, list_items = 0, list_overflow = 0, list_violations = 0, list_rays = 0;
     const float top = 1.0f - 1.0f / 16777216.0f;
     for (int r = 0; r < n_req; r++) {
         // origin: a point on a random primitive pushed off along +-normal like BVHStrategy.hpp:15, or a free point
@@ -109,6 +112,10 @@ int main(int argc, char** argv) {
             const bool is_empty = wrt_shaft_is_empty(onodes.data(), nn, o, L.tri);
             if (!made) { gave_up++; if (is_empty) violations++; continue; }
             if (is_empty) empty++; else nonempty++;
+            // candidate list of the same shaft (k_shadow_soft_list, phase 1)
+            int stack[64], list[64];
+            const int cnt = wrt_shaft_candidates(onodes.data(), nn, &sh, stack, 1, 64, list, 64);
+            if (cnt < 0) list_overflow++; else { lists++; list_items += cnt; if (is_empty != (cnt == 0)) violations++; }
             V v0{L.tri[0], L.tri[1], L.tri[2]}, v1{L.tri[3], L.tri[4], L.tri[5]}, v2{L.tri[6], L.tri[7], L.tri[8]};
             const int ns = is_empty ? 40 : 12;
             for (int s = 0; s < ns; s++) {
@@ -130,7 +137,19 @@ int main(int argc, char** argv) {
                     bool neg = dv[k] < 0;
                     if (!(iv[k] >= sh.ilo[k] && iv[k] <= sh.ihi[k]) || neg != (((sh.octant >> k) & 1) != 0) || dv[k] == 0) bound_violations++;
                 }
-                if (dv[0] == 0 || dv[1] == 0 || dv[2] == 0) degenerate_rays++;
+                const bool degenerate = dv[0] == 0 || dv[1] == 0 || dv[2] == 0;
+                if (degenerate) degenerate_rays++;
+                if (cnt >= 0 && !degenerate) {
+                    // every primitive whose own box this ray hits must be on the list
+                    V ov{o[0], o[1], o[2]};
+                    for (int p = 0; p < np; p++) {
+                        if (!slab(&box[6 * (size_t)p], &box[6 * (size_t)p + 3], ov, d, inv)) continue;
+                        bool found = false;
+                        for (int c = 0; c < cnt; c++) found = found || list[c] == p;
+                        if (!found) list_violations++;
+                    }
+                    list_rays++;
+                }
                 if (!is_empty) continue;
                 rays_checked++;
                 V ov{o[0], o[1], o[2]};
@@ -140,8 +159,9 @@ int main(int argc, char** argv) {
         }
     }
     printf("{\"prims\": %d, \"empty\": %lld, \"nonempty\": %lld, \"gave_up\": %lld, \"rays_checked\": %lld, "
-           "\"degenerate_rays\": %lld, \"violations\": %lld, \"bound_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked,
-           degenerate_rays, violations, bound_violations);
+           "\"degenerate_rays\": %lld, \"violations\": %lld, \"bound_violations\": %lld, \"lists\": %lld, \"list_items\": %lld, "
+           "\"list_overflow\": %lld, \"list_rays\": %lld, \"list_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked,
+           degenerate_rays, violations, bound_violations, lists, list_items, list_overflow, list_rays, list_violations);
     wrt_scene_free(sc);
-    return (violations || bound_violations) ? 1 : 0;
+    return (violations || bound_violations || list_violations) ? 1 : 0;
 }

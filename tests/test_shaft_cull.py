@@ -61,7 +61,8 @@ def test_empty_shaft_verdicts_hold_by_brute_force(name, checker, workdir):
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     r = json.loads(out.stdout.strip().splitlines()[-1])
-    assert r["violations"] == 0 and r["bound_violations"] == 0
+    assert r["violations"] == 0 and r["bound_violations"] == 0 and r["list_violations"] == 0
+    assert r["list_rays"] > 0
     assert r["empty"] + r["nonempty"] + r["gave_up"] > 0
     if name in ("water_bunny_tex", "bunny_shadow"):
         assert r["empty"] > 0 and r["nonempty"] > 0          # the test exercises both verdicts

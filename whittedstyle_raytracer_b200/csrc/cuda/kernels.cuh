@@ -490,6 +490,108 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
               st, refill);
 }
 
+// ---- K4b': soft shadows through per-request candidate lists ----
+// The 50 rays of a request share their origin and aim at one small light, so they cross almost the same
+// nodes; k_shadow_soft pays that walk (descend from the root to the neighbourhood of the origin, ~20-30 node
+// steps on the bunny's surface) 50 times.  Here a warp takes WRT_LIST_REQS requests at a time:
+//   phase 1  one lane per request walks the SAH tree ONCE with the conservative shaft test (shaft_cull.h) and
+//            writes the primitives whose leaf box some ray of the shaft may hit to a list, nearest first;
+//   phase 2  the 16 x 50 = 800 sample rays are spread over 25 full warp passes; a ray tests only the list:
+//            own-box test (exact BoundBox::IntersectRay) + intersection test, stop at the first blocker.
+// Exact: a non-degenerate ray tests precisely the primitives whose own box it hits,
+// and those are all in the list, so OR over the list == the any-hit walk.  Requests whose list would
+// exceed WRT_LIST_CAP, shafts without a definite axis, and axis-degenerate rays are traced by the
+// ordinary per-ray walk.  Not used for scenes with light-avatar primitives (literal hasIntersection path).
+#define WRT_LIST_REQS 16
+#define WRT_LIST_CAP 64
+#define WRT_LIST_PASSES (WRT_LIST_REQS * WRT_SOFT_SAMPLES / 32)
+static_assert(WRT_LIST_REQS * WRT_SOFT_SAMPLES % 32 == 0, "a request batch must fill whole warp passes");
+
+__global__ void WRT_TRACE_BOUNDS k_shadow_soft_list(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
+                                                    int work_slot, unsigned seed, int stack_rows, int* __restrict__ scratch) {
+    extern __shared__ int smem[];
+    __shared__ int s_cnt[4][WRT_LIST_REQS];                    // 128 threads = 4 warps
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
+    const int par = level % WRT_SETS;
+    int* lists = scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (WRT_LIST_REQS * WRT_LIST_CAP);
+    unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
+    while (true) {
+        unsigned long long claimed = 0;
+        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)WRT_LIST_REQS);
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        if (claimed >= nreq) break;
+        const unsigned base = (unsigned)claimed;
+        // ---- phase 1: candidate lists ----
+        if (lane < WRT_LIST_REQS) {
+            int cnt = 0;
+            const unsigned req = base + lane;
+            if (req < nreq) {
+                cnt = -1;
+                float4 o4 = fb.preq_o[par][req];
+                uint4 k = fb.preq_k[par][req];
+                const WrtLight* L = s.lights + k.x;
+                float tri[9];
+                for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
+                const float o[3] = {o4.x, o4.y, o4.z};
+                WrtShaft sh;
+                if (wrt_shaft_make(o, tri, &sh))
+                    cnt = wrt_shaft_candidates(s.onodes, s.n_nodes, &sh, st.base, st.stride, stack_rows, lists + lane * WRT_LIST_CAP, WRT_LIST_CAP);
+            }
+            s_cnt[warp][lane] = cnt;
+        }
+        __syncwarp();
+        // ---- phase 2: 25 passes of 32 sample rays ----
+#pragma unroll 1
+        for (int pass = 0; pass < WRT_LIST_PASSES; pass++) {
+            const unsigned j = (unsigned)pass * 32u + lane;
+            const unsigned rq = j / WRT_SOFT_SAMPLES, sample = j - rq * WRT_SOFT_SAMPLES;
+            const unsigned req = base + rq;
+            bool lit = false;
+            unsigned out = 0;
+            if (req < nreq) {
+                float4 o4 = fb.preq_o[par][req];
+                uint4 k = fb.preq_k[par][req];
+                f3 v0, v1, v2;
+                if (k.x < WRT_INLINE_LIGHTS) {
+                    const WrtLight& L = s.lights_c[k.x];
+                    v0 = mk3(L.tri[0], L.tri[1], L.tri[2]); v1 = mk3(L.tri[3], L.tri[4], L.tri[5]); v2 = mk3(L.tri[6], L.tri[7], L.tri[8]);
+                } else {
+                    const WrtLight* L = s.lights + k.x;
+                    v0 = mk3(L->tri[0], L->tri[1], L->tri[2]); v1 = mk3(L->tri[3], L->tri[4], L->tri[5]); v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
+                }
+                float u, v;
+                wrt_light_sample_uv(seed, k.y, k.z, k.x, sample, &u, &v);
+                f3 lightPos = (1 - u - v) * v0 + u * v1 + v * v2;                 // Triangle.hpp:139-145
+                f3 orig = mk3(o4);
+                f3 raydir = normalized(lightPos - orig);
+                const float dis = norm(lightPos - orig);
+                const Ray r = make_ray(orig, raydir);
+                out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
+                const int cnt = s_cnt[warp][rq];
+                bool occ = false;
+                if (cnt < 0 || degenerate_dir(raydir)) {
+                    occ = occluded(s, degenerate_dir(raydir) ? s.nodes : s.fnodes, r, dis, st);
+                } else {
+                    const int* list = lists + rq * WRT_LIST_CAP;
+                    for (int c = 0; c < cnt && !occ; c++) occ = occluder_cache_hit(s, r, dis, list[c]);
+                }
+                lit = !occ;
+            }
+            // one float atomic per request segment of the pass (small integer sums are exact and order-free)
+            const unsigned lit_mask = __ballot_sync(0xffffffffu, lit);
+            const unsigned rq0 = ((unsigned)pass * 32u) / WRT_SOFT_SAMPLES;
+            const unsigned first = __ballot_sync(0xffffffffu, rq == rq0);        // lanes of the pass's first request
+            const unsigned mine = rq == rq0 ? first : ~first;
+            const unsigned n_lit = __popc(lit_mask & mine);
+            if (n_lit && lane == (unsigned)(__ffs(mine) - 1)) atomicAdd(fb.coeff[par] + out, (float)n_lit);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- K4c: directional-light shadows, Renderer.hpp:381-400 (dilated-tree culling, dev_traverse.cuh) ----
 __global__ void __launch_bounds__(128) k_shadow_directional(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
                                                             int level) {

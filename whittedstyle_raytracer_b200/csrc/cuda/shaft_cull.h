@@ -128,6 +128,69 @@ WRT_SHAFT_HD bool wrt_shaft_may_hit(const WrtShaft* sh, const float4 nearp, cons
     return lb <= ub && ub >= 0.f;
 }
 
+// The same test, also returning the lower bound of the entry distance (orders the candidate walk).
+WRT_SHAFT_HD bool wrt_shaft_may_hit_lb(const WrtShaft* sh, const float4 nearp, const float4 farp, float* lb_out) {
+    float ax = nearp.x - sh->o[0], ay = nearp.y - sh->o[1], az = nearp.z - sh->o[2];
+    float bx = farp.x - sh->o[0], by = farp.y - sh->o[1], bz = farp.z - sh->o[2];
+    float lx = fminf(ax * sh->ilo[0], ax * sh->ihi[0]), ux = fmaxf(bx * sh->ilo[0], bx * sh->ihi[0]);
+    float ly = fminf(ay * sh->ilo[1], ay * sh->ihi[1]), uy = fmaxf(by * sh->ilo[1], by * sh->ihi[1]);
+    float lz = fminf(az * sh->ilo[2], az * sh->ihi[2]), uz = fmaxf(bz * sh->ilo[2], bz * sh->ihi[2]);
+    if (!(sh->use & 1)) { lx = -INFINITY; ux = INFINITY; }
+    if (!(sh->use & 2)) { ly = -INFINITY; uy = INFINITY; }
+    if (!(sh->use & 4)) { lz = -INFINITY; uz = INFINITY; }
+    float lb = fmaxf(lx, fmaxf(ly, lz)), ub = fminf(ux, fminf(uy, uz));
+    *lb_out = lb;
+    return lb <= ub && ub >= 0.f;
+}
+
+// Candidate occluders of a shaft: every primitive whose leaf box may be hit by some ray of the shaft, written
+// to out[0 .. n) nearest-first (by the entry lower bound).  A sample ray of the request that is not
+// axis-degenerate tests exactly the primitives whose own box it hits and all of those are
+// in the list, so "any list member blocks the ray" equals the any-hit traversal's answer.
+// Returns n, or -1 when the list would exceed out_cap or the walk's stack would overflow (the request is then
+// traced ray by ray).  stack[k * stack_stride], k < stack_cap, is the caller's traversal stack.
+WRT_SHAFT_HD int wrt_shaft_candidates(const float4* onodes, int n_nodes, const WrtShaft* sh, int* stack, int stack_stride,
+                                      int stack_cap, int* out, int out_cap) {
+    if (n_nodes <= 0) return 0;
+    const float4* nodes = onodes + (size_t)sh->octant * 2 * (size_t)n_nodes;
+    union { float f; int i; } w;
+    w.f = WRT_SHAFT_LD4(nodes).w;
+    int cur = w.i;
+    if (cur < 0) return -1;                                               // lone primitive: tested without its box
+    int sp = 0, n = 0;
+    while (true) {
+        const float4* nd = nodes + 2 * (size_t)cur;
+        float4 l0 = WRT_SHAFT_LD4(nd), l1 = WRT_SHAFT_LD4(nd + 1), r0 = WRT_SHAFT_LD4(nd + 2), r1 = WRT_SHAFT_LD4(nd + 3);
+        float tl, tr;
+        bool hl = wrt_shaft_may_hit_lb(sh, l0, l1, &tl), hr = wrt_shaft_may_hit_lb(sh, r0, r1, &tr);
+        w.f = l0.w; const int linkL = w.i;
+        w.f = r0.w; const int linkR = w.i;
+        const bool right_first = hl && hr && tr < tl;
+        // leaves: into the list, nearer one first
+        if (hl && linkL < 0 && hr && linkR < 0) {
+            if (n + 2 > out_cap) return -1;
+            out[n++] = right_first ? ~linkR : ~linkL;
+            out[n++] = right_first ? ~linkL : ~linkR;
+            hl = false; hr = false;
+        } else {
+            if (hl && linkL < 0) { if (n == out_cap) return -1; out[n++] = ~linkL; hl = false; }
+            if (hr && linkR < 0) { if (n == out_cap) return -1; out[n++] = ~linkR; hr = false; }
+        }
+        if (hl && hr) {
+            if (sp == stack_cap) return -1;
+            stack[sp * stack_stride] = right_first ? linkL : linkR;
+            ++sp;
+            cur = right_first ? linkR : linkL;
+        } else if (hl) cur = linkL;
+        else if (hr) cur = linkR;
+        else {
+            if (sp == 0) return n;
+            --sp;
+            cur = stack[sp * stack_stride];
+        }
+    }
+}
+
 // True when no leaf box of the tree can be hit by any ray of the shaft.
 // onodes: the 8 octant copies of the SAH tree (2 float4 per record, n_nodes records per copy).
 WRT_SHAFT_HD bool wrt_shaft_is_empty(const float4* onodes, int n_nodes, const float o[3], const float tri[9]) {

@@ -72,6 +72,9 @@ struct WrtContext {
     int refill = 16;                   // idle lanes that trigger a refill on deep ray-tree levels
     int refill_soft = 24;
     bool shaft_cull = true;            // soft shadows: answer requests whose light shaft is empty without tracing (shaft_cull.h)
+    bool soft_lists = true;            // soft shadows: per-request candidate lists (k_shadow_soft_list) instead of per-ray walks
+    int lists_from_level = 0;
+    int* d_lists[WRT_SIDE_STREAMS] = {};
     bool unlit_cull = true;            // drop shadow requests of lights whose shading terms are exactly 0 at the point
     int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
     int chunk_div = 16;                // work claiming: 0 = one atomic per refill, k = chunks of n/(warps*k) items
@@ -214,6 +217,10 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
         if (frame_alloc(c, &fb.coeff[k], (size_t)cap * std::max(1, ds.n_lights))) return 1;
     }
     if (frame_alloc(c, &fb.counters, wrt::C_TOTAL)) return 1;
+    // candidate lists of k_shadow_soft_list: one private block per warp, one set per side stream (launches
+    // on different side streams overlap)
+    for (int k = 0; k < WRT_SIDE_STREAMS; k++)
+        if (frame_alloc(c, &c->d_lists[k], (size_t)c->num_sms * c->trace_blocks_per_sm * 4 * WRT_LIST_REQS * WRT_LIST_CAP)) return 1;
     c->batch_slots = slots;
     c->fb_lights = ds.n_lights; c->fb_point = ds.n_point_lights; c->fb_dir = ds.n_dir_lights;
     return 0;
@@ -318,8 +325,16 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
                                                           c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
             } else {
                 LaunchScope ls(c, ss, F_SHADOW_SOFT);
-                k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
-                                                          d >= c->cache_from_level ? 1 : 0);
+                // per-request candidate lists (kernels.cuh, K4b'); scenes with light avatars keep the per-ray kernel,
+                // whose literal hasIntersection path they need, and so does WRT_TRAVERSAL_EXHAUSTIVE
+                const bool lists = c->soft_lists && !ds.has_light_prims && ds.n_nodes > 0 && c->traversal == WRT_TRAVERSAL_PRUNED &&
+                                   d >= c->lists_from_level;
+                if (lists)
+                    k_shadow_soft_list<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->stack_rows,
+                                                                   c->d_lists[d % WRT_SIDE_STREAMS]);
+                else
+                    k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
+                                                              d >= c->cache_from_level ? 1 : 0);
             }
         }
         if (ds.n_dir_lights > 0) {
@@ -517,6 +532,8 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_CACHE_FROM")) c->cache_from_level = atoi(e);
     if (const char* e = getenv("WRT_SHAFT_CULL")) c->shaft_cull = atoi(e) != 0;
     if (const char* e = getenv("WRT_UNLIT_CULL")) c->unlit_cull = atoi(e) != 0;
+    if (const char* e = getenv("WRT_SOFT_LISTS")) c->soft_lists = atoi(e) != 0;
+    if (const char* e = getenv("WRT_LISTS_FROM")) c->lists_from_level = atoi(e);
     if (const char* e = getenv("WRT_CHUNK_DIV")) c->chunk_div = std::max(0, std::min(255, atoi(e)));
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));

@@ -502,8 +502,12 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 // and those are all in the list, so OR over the list == the any-hit walk.  Requests whose list would
 // exceed WRT_LIST_CAP, shafts without a definite axis, and axis-degenerate rays are traced by the
 // ordinary per-ray walk.  Not used for scenes with light-avatar primitives (literal hasIntersection path).
-#define WRT_LIST_REQS 16
-#define WRT_LIST_CAP 64
+#ifndef WRT_LIST_REQS
+#define WRT_LIST_REQS 32
+#endif
+#ifndef WRT_LIST_CAP
+#define WRT_LIST_CAP 192
+#endif
 #define WRT_LIST_PASSES (WRT_LIST_REQS * WRT_SOFT_SAMPLES / 32)
 static_assert(WRT_LIST_REQS * WRT_SOFT_SAMPLES % 32 == 0, "a request batch must fill whole warp passes");
 

@@ -38,10 +38,11 @@ enum CounterSlot {
     C_NDREQ = 32,                // [9] directional-light shadow requests per level
     C_VALID0 = 48,               // valid (non-padding) primary rays
     C_OVERFLOW = 49,             // set when a queue append was dropped
-    C_WORK = 64,                 // work-distribution counters, one per persistent launch
+    C_WORK = 192,                // [<= 32 x 2] work-distribution counters (64-bit), one per persistent launch
     C_NCULL = 128,               // [9] soft-shadow requests answered by the shaft test (shaft_cull.h), never queued
     C_NSKIP = 144,               // [9] point-light requests whose light terms vanish (dev_shade.cuh), never queued
     C_NDSKIP = 160,              // [9] the same for directional lights
+    C_POOL = 176,                // [9] fill level of the candidate-list pool (k_soft_lists)
     C_TOTAL = 256
 };
 
@@ -496,7 +497,7 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 // steps on the bunny's surface) 50 times.  Here a warp takes WRT_LIST_REQS requests at a time:
 //   phase 1  one lane per request walks the SAH tree ONCE with the conservative shaft test (shaft_cull.h) and
 //            writes the primitives whose leaf box some ray of the shaft may hit to a list, nearest first;
-//   phase 2  the 16 x 50 = 800 sample rays are spread over 25 full warp passes; a ray tests only the list:
+//   phase 2  the 32 x 50 = 1600 sample rays are spread over 50 full warp passes; a ray tests only the list:
 //            own-box test (exact BoundBox::IntersectRay) + intersection test, stop at the first blocker.
 // Exact: a non-degenerate ray tests precisely the primitives whose own box it hits,
 // and those are all in the list, so OR over the list == the any-hit walk.  Requests whose list would
@@ -508,8 +509,7 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 #ifndef WRT_LIST_CAP
 #define WRT_LIST_CAP 192
 #endif
-#define WRT_LIST_PASSES (WRT_LIST_REQS * WRT_SOFT_SAMPLES / 32)
-static_assert(WRT_LIST_REQS * WRT_SOFT_SAMPLES % 32 == 0, "a request batch must fill whole warp passes");
+static_assert(WRT_LIST_REQS <= 32, "one lane per request in phase 1");
 
 __global__ void WRT_TRACE_BOUNDS k_shadow_soft_list(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
                                                     int work_slot, unsigned seed, int stack_rows, int* __restrict__ scratch) {
@@ -523,13 +523,17 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft_list(const __grid_constant__ DevS
     int* lists = scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (WRT_LIST_REQS * WRT_LIST_CAP);
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
     while (true) {
+        // Fixed batches.  (Guided, shrinking claims towards the end of the queue were tried to fix the tail — ncu:
+        // achieved occupancy 49 % of the 62 % the registers allow — and lost 14 %: a deep level only holds
+        // ~1.7 batches per warp, so most of the work ran in small batches whose phase 1 uses few lanes.)
         unsigned long long claimed = 0;
-        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)WRT_LIST_REQS);
+        const unsigned n_claim = WRT_LIST_REQS;
+        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)n_claim);
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
         if (claimed >= nreq) break;
         const unsigned base = (unsigned)claimed;
         // ---- phase 1: candidate lists ----
-        if (lane < WRT_LIST_REQS) {
+        if (lane < n_claim) {
             int cnt = 0;
             const unsigned req = base + lane;
             if (req < nreq) {
@@ -548,14 +552,15 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft_list(const __grid_constant__ DevS
         }
         __syncwarp();
         // ---- phase 2: 25 passes of 32 sample rays ----
+        const int passes = (int)((n_claim * WRT_SOFT_SAMPLES + 31u) / 32u);
 #pragma unroll 1
-        for (int pass = 0; pass < WRT_LIST_PASSES; pass++) {
+        for (int pass = 0; pass < passes; pass++) {
             const unsigned j = (unsigned)pass * 32u + lane;
             const unsigned rq = j / WRT_SOFT_SAMPLES, sample = j - rq * WRT_SOFT_SAMPLES;
             const unsigned req = base + rq;
             bool lit = false;
             unsigned out = 0;
-            if (req < nreq) {
+            if (rq < n_claim && req < nreq) {
                 float4 o4 = fb.preq_o[par][req];
                 uint4 k = fb.preq_k[par][req];
                 f3 v0, v1, v2;
@@ -579,6 +584,8 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft_list(const __grid_constant__ DevS
                 if (cnt < 0 || degenerate_dir(raydir)) {
                     occ = occluded(s, degenerate_dir(raydir) ? s.nodes : s.fnodes, r, dis, st);
                 } else {
+                    // own-box test (exact BoundBox::IntersectRay) then the intersection test, per list member
+                    // (fetching the next member's box ahead of the test was tried: +1 %, 8 more registers)
                     const int* list = lists + rq * WRT_LIST_CAP;
                     for (int c = 0; c < cnt && !occ; c++) occ = occluder_cache_hit(s, r, dis, list[c]);
                 }
@@ -593,6 +600,135 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft_list(const __grid_constant__ DevS
             if (n_lit && lane == (unsigned)(__ffs(mine) - 1)) atomicAdd(fb.coeff[par] + out, (float)n_lit);
         }
         __syncwarp();
+    }
+}
+
+// ---- K4b'': the same in two launches (the default) ----
+// In the fused kernel a warp owns a batch of 32 requests from the shaft walk to the last of its 1600 rays:
+// ~0.4 ms of dependent work per batch, while a deep level only holds ~1.7 batches per warp — ncu: achieved
+// occupancy 49 % of the 62 % the registers allow, the launch ends with a long under-filled tail.  Split:
+//   k_soft_lists      phase 1 only.  The lists go to a pool (bump allocation, one atomic per warp); a request
+//                     keeps {offset, count}, count < 0 = trace ray by ray.
+//   k_soft_list_rays  phase 2 only.  The level's nreq x 50 rays are cut into warp passes of 32 consecutive rays
+//                     and handed out 8 passes at a time from a global counter: balanced to ~10 us.
+struct SoftListBuffers {
+    int*  scratch;        // one block of 32 x WRT_LIST_CAP ints per warp: the walk writes here, then compacts
+    int*  pool;           // compacted lists
+    int2* ref;            // per request: {pool offset, count}
+    unsigned pool_cap;
+};
+#define WRT_LIST_CHUNK_PASSES 8
+
+__global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
+                                              int work_slot, int stack_rows, SoftListBuffers lb) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
+    const int par = level % WRT_SETS;
+    int* mine = lb.scratch + (((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane) * WRT_LIST_CAP;
+    unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
+    unsigned* pool_head = fb.counters + C_POOL + level;
+    while (true) {
+        unsigned long long claimed = 0;
+        if (lane == 0) claimed = atomicAdd(work, 32ull);
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        if (claimed >= nreq) break;
+        const unsigned req = (unsigned)claimed + lane;
+        int cnt = 0;
+        if (req < nreq) {
+            cnt = -1;
+            float4 o4 = fb.preq_o[par][req];
+            uint4 k = fb.preq_k[par][req];
+            const WrtLight* L = s.lights + k.x;
+            float tri[9];
+            for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
+            const float o[3] = {o4.x, o4.y, o4.z};
+            WrtShaft sh;
+            if (wrt_shaft_make(o, tri, &sh))
+                cnt = wrt_shaft_candidates(s.onodes, s.n_nodes, &sh, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+        }
+        // pool space for the warp's lists: one atomic
+        const int n = cnt > 0 ? cnt : 0;
+        int incl = n;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= (unsigned)off) incl += v;
+        }
+        const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+        unsigned base = 0;
+        if (lane == 31 && total > 0) base = atomicAdd(pool_head, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        const unsigned off = base + (unsigned)(incl - n);
+        if (total > 0 && (base > lb.pool_cap || total > lb.pool_cap - base) && cnt > 0) cnt = -1;     // pool full: per-ray walk
+        if (req < nreq) {
+            for (int i = 0; i < cnt; i++) lb.pool[off + i] = mine[i];
+            lb.ref[req] = make_int2((int)off, cnt);
+        }
+    }
+}
+
+__global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
+                                                  int work_slot, unsigned seed, SoftListBuffers lb) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);      // host guarantees nreq * 50 < 2^32
+    const int par = level % WRT_SETS;
+    const unsigned n_rays = nreq * WRT_SOFT_SAMPLES, n_pass = (n_rays + 31u) / 32u;
+    unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
+    while (true) {
+        unsigned long long claimed = 0;
+        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)WRT_LIST_CHUNK_PASSES);
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        if (claimed >= n_pass) break;
+        const unsigned p0 = (unsigned)claimed, p1 = p0 + WRT_LIST_CHUNK_PASSES < n_pass ? p0 + WRT_LIST_CHUNK_PASSES : n_pass;
+#pragma unroll 1
+        for (unsigned pass = p0; pass < p1; pass++) {
+            const unsigned j = pass * 32u + lane;
+            const unsigned req = j / WRT_SOFT_SAMPLES, sample = j - req * WRT_SOFT_SAMPLES;
+            bool lit = false;
+            unsigned out = 0;
+            if (req < nreq) {
+                float4 o4 = fb.preq_o[par][req];
+                uint4 k = fb.preq_k[par][req];
+                const int2 ref = lb.ref[req];
+                f3 v0, v1, v2;
+                if (k.x < WRT_INLINE_LIGHTS) {
+                    const WrtLight& L = s.lights_c[k.x];
+                    v0 = mk3(L.tri[0], L.tri[1], L.tri[2]); v1 = mk3(L.tri[3], L.tri[4], L.tri[5]); v2 = mk3(L.tri[6], L.tri[7], L.tri[8]);
+                } else {
+                    const WrtLight* L = s.lights + k.x;
+                    v0 = mk3(L->tri[0], L->tri[1], L->tri[2]); v1 = mk3(L->tri[3], L->tri[4], L->tri[5]); v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
+                }
+                float u, v;
+                wrt_light_sample_uv(seed, k.y, k.z, k.x, sample, &u, &v);
+                f3 lightPos = (1 - u - v) * v0 + u * v1 + v * v2;                 // Triangle.hpp:139-145
+                f3 orig = mk3(o4);
+                f3 raydir = normalized(lightPos - orig);
+                const float dis = norm(lightPos - orig);
+                const Ray r = make_ray(orig, raydir);
+                out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
+                bool occ = false;
+                if (ref.y < 0 || degenerate_dir(raydir)) {
+                    occ = occluded(s, degenerate_dir(raydir) ? s.nodes : s.fnodes, r, dis, st);
+                } else {
+                    const int* list = lb.pool + ref.x;
+                    for (int c = 0; c < ref.y && !occ; c++) occ = occluder_cache_hit(s, r, dis, list[c]);
+                }
+                lit = !occ;
+            }
+            // one float atomic per request segment of the pass (small integer sums are exact and order-free)
+            const unsigned lit_mask = __ballot_sync(0xffffffffu, lit);
+            const unsigned rq0 = (pass * 32u) / WRT_SOFT_SAMPLES;
+            const unsigned first = __ballot_sync(0xffffffffu, req == rq0);       // lanes of the pass's first request
+            const unsigned mine = req == rq0 ? first : ~first;
+            const unsigned n_lit = __popc(lit_mask & mine);
+            if (n_lit && lane == (unsigned)(__ffs(mine) - 1)) atomicAdd(fb.coeff[par] + out, (float)n_lit);
+        }
     }
 }
 

@@ -617,8 +617,13 @@ struct SoftListBuffers {
     int2* ref;            // per request: {pool offset, count}
     unsigned pool_cap;
 };
+#ifndef WRT_LIST_CHUNK_PASSES
 #define WRT_LIST_CHUNK_PASSES 8
+#endif
 
+// (Phase 1 as a run_queue query with per-lane refill was tried — walk lengths differ a lot, 7-13 of 32 lanes are
+// active — and was slower, 19.5 vs 18.3 ms per frame: the refilled lanes run the ~200-instruction shaft set-up a few
+// lanes at a time, and lists allocated out of request order scatter phase 2's reads.)
 __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
                                               int work_slot, int stack_rows, SoftListBuffers lb) {
     extern __shared__ int smem[];

@@ -47,7 +47,10 @@ ALGO_TESTS = {"config": (75.1, 4.11), "bunny_shadow_4k": (77.5, 4.28), "gla_bunn
 ALGO_BYTES = {
     "trace_closest": 48.0,                 # ray 2 x float4 read + hit float4 written, per ray
     "shadow_hard": 36.0,                   # request 32 B read + coefficient 4 B written, per ray
-    "shadow_soft": 36.0 / 50.0,            # one 32 B request + one 4 B coefficient serve 50 sample rays
+    # one 32 B request + 8 B list reference + 4 B coefficient serve 50 sample rays, which also read the request's
+    # candidate list once (written once by k_soft_lists): ~25 members x 4 B x (write + read) per request
+    "shadow_soft": (44.0 + 8.0 * 25.0) / 50.0,
+    "soft_lists": 32.0 + 8.0 + 4.0 * 25.0, # per request: request read, reference + list written
     "shadow_directional": 36.0,
 }
 
@@ -361,16 +364,23 @@ def run_cuda_arm(args):
     fma_tf, muladd_tf = ctx.measure_fp32_peak()
     fpr = flops_per_ray(args.workload)
     bpu = ALGO_BYTES.get(dom, 112.0)
+    kernel_names = {"shadow_soft": "k_soft_list_rays", "soft_lists": "k_soft_lists", "trace_closest": "k_trace_closest",
+                    "shadow_hard": "k_shadow_hard", "surface": "k_surface_spawn"}
     roofline = {
-        "kernel": f"k_{dom}", "share_of_step": dom_share, "launches_per_step": dom_launches,
+        "kernel": kernel_names.get(dom, f"k_{dom}"), "share_of_step": dom_share, "launches_per_step": dom_launches,
         "avg_launch_ms": fam_ms[dom] / dom_launches, "units_per_step": dom_units,
         "bound": "hbm", "achieved": dom_units * bpu / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": dom_units * bpu / dom_s / 1e9 / hbm_peak, "peak_source": peak_src,
         "algorithmic_bytes_per_unit": bpu, "algorithmic_bytes_per_launch": dom_units * bpu / dom_launches,
-        "traffic": profile_traffic(dom),
-        "binding_bound": "NOT hbm and not tensor: FP32 issue rate (deep levels: SM throughput 84 %, IPC 3.3/4) and L1 load "
-                         "latency (level 0); `bound` says hbm only because the schema offers hbm|tensor — see `fp32` and DESIGN.md section 6",
+        "traffic": profile_traffic(kernel_names.get(dom, f"k_{dom}")),
+        "binding_bound": "NOT hbm and not tensor: instruction issue + L1 load latency of a divergent per-lane loop "
+                         "(own-box + triangle tests over the request's candidate list); `bound` says hbm only because the "
+                         "schema offers hbm|tensor — see `fp32` and DESIGN.md section 6",
+        # FP32 work: the reference's own traversal counts per ray x the rays this kernel traces.
+        # (Counting the frame's reference-equivalent rays instead gives `frame_equivalent_tflops`: what the reference's
+        # algorithm would have needed for the same image in the same time.)
         "fp32": {"algorithmic_flops_per_ray": fpr, "achieved_tflops": dom_units * fpr / dom_s / 1e12,
+                 "frame_equivalent_tflops": rays_frame * fpr / (ms_per_step * 1e-3) / 1e12,
                  "peak_tflops_fma_measured": fma_tf, "peak_tflops_fmul_fadd_measured": muladd_tf,
                  "frac_of_fma_peak": dom_units * fpr / dom_s / 1e12 / max(fma_tf, 1e-9),
                  "frac_of_fmul_fadd_peak": dom_units * fpr / dom_s / 1e12 / max(muladd_tf, 1e-9)},
@@ -426,7 +436,7 @@ def profile_traffic(family):
     p = REPO / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(f"k_{family}")
+            return json.loads(p.read_text()).get(family)
         except (ValueError, OSError):
             return None
     return None

@@ -33,7 +33,7 @@ int fail(const std::string& msg) {
         }                                                                                             \
     } while (0)
 
-enum Family { F_RAYGEN, F_TRACE, F_SURFACE, F_SHADOW_HARD, F_SHADOW_SOFT, F_SHADOW_DIR, F_SHADE, F_COMBINE, F_RESOLVE };
+enum Family { F_RAYGEN, F_TRACE, F_SURFACE, F_SHADOW_HARD, F_SHADOW_SOFT, F_SHADOW_DIR, F_SHADE, F_COMBINE, F_RESOLVE, F_SOFT_LISTS };
 
 struct TimedLaunch {
     int family;
@@ -334,22 +334,27 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
                 k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8),
                                                           c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
             } else {
-                LaunchScope ls(c, ss, F_SHADOW_SOFT);
                 // per-request candidate lists (kernels.cuh, K4b'); scenes with light avatars keep the per-ray kernel,
                 // whose literal hasIntersection path they need, and so does WRT_TRAVERSAL_EXHAUSTIVE
                 const bool lists = c->soft_lists && !ds.has_light_prims && ds.n_nodes > 0 && c->traversal == WRT_TRAVERSAL_PRUNED &&
                                    d >= c->lists_from_level;
                 if (lists && c->soft_lists_mode == 2 && (unsigned long long)fb.preq_cap * WRT_SOFT_SAMPLES < (1ull << 32)) {
                     const SoftListBuffers& lb = c->list_bufs[d % WRT_SIDE_STREAMS];
-                    k_soft_lists<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->stack_rows, lb);
-                    ++c->launches;
+                    {
+                        LaunchScope ls(c, ss, F_SOFT_LISTS);
+                        k_soft_lists<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->stack_rows, lb);
+                    }
+                    LaunchScope ls(c, ss, F_SHADOW_SOFT);
                     k_soft_list_rays<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, lb);
-                } else if (lists)
+                } else if (lists) {
+                    LaunchScope ls(c, ss, F_SHADOW_SOFT);
                     k_shadow_soft_list<<<grid_for(c, c->list_blocks_per_sm), TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->stack_rows,
-                                                                   c->d_lists[d % WRT_SIDE_STREAMS]);
-                else
+                                                                                          c->d_lists[d % WRT_SIDE_STREAMS]);
+                } else {
+                    LaunchScope ls(c, ss, F_SHADOW_SOFT);
                     k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
                                                               d >= c->cache_from_level ? 1 : 0);
+                }
             }
         }
         if (ds.n_dir_lights > 0) {

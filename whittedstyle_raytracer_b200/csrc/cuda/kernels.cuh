@@ -494,125 +494,27 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 // ---- K4b': soft shadows through per-request candidate lists ----
 // The 50 rays of a request share their origin and aim at one small light, so they cross almost the same
 // nodes; k_shadow_soft pays that walk (descend from the root to the neighbourhood of the origin, ~20-30 node
-// steps on the bunny's surface) 50 times.  Here a warp takes WRT_LIST_REQS requests at a time:
-//   phase 1  one lane per request walks the SAH tree ONCE with the conservative shaft test (shaft_cull.h) and
-//            writes the primitives whose leaf box some ray of the shaft may hit to a list, nearest first;
-//   phase 2  the 32 x 50 = 1600 sample rays are spread over 50 full warp passes; a ray tests only the list:
-//            own-box test (exact BoundBox::IntersectRay) + intersection test, stop at the first blocker.
-// Exact: a non-degenerate ray tests precisely the primitives whose own box it hits,
-// and those are all in the list, so OR over the list == the any-hit walk.  Requests whose list would
-// exceed WRT_LIST_CAP, shafts without a definite axis, and axis-degenerate rays are traced by the
-// ordinary per-ray walk.  Not used for scenes with light-avatar primitives (literal hasIntersection path).
-#ifndef WRT_LIST_REQS
-#define WRT_LIST_REQS 32
-#endif
+// steps on the bunny's surface) 50 times.  Instead:
+//   k_soft_lists      one lane per request walks the SAH tree ONCE with the conservative shaft test (shaft_cull.h)
+//                     and writes the primitives whose leaf box some ray of the shaft may hit, nearest first, to a
+//                     pool (bump allocation, one atomic per warp); the request keeps {offset, count}, count < 0 =
+//                     trace ray by ray.
+//   k_soft_list_rays  the level's nreq x 50 rays are cut into warp passes of 32 consecutive rays, handed out 8 passes
+//                     at a time from a global counter (balanced to ~10 us).  A ray tests only its request's list:
+//                     own-box test (exact BoundBox::IntersectRay) + intersection test, first blocker ends it.
+// Exact: a non-degenerate ray tests precisely the primitives whose own box it hits, and
+// those are all in the list, so OR over the list == the any-hit walk.  Requests whose list would exceed
+// WRT_LIST_CAP, shafts without a definite axis, and axis-degenerate rays are traced by the ordinary per-ray
+// walk.  Not used for scenes with light-avatar primitives (literal hasIntersection path).
+// Tried and dropped (profiles/NOTES.md): one fused kernel in which a warp owns 32 requests from the walk to the last
+// of their 1600 rays (19.1 vs 18.3 ms: ~0.4 ms of dependent work per batch, ~1.7 batches per warp on a deep level,
+// long under-filled tail); 32-byte list entries carrying `plane - o` so that the ray kernel needs no box fetch
+// (-11 % instructions, but 4x the DRAM traffic of both kernels: 18.4 ms); list build with per-lane refill (19.5 ms).
 #ifndef WRT_LIST_CAP
 #define WRT_LIST_CAP 192
 #endif
-static_assert(WRT_LIST_REQS <= 32, "one lane per request in phase 1");
-
-__global__ void WRT_TRACE_BOUNDS k_shadow_soft_list(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
-                                                    int work_slot, unsigned seed, int stack_rows, int* __restrict__ scratch) {
-    extern __shared__ int smem[];
-    __shared__ int s_cnt[4][WRT_LIST_REQS];                    // 128 threads = 4 warps
-    Stack st;
-    st.init(smem, threadIdx.x, blockDim.x);
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    const int par = level % WRT_SETS;
-    int* lists = scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (WRT_LIST_REQS * WRT_LIST_CAP);
-    unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
-    while (true) {
-        // Fixed batches.  (Guided, shrinking claims towards the end of the queue were tried to fix the tail — ncu:
-        // achieved occupancy 49 % of the 62 % the registers allow — and lost 14 %: a deep level only holds
-        // ~1.7 batches per warp, so most of the work ran in small batches whose phase 1 uses few lanes.)
-        unsigned long long claimed = 0;
-        const unsigned n_claim = WRT_LIST_REQS;
-        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)n_claim);
-        claimed = __shfl_sync(0xffffffffu, claimed, 0);
-        if (claimed >= nreq) break;
-        const unsigned base = (unsigned)claimed;
-        // ---- phase 1: candidate lists ----
-        if (lane < n_claim) {
-            int cnt = 0;
-            const unsigned req = base + lane;
-            if (req < nreq) {
-                cnt = -1;
-                float4 o4 = fb.preq_o[par][req];
-                uint4 k = fb.preq_k[par][req];
-                const WrtLight* L = s.lights + k.x;
-                float tri[9];
-                for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
-                const float o[3] = {o4.x, o4.y, o4.z};
-                WrtShaft sh;
-                if (wrt_shaft_make(o, tri, &sh))
-                    cnt = wrt_shaft_candidates(s.onodes, s.n_nodes, &sh, st.base, st.stride, stack_rows, lists + lane * WRT_LIST_CAP, WRT_LIST_CAP);
-            }
-            s_cnt[warp][lane] = cnt;
-        }
-        __syncwarp();
-        // ---- phase 2: 25 passes of 32 sample rays ----
-        const int passes = (int)((n_claim * WRT_SOFT_SAMPLES + 31u) / 32u);
-#pragma unroll 1
-        for (int pass = 0; pass < passes; pass++) {
-            const unsigned j = (unsigned)pass * 32u + lane;
-            const unsigned rq = j / WRT_SOFT_SAMPLES, sample = j - rq * WRT_SOFT_SAMPLES;
-            const unsigned req = base + rq;
-            bool lit = false;
-            unsigned out = 0;
-            if (rq < n_claim && req < nreq) {
-                float4 o4 = fb.preq_o[par][req];
-                uint4 k = fb.preq_k[par][req];
-                f3 v0, v1, v2;
-                if (k.x < WRT_INLINE_LIGHTS) {
-                    const WrtLight& L = s.lights_c[k.x];
-                    v0 = mk3(L.tri[0], L.tri[1], L.tri[2]); v1 = mk3(L.tri[3], L.tri[4], L.tri[5]); v2 = mk3(L.tri[6], L.tri[7], L.tri[8]);
-                } else {
-                    const WrtLight* L = s.lights + k.x;
-                    v0 = mk3(L->tri[0], L->tri[1], L->tri[2]); v1 = mk3(L->tri[3], L->tri[4], L->tri[5]); v2 = mk3(L->tri[6], L->tri[7], L->tri[8]);
-                }
-                float u, v;
-                wrt_light_sample_uv(seed, k.y, k.z, k.x, sample, &u, &v);
-                f3 lightPos = (1 - u - v) * v0 + u * v1 + v * v2;                 // Triangle.hpp:139-145
-                f3 orig = mk3(o4);
-                f3 raydir = normalized(lightPos - orig);
-                const float dis = norm(lightPos - orig);
-                const Ray r = make_ray(orig, raydir);
-                out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
-                const int cnt = s_cnt[warp][rq];
-                bool occ = false;
-                if (cnt < 0 || degenerate_dir(raydir)) {
-                    occ = occluded(s, degenerate_dir(raydir) ? s.nodes : s.fnodes, r, dis, st);
-                } else {
-                    // own-box test (exact BoundBox::IntersectRay) then the intersection test, per list member
-                    // (fetching the next member's box ahead of the test was tried: +1 %, 8 more registers)
-                    const int* list = lists + rq * WRT_LIST_CAP;
-                    for (int c = 0; c < cnt && !occ; c++) occ = occluder_cache_hit(s, r, dis, list[c]);
-                }
-                lit = !occ;
-            }
-            // one float atomic per request segment of the pass (small integer sums are exact and order-free)
-            const unsigned lit_mask = __ballot_sync(0xffffffffu, lit);
-            const unsigned rq0 = ((unsigned)pass * 32u) / WRT_SOFT_SAMPLES;
-            const unsigned first = __ballot_sync(0xffffffffu, rq == rq0);        // lanes of the pass's first request
-            const unsigned mine = rq == rq0 ? first : ~first;
-            const unsigned n_lit = __popc(lit_mask & mine);
-            if (n_lit && lane == (unsigned)(__ffs(mine) - 1)) atomicAdd(fb.coeff[par] + out, (float)n_lit);
-        }
-        __syncwarp();
-    }
-}
-
-// ---- K4b'': the same in two launches (the default) ----
-// In the fused kernel a warp owns a batch of 32 requests from the shaft walk to the last of its 1600 rays:
-// ~0.4 ms of dependent work per batch, while a deep level only holds ~1.7 batches per warp — ncu: achieved
-// occupancy 49 % of the 62 % the registers allow, the launch ends with a long under-filled tail.  Split:
-//   k_soft_lists      phase 1 only.  The lists go to a pool (bump allocation, one atomic per warp); a request
-//                     keeps {offset, count}, count < 0 = trace ray by ray.
-//   k_soft_list_rays  phase 2 only.  The level's nreq x 50 rays are cut into warp passes of 32 consecutive rays
-//                     and handed out 8 passes at a time from a global counter: balanced to ~10 us.
 struct SoftListBuffers {
-    int*  scratch;        // one block of 32 x WRT_LIST_CAP ints per warp: the walk writes here, then compacts
+    int*  scratch;        // WRT_LIST_CAP ints per thread of the grid: the walk writes here, then compacts into the pool
     int*  pool;           // compacted lists
     int2* ref;            // per request: {pool offset, count}
     unsigned pool_cap;

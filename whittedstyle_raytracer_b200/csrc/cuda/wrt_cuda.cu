@@ -72,11 +72,8 @@ struct WrtContext {
     int refill = 16;                   // idle lanes that trigger a refill on deep ray-tree levels
     int refill_soft = 24;
     bool shaft_cull = true;            // soft shadows: answer requests whose light shaft is empty without tracing (shaft_cull.h)
-    bool soft_lists = true;            // soft shadows: per-request candidate lists (k_shadow_soft_list) instead of per-ray walks
+    bool soft_lists = true;            // soft shadows: per-request candidate lists (k_soft_lists + k_soft_list_rays) instead of per-ray walks
     int lists_from_level = 0;
-    int list_blocks_per_sm = 10;       // <= trace_blocks_per_sm (the list scratch is sized for that grid)
-    int soft_lists_mode = 2;           // 1: fused k_shadow_soft_list; 2: k_soft_lists + k_soft_list_rays
-    int* d_lists[WRT_SIDE_STREAMS] = {};
     wrt::SoftListBuffers list_bufs[WRT_SIDE_STREAMS] = {};
     bool unlit_cull = true;            // drop shadow requests of lights whose shading terms are exactly 0 at the point
     int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
@@ -220,14 +217,13 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
         if (frame_alloc(c, &fb.coeff[k], (size_t)cap * std::max(1, ds.n_lights))) return 1;
     }
     if (frame_alloc(c, &fb.counters, wrt::C_TOTAL)) return 1;
-    // candidate lists of k_shadow_soft_list: one private block per warp, one set per side stream (launches
-    // on different side streams overlap)
+    // candidate lists of the soft-shadow path (kernels.cuh, K4b'), one set per side stream (launches on different
+    // side streams overlap): walk scratch per thread, list pool, per-request {offset, count}.  A full pool only
+    // means per-ray walks for the remaining requests.
     for (int k = 0; k < WRT_SIDE_STREAMS; k++) {
-        if (frame_alloc(c, &c->d_lists[k], (size_t)c->num_sms * c->trace_blocks_per_sm * 4 * 32 * WRT_LIST_CAP)) return 1;
-        // split form: list pool + per-request {offset, count}; a full pool only means per-ray walks for the rest
         wrt::SoftListBuffers& lb = c->list_bufs[k];
-        lb.scratch = c->d_lists[k];
         lb.pool_cap = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(8ull << 20, 2ull * fb.preq_cap), 1ull << 30);
+        if (frame_alloc(c, &lb.scratch, (size_t)c->num_sms * c->trace_blocks_per_sm * 128 * WRT_LIST_CAP)) return 1;
         if (frame_alloc(c, &lb.pool, lb.pool_cap)) return 1;
         if (frame_alloc(c, &lb.ref, ds.n_point_lights ? fb.preq_cap : 1)) return 1;
     }
@@ -337,8 +333,8 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
                 // per-request candidate lists (kernels.cuh, K4b'); scenes with light avatars keep the per-ray kernel,
                 // whose literal hasIntersection path they need, and so does WRT_TRAVERSAL_EXHAUSTIVE
                 const bool lists = c->soft_lists && !ds.has_light_prims && ds.n_nodes > 0 && c->traversal == WRT_TRAVERSAL_PRUNED &&
-                                   d >= c->lists_from_level;
-                if (lists && c->soft_lists_mode == 2 && (unsigned long long)fb.preq_cap * WRT_SOFT_SAMPLES < (1ull << 32)) {
+                                   d >= c->lists_from_level && (unsigned long long)fb.preq_cap * WRT_SOFT_SAMPLES < (1ull << 32);
+                if (lists) {
                     const SoftListBuffers& lb = c->list_bufs[d % WRT_SIDE_STREAMS];
                     {
                         LaunchScope ls(c, ss, F_SOFT_LISTS);
@@ -346,10 +342,6 @@ int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, u
                     }
                     LaunchScope ls(c, ss, F_SHADOW_SOFT);
                     k_soft_list_rays<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, lb);
-                } else if (lists) {
-                    LaunchScope ls(c, ss, F_SHADOW_SOFT);
-                    k_shadow_soft_list<<<grid_for(c, c->list_blocks_per_sm), TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->stack_rows,
-                                                                                          c->d_lists[d % WRT_SIDE_STREAMS]);
                 } else {
                     LaunchScope ls(c, ss, F_SHADOW_SOFT);
                     k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
@@ -553,10 +545,8 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_CACHE_FROM")) c->cache_from_level = atoi(e);
     if (const char* e = getenv("WRT_SHAFT_CULL")) c->shaft_cull = atoi(e) != 0;
     if (const char* e = getenv("WRT_UNLIT_CULL")) c->unlit_cull = atoi(e) != 0;
-    if (const char* e = getenv("WRT_SOFT_LISTS")) { c->soft_lists = atoi(e) != 0; if (atoi(e) > 0) c->soft_lists_mode = atoi(e); }
+    if (const char* e = getenv("WRT_SOFT_LISTS")) c->soft_lists = atoi(e) != 0;
     if (const char* e = getenv("WRT_LISTS_FROM")) c->lists_from_level = atoi(e);
-    if (const char* e = getenv("WRT_LIST_BLOCKS")) c->list_blocks_per_sm = std::max(1, atoi(e));
-    c->list_blocks_per_sm = std::min(c->list_blocks_per_sm, c->trace_blocks_per_sm);
     if (const char* e = getenv("WRT_CHUNK_DIV")) c->chunk_div = std::max(0, std::min(255, atoi(e)));
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));

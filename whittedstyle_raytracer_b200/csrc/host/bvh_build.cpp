@@ -15,6 +15,7 @@
 // 64-byte aligned, primitives renumbered in depth-first leaf order.
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 #include "host_scene.hpp"
 
@@ -25,11 +26,8 @@ namespace {
 struct Builder {
     HostScene& s;
     std::vector<int> order;      // object indices, permuted in place
-    std::vector<int> leaf_objs;  // objects in DFS leaf order
     std::vector<float> cen;      // box centroids, 3 per object (same floats the reference recomputes in its comparator)
     std::vector<float> box;      // pMin, pMax per object, 6 floats: keeps the union loops out of the 200-byte Object records
-    int max_depth = 0;
-
     explicit Builder(HostScene& hs) : s(hs) {}
 
     static float centroid(const Object& o, int axis) {            // BoundBox.hpp:33
@@ -38,17 +36,20 @@ struct Builder {
         return mn[axis] * 0.5f + mx[axis] * 0.5f;
     }
 
-    // Builds the subtree over order[b,e) into record `rec`; returns its box.
-    void build(int rec, int b, int e, int depth) {
-        max_depth = std::max(max_depth, depth);
+    // Builds the subtree over order[b,e) into record `rec`; its descendants take records [free, free + 2(e-b) - 2):
+    // a subtree over k objects has exactly 2k-2 records below its root, so the layout the sequential depth-first
+    // build produces (pair of a node = next free record when the node is visited) is known in advance, the leaf
+    // of order[p] has depth-first rank p, and sibling subtrees can be built by different threads into disjoint
+    // ranges of the preallocated array — same records, same order[] as one thread would produce.
+    // Returns the depth of the deepest leaf.
+    int build(int rec, int b, int e, int free, int depth) {
         int n = e - b;
         if (n == 1) {
             const Object& o = s.objList[order[b]];
             WrtNode& nd = s.nodes[rec];
             set_box(nd, o.bmin, o.bmax);
-            nd.link = ~(int)leaf_objs.size();
-            leaf_objs.push_back(order[b]);
-            return;
+            nd.link = ~b;
+            return depth;
         }
         if (n > 2) {
             const float* b0 = &box[6 * (size_t)order[b]];
@@ -59,13 +60,19 @@ struct Builder {
             const float* cp = cen.data() + axis;
             std::sort(order.begin() + b, order.begin() + e, [cp](int a, int c) { return cp[3 * a] < cp[3 * c]; });
         }
-        int mid = (n == 2) ? b + 1 : b + n / 2;
-        int pair = (int)s.nodes.size();
-        s.nodes.resize(pair + 2);
-        memset(&s.nodes[pair], 0, 2 * sizeof(WrtNode));
+        const int mid = (n == 2) ? b + 1 : b + n / 2;
+        const int pair = free;
         s.nodes[rec].link = pair;
-        build(pair, b, mid, depth + 1);
-        build(pair + 1, mid, e, depth + 1);
+        const int free_l = free + 2, free_r = free + 2 * (mid - b);
+        int dl, dr;
+        if (n >= 8192 && depth < 4) {                              // up to 16 concurrent subtrees
+            std::thread left([&] { dl = build(pair, b, mid, free_l, depth + 1); });
+            dr = build(pair + 1, mid, e, free_r, depth + 1);
+            left.join();
+        } else {
+            dl = build(pair, b, mid, free_l, depth + 1);
+            dr = build(pair + 1, mid, e, free_r, depth + 1);
+        }
         const WrtNode& L = s.nodes[pair];
         const WrtNode& R = s.nodes[pair + 1];
         WrtNode& nd = s.nodes[rec];
@@ -74,6 +81,7 @@ struct Builder {
             nd.pmin[k] = fminf(lo, hi);
             nd.pmax[k] = fmaxf(lo, hi);
         }
+        return std::max(dl, dr);
     }
 
     static void set_box(WrtNode& nd, const V3& mn, const V3& mx) {
@@ -119,13 +127,12 @@ void HostScene::buildAndFlatten() {
             float* bx = &b.box[6 * (size_t)i];
             bx[0] = mn.x; bx[1] = mn.y; bx[2] = mn.z; bx[3] = mx.x; bx[4] = mx.y; bx[5] = mx.z;
         }
-        nodes.reserve(2 * (size_t)n);
-        nodes.resize(2);
-        memset(nodes.data(), 0, 2 * sizeof(WrtNode));
+        nodes.assign(2 * (size_t)n, WrtNode{});                   // root, padding record, 2n-2 descendants
         nodes[1].link = ~0;       // padding record, never referenced
-        b.build(0, 0, n, 0);
+        bvh_depth = b.build(0, 0, n, 2, 0);
+    } else {
+        bvh_depth = 0;
     }
-    bvh_depth = b.max_depth;
 
     prim_geom.assign((size_t)n * 12, 0.f);
     prim_normals.assign((size_t)n * 9, 0.f);
@@ -137,7 +144,7 @@ void HostScene::buildAndFlatten() {
     prim_object.assign(n, -1);
     object_prim.assign(n, -1);
     for (int p = 0; p < n; p++) {
-        int oi = b.leaf_objs[p];
+        int oi = b.order[p];               // the leaf of order[p] has depth-first rank p
         const Object& o = objList[oi];
         prim_object[p] = oi;
         object_prim[oi] = p;

@@ -419,3 +419,75 @@ def test_request_culling_changes_the_work_not_the_result(workdir, monkeypatch):
         d = image_diff(on, ref)
         assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
         assert st_on["shadow_rays"] == ost.shadow_rays
+
+
+MANY_LIGHTS = """imsize 96 64
+eye 0 1 6
+viewdir 0 -0.1 -1
+hfov 60
+updir 0 1 0
+bkgcolor 0.1 0.1 0.2 1.0
+shadow soft
+light 3 6 4 1 0.3 0.3 0.3
+light -4 5 3 1 0.3 0.2 0.2
+light 0 8 -2 1 0.2 0.3 0.2
+light 6 2 6 1 0.2 0.2 0.3
+light -6 3 -4 1 0.3 0.3 0.1
+attlight 1 7 7 1 0.4 0.4 0.4 0.5 0.02 0.001
+mtlcolor 0.8 0.3 0.2 1 1 1 0.2 0.6 0.3 24 1 1.5
+sphere -1.5 0 -1 1.2
+mtlcolor 0.9 0.9 1.0 1 1 1 0.05 0.2 0.4 60 0.2 1.4
+sphere 1.4 0.2 0.5 1.0
+mtlcolor 0.4 0.7 0.4 1 1 1 0.2 0.7 0.1 10 1 1.0
+v -10 -1.2 8
+v 10 -1.2 8
+v 10 -1.2 -12
+v -10 -1.2 -12
+f 1 2 3
+f 1 3 4
+"""
+
+AXIS_ALIGNED = """imsize 33 33
+eye 0 0 3
+viewdir 0 0 -1
+hfov 70
+updir 0 1 0
+bkgcolor 0.1 0.1 0.2 1.0
+shadow soft
+light 0 0 5 1 1 1 1
+mtlcolor 0.7 0.7 0.7 1 1 1 0.2 0.7 0.2 10 1 1.0
+v -6 -6 -2
+v 6 -6 -2
+v 6 6 -2
+v -6 6 -2
+f 1 2 3
+f 1 3 4
+mtlcolor 0.8 0.3 0.2 1 1 1 0.2 0.6 0.3 24 1 1.0
+sphere 0.3 0 0 0.5
+sphere -1.2 0.4 -0.5 0.4
+"""
+
+
+@pytest.mark.parametrize("name,text", [("many_lights", MANY_LIGHTS), ("axis_aligned", AXIS_ALIGNED)])
+def test_soft_shadow_list_path_corner_cases(workdir, monkeypatch, name, text):
+    """Soft shadows through the candidate-list kernels, bit-compared with the oracle (which traces all 50 samples of
+    every request): six area lights (more than the kernel-parameter light bank holds, attenuation included); an odd
+    image looking along -z at a wall from y = 0 with the light's corners at y = 0 too, so the middle rows' shafts have
+    no definite sign on y (the shaft test drops the axis; rays of both signs share a list).  Exactly axis-degenerate
+    samples are covered on the CPU (tests/test_shaft_cull.py) and take the same per-ray walk as the pool-full case
+    forced here: with a 64-entry list pool almost every request overflows to that walk, same image."""
+    scene = Scene(text=text, asset_dir=workdir)
+    ref, ost = ob.OracleScene(scene).render()
+    img, st = gpu_render(scene)
+    d = image_diff(img, ref)
+    assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+    assert st["shadow_rays"] == ost.shadow_rays and st["closest_rays"] == ost.closest_rays
+    assert st["shadow_rays_traced"] < st["shadow_rays"]
+    monkeypatch.setenv("WRT_LIST_POOL_CAP", "64")
+    small, st2 = gpu_render(scene)
+    monkeypatch.delenv("WRT_LIST_POOL_CAP")
+    assert np.array_equal(small, img) and st2["shadow_rays"] == st["shadow_rays"]
+    monkeypatch.setenv("WRT_SOFT_LISTS", "0")
+    plain, _ = gpu_render(scene)
+    monkeypatch.delenv("WRT_SOFT_LISTS")
+    assert np.array_equal(plain, img)

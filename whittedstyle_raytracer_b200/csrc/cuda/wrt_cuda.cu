@@ -74,6 +74,7 @@ struct WrtContext {
     bool shaft_cull = true;            // soft shadows: answer requests whose light shaft is empty without tracing (shaft_cull.h)
     bool soft_lists = true;            // soft shadows: per-request candidate lists (k_soft_lists + k_soft_list_rays) instead of per-ray walks
     int lists_from_level = 0;
+    long long list_pool_cap_override = 0;
     wrt::SoftListBuffers list_bufs[WRT_SIDE_STREAMS] = {};
     bool unlit_cull = true;            // drop shadow requests of lights whose shading terms are exactly 0 at the point
     int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
@@ -223,6 +224,7 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
     for (int k = 0; k < WRT_SIDE_STREAMS; k++) {
         wrt::SoftListBuffers& lb = c->list_bufs[k];
         lb.pool_cap = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(8ull << 20, 2ull * fb.preq_cap), 1ull << 30);
+        if (c->list_pool_cap_override > 0) lb.pool_cap = (unsigned)c->list_pool_cap_override;     // tests: force the pool-full path
         if (frame_alloc(c, &lb.scratch, (size_t)c->num_sms * c->trace_blocks_per_sm * 128 * WRT_LIST_CAP)) return 1;
         if (frame_alloc(c, &lb.pool, lb.pool_cap)) return 1;
         if (frame_alloc(c, &lb.ref, ds.n_point_lights ? fb.preq_cap : 1)) return 1;
@@ -547,6 +549,7 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_UNLIT_CULL")) c->unlit_cull = atoi(e) != 0;
     if (const char* e = getenv("WRT_SOFT_LISTS")) c->soft_lists = atoi(e) != 0;
     if (const char* e = getenv("WRT_LISTS_FROM")) c->lists_from_level = atoi(e);
+    if (const char* e = getenv("WRT_LIST_POOL_CAP")) c->list_pool_cap_override = atoll(e);
     if (const char* e = getenv("WRT_CHUNK_DIV")) c->chunk_div = std::max(0, std::min(255, atoi(e)));
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));

@@ -168,7 +168,8 @@ __device__ __forceinline__ void light_factors(const WrtLight* L, f3 p_eye_dir, f
     f3 h = normalized(p_light_dir + p_eye_dir);
     float hn = dot(h, nDir);
     float mh = (hn < 0.f) ? 0.f : hn;
-    pw = ref_powf(mh, n_exp);
+    // pow(+0, n) = +0 for n > 0 (C99 F.9.4.4): the common back-facing case needs no double-precision pow
+    pw = (mh == 0.f && n_exp > 0.f) ? 0.f : ref_powf(mh, n_exp);
 }
 
 // True when light L adds exactly the same value to the pixel whatever its shadow coefficient is: both

@@ -38,6 +38,7 @@ enum CounterSlot {
     C_NDREQ = 32,                // [9] directional-light shadow requests per level
     C_VALID0 = 48,               // valid (non-padding) primary rays
     C_OVERFLOW = 49,             // set when a queue append was dropped
+    C_NEMPTY = 50,               // [9] queued soft-shadow requests whose candidate list came out empty (= 50 lit samples)
     C_WORK = 192,                // [<= 32 x 2] work-distribution counters (64-bit), one per persistent launch
     C_NCULL = 128,               // [9] soft-shadow requests answered by the shaft test (shaft_cull.h), never queued
     C_NSKIP = 144,               // [9] point-light requests whose light terms vanish (dev_shade.cuh), never queued
@@ -574,6 +575,9 @@ __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s
             for (int i = 0; i < cnt; i++) lb.pool[off + i] = mine[i];
             lb.ref[req] = make_int2((int)off, cnt);
         }
+        // an empty list is an empty shaft: the ray kernel answers "lit" without building the rays (statistics only here)
+        const unsigned n_empty = __popc(__ballot_sync(0xffffffffu, req < nreq && cnt == 0));
+        if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY + level, n_empty);
     }
 }
 
@@ -599,10 +603,15 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
             const unsigned req = j / WRT_SOFT_SAMPLES, sample = j - req * WRT_SOFT_SAMPLES;
             bool lit = false;
             unsigned out = 0;
-            if (req < nreq) {
+            const int2 ref = req < nreq ? lb.ref[req] : make_int2(0, 0);
+            if (req < nreq && ref.y == 0) {
+                // empty list = no leaf box can be hit by any sample of this request (shaft_cull.h, axis-degenerate
+                // samples included): lit, and the ray itself is never needed
+                out = __float_as_uint(fb.preq_o[par][req].w) * (unsigned)s.n_lights + fb.preq_k[par][req].x;
+                lit = true;
+            } else if (req < nreq) {
                 float4 o4 = fb.preq_o[par][req];
                 uint4 k = fb.preq_k[par][req];
-                const int2 ref = lb.ref[req];
                 f3 v0, v1, v2;
                 if (k.x < WRT_INLINE_LIGHTS) {
                     const WrtLight& L = s.lights_c[k.x];

@@ -400,11 +400,11 @@ def test_request_culling_changes_the_work_not_the_result(workdir, monkeypatch):
         fixtures.write_config(workdir, name, fixtures.water_bunny_tex_config(640, 360, soft=soft))
         scene = Scene.from_workdir(workdir, name)
         on, st_on = gpu_render(scene)
-        monkeypatch.setenv("WRT_SHAFT_CULL", "0")           # read by wrt_create
-        monkeypatch.setenv("WRT_UNLIT_CULL", "0")
+        for k in ("WRT_SHAFT_CULL", "WRT_UNLIT_CULL", "WRT_SOFT_LISTS"):     # read by wrt_create; lists off too: an
+            monkeypatch.setenv(k, "0")                                       # empty candidate list also answers "lit"
         off, st_off = gpu_render(scene)
-        monkeypatch.delenv("WRT_SHAFT_CULL")
-        monkeypatch.delenv("WRT_UNLIT_CULL")
+        for k in ("WRT_SHAFT_CULL", "WRT_UNLIT_CULL", "WRT_SOFT_LISTS"):
+            monkeypatch.delenv(k)
         assert np.array_equal(on, off)
         assert st_off["shaft_culled_requests"] == 0 and st_off["unlit_skipped_requests"] == 0
         assert st_off["shadow_rays_traced"] == st_off["shadow_rays"]

@@ -34,8 +34,16 @@ extern "C" {
 
 typedef struct WrtContext WrtContext;
 
-#define WRT_TRAVERSAL_EXHAUSTIVE 0  /* visit every node whose box is hit, like BVH.hpp:137-159 */
-#define WRT_TRAVERSAL_PRUNED     1  /* near-first order, skip boxes entered beyond the best hit (same result) */
+#define WRT_TRAVERSAL_EXHAUSTIVE 0  /* visit every node whose box is hit, like BVH.hpp:137-159; every shadow ray the
+                                     * reference traces is traced */
+#define WRT_TRAVERSAL_PRUNED     1  /* near-first order, skip boxes entered beyond the best hit; shadow requests that
+                                     * provably cannot change the image are answered without tracing and soft-shadow
+                                     * rays test per-request candidate lists.  Same result. */
+
+/* Development switches read from the environment by wrt_create() (all default to "on"; results are identical
+ * either way, the GPU tests compare them): WRT_UNLIT_CULL=0 (queue shadow requests of lights whose Blinn-Phong
+ * factors are exactly 0), WRT_SHAFT_CULL=0 (trace soft-shadow requests whose shaft to the light is empty),
+ * WRT_SOFT_LISTS=0 (per-ray soft-shadow kernel instead of the candidate-list kernels). */
 
 int  wrt_create(int device, WrtContext** out);
 void wrt_destroy(WrtContext* ctx);

@@ -177,21 +177,23 @@ struct FastBvhBuilder {
     // with each record's planes pre-swapped into {entry planes}{exit planes} for that octant.
     std::vector<WrtNode> octant_copies() const { return octant_copies_of(nodes.data(), nodes.size()); }
     static std::vector<WrtNode> octant_copies_of(const WrtNode* nodes, size_t n_nodes) {
-        struct View { const WrtNode* p; size_t n; size_t size() const { return n; } const WrtNode& operator[](size_t i) const { return p[i]; } };
-        View nodes_v{nodes, n_nodes};
-        return octant_copies_impl(nodes_v);
-    }
-    template <class NodesT>
-    static std::vector<WrtNode> octant_copies_impl(const NodesT& nodes) {
-        std::vector<WrtNode> o(8 * nodes.size());
-        for (int oct = 0; oct < 8; oct++)
-            for (size_t i = 0; i < nodes.size(); i++) {
-                WrtNode nd = nodes[i];
-                for (int k = 0; k < 3; k++)
-                    if (oct & (1 << k)) { float t = nd.pmin[k]; nd.pmin[k] = nd.pmax[k]; nd.pmax[k] = t; }
-                o[(size_t)oct * nodes.size() + i] = nd;
-            }
+        std::vector<WrtNode> o;
+        octant_copies_into(nodes, n_nodes, o);
         return o;
+    }
+    // Into a caller-owned vector (wrt_upload_scene keeps it between uploads: no fresh pages to fault in; this runs
+    // inside the end-to-end time of a frame).  Copy, then swap the planes of the axes the octant looks down.
+    static void octant_copies_into(const WrtNode* nodes, size_t n, std::vector<WrtNode>& o) {
+        o.resize(8 * n);
+        if (n == 0) return;
+        for (int oct = 0; oct < 8; oct++) {
+            WrtNode* dst = o.data() + (size_t)oct * n;
+            memcpy(dst, nodes, n * sizeof(WrtNode));
+            for (int k = 0; k < 3; k++) {
+                if (!(oct & (1 << k))) continue;
+                for (size_t i = 0; i < n; i++) { float t = dst[i].pmin[k]; dst[i].pmin[k] = dst[i].pmax[k]; dst[i].pmax[k] = t; }
+            }
+        }
     }
 
     // Copy of the tree whose leaf boxes are grown by rel * (largest extent, largest |coordinate|) + abs

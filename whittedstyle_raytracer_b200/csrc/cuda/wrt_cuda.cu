@@ -77,6 +77,8 @@ struct WrtContext {
     long long list_pool_cap_override = 0;
     int shaft_cull_max_level = 0;      // deepest ray-tree level whose surface kernel runs the shaft test (when lists are on)
     wrt::SoftListBuffers list_bufs[WRT_SIDE_STREAMS] = {};
+    wrt::FastBvhBuilder fbvh;          // host scratch of wrt_upload_scene, kept between uploads
+    std::vector<WrtNode> h_oct;
     bool unlit_cull = true;            // drop shadow requests of lights whose shading terms are exactly 0 at the point
     int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
     int chunk_div = 16;                // work claiming: 0 = one atomic per refill, k = chunks of n/(warps*k) items
@@ -600,16 +602,17 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     static_assert(sizeof(WrtNode) == 32, "WrtNode must be 32 bytes");
     if (dev_upload(c, (const float4*)s->nodes, 2 * (size_t)s->n_nodes, &ds.nodes)) return 1;
     // SAH tree over the same leaf boxes (fast_bvh.hpp explains why results are identical)
-    wrt::FastBvhBuilder fbvh;
-    auto t_sah0 = std::chrono::steady_clock::now();
+    wrt::FastBvhBuilder& fbvh = c->fbvh;               // host-side scratch lives in the context: uploads of same-sized
+    auto t_sah0 = std::chrono::steady_clock::now();    // scenes (every frame of the end-to-end path) reuse its pages
     fbvh.build(s);
     auto t_sah1 = std::chrono::steady_clock::now();
     if (fbvh.nodes.size() != (size_t)s->n_nodes) return fail("wrt_upload_scene: fast BVH build failed");
     if (dev_upload(c, (const float4*)fbvh.nodes.data(), 2 * fbvh.nodes.size(), &ds.fnodes)) return 1;
     {
-        std::vector<WrtNode> oct = fbvh.octant_copies();
+        std::vector<WrtNode>& oct = c->h_oct;
+        wrt::FastBvhBuilder::octant_copies_into(fbvh.nodes.data(), fbvh.nodes.size(), oct);
         if (dev_upload(c, (const float4*)oct.data(), 2 * oct.size(), &ds.onodes)) return 1;
-        oct = wrt::FastBvhBuilder::octant_copies_of(s->nodes, (size_t)s->n_nodes);
+        wrt::FastBvhBuilder::octant_copies_into(s->nodes, (size_t)s->n_nodes, oct);      // (the previous copy was staged)
         if (dev_upload(c, (const float4*)oct.data(), 2 * oct.size(), &ds.ronodes)) return 1;
     }
     // dilated copy for the directional-shadow loop, which the reference runs without any box test

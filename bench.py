@@ -180,7 +180,9 @@ def run_reference_arm(args):
     workdir = Path(tempfile.mkdtemp(prefix="wrt_bench_ref_"))
     scene, glass = prepare_scene(args.workload, workdir)
     total = args.steps + args.warmup
-    per_step = min(10.0, max(1.0, 150.0 / max(1, total)))
+    per_step = min(10.0, max(1.0, 150.0 / max(1, total)))      # the whole arm stays within ~2.5 minutes
+    if args.ref_step_seconds is not None:
+        per_step = args.ref_step_seconds
     vals, last = [], None
     for i in range(total):
         last = cpu_reference_sample(scene, workdir, args.workload, glass, per_step)
@@ -465,6 +467,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-step-seconds", type=float, default=None,
+                    help="--impl reference: CPU seconds per step's pixel sample (default: 150 s / (steps + warmup), 1..10 s)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

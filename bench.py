@@ -38,10 +38,18 @@ WORKLOAD_DESC = {
     "gla_bunny_tex_4k": "gla_bunny_tex.txt @ 3840x2160, hard shadows + Fresnel recursion (BASELINE.json configs[2])",
     "water_bunny_tex_soft_4k": "out/water_bunny_tex.txt + shadow soft @ 3840x2160 (BASELINE.json configs[3])",
     "glass_bunny_soft_8k": "glass-bunny + shadow soft @ 7680x4320 (BASELINE.json configs[4])",
+    "f4_directional_4k": "water_bunny_tex + a directional light @ 3840x2160, hard shadows (SURVEY section 8 f4)",
+    "f4_bump_4k": "water_bunny_tex with a normal-mapped wall @ 3840x2160, hard shadows (SURVEY section 8 f4)",
+    "f4_spheres_1k_4k": "1024 spheres over a floor, 2 lights, no bunny @ 3840x2160, hard shadows (SURVEY section 8 f4)",
 }
+PER_CONFIG = ["config", "bunny_shadow_4k", "gla_bunny_tex_4k", "glass_bunny_soft_8k", "f4_directional_4k", "f4_bump_4k",
+              "f4_spheres_1k_4k"]
 # Reference traversal work per ray: box tests, triangle tests -> FLOPs at 21 / 61 per test
 ALGO_TESTS = {"config": (75.1, 4.11), "bunny_shadow_4k": (77.5, 4.28), "gla_bunny_tex_4k": (69.5, 4.30),
-              "water_bunny_tex_soft_4k": (48.6, 2.86), "glass_bunny_soft_8k": (48.6, 2.86)}
+              "water_bunny_tex_soft_4k": (48.6, 2.86), "glass_bunny_soft_8k": (48.6, 2.86),
+              # f4 workloads: not in SURVEY's table; the bunny scenes reuse gla_bunny_tex's counts, the sphere field is
+              # counted by the oracle (median-split tree over 1026 objects)
+              "f4_directional_4k": (69.5, 4.30), "f4_bump_4k": (69.5, 4.30), "f4_spheres_1k_4k": (40.0, 3.0)}
 # Algorithmic HBM bytes per unit of each traversal kernel: what one launch must move
 # at minimum.  (SURVEY.md section 8d's 112 B/ray is the whole pipeline's queue traffic per closest-hit ray.)
 ALGO_BYTES = {
@@ -129,7 +137,8 @@ def prepare_scene(workload, workdir):
     fixtures.ensure_assets(workdir)
     fixtures.write_config(workdir, workload, fixtures.bench_config_text(workload))
     glass = bool(fixtures.BENCH_CONFIGS[workload].get("glass"))
-    return Scene.from_workdir(workdir, workload, glass=glass), glass
+    bunny = bool(fixtures.BENCH_CONFIGS[workload].get("bunny", True))
+    return Scene.from_workdir(workdir, workload, bunny=bunny, glass=glass), glass
 
 
 # --------------------------------------------------------------------------------------
@@ -150,7 +159,8 @@ def cpu_reference_sample(scene, workdir, workload, glass, target_seconds):
         want_px = max(256.0, target_seconds * ref_rate / rays_per_px)
         stride = max(1, int(round((w * h / want_px) ** 0.5)))
         with quiet_stdout():
-            ref = ob.ReferenceScene(workdir, workload, glass=glass)
+            from whittedstyle_raytracer_b200 import fixtures
+            ref = ob.ReferenceScene(workdir, workload, glass=glass, bunny=bool(fixtures.BENCH_CONFIGS[workload].get("bunny", True)))
             o, d = ob.OracleScene(scene).primary_rays()
             o = o.reshape(h, w, 3)[::stride, ::stride].reshape(-1, 3)
             d = d.reshape(h, w, 3)[::stride, ::stride].reshape(-1, 3)
@@ -207,7 +217,13 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------------------
-def run_cuda_arm(args):
+KERNEL_NAMES = {"shadow_soft": "k_soft_list_rays", "soft_lists": "k_soft_lists", "trace_closest": "k_trace_closest",
+                "shadow_hard": "k_shadow_hard", "surface": "k_surface_spawn", "shadow_directional": "k_shadow_directional",
+                "shade": "k_shade", "combine": "k_combine_resolve"}
+
+
+def measure_workload(workload, steps, warmup, dist_env, cpu_seconds, want_clocks):
+    """Benchmarks one workload on this rank (all ranks call it together).  Returns the JSON-line dict on rank 0."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -215,18 +231,7 @@ def run_cuda_arm(args):
     from whittedstyle_raytracer_b200 import cabi
     from whittedstyle_raytracer_b200.parallel import DistributedRenderer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus} (one rank per GPU)")
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world, rank, local = dist_env
 
     def barrier():
         if world > 1:
@@ -234,7 +239,7 @@ def run_cuda_arm(args):
         torch.cuda.synchronize()
 
     workdir = Path(tempfile.mkdtemp(prefix=f"wrt_bench_{rank}_"))
-    scene, glass = prepare_scene(args.workload, workdir)
+    scene, glass = prepare_scene(workload, workdir)
     tile = tuple(int(x) for x in os.environ.get("WRT_TILE", "8x4").split("x"))
     dr = DistributedRenderer(scene, rank, world, local, tile=tile)
     ctx = dr.renderer.ctx
@@ -244,34 +249,32 @@ def run_cuda_arm(args):
     def l2_flush():
         flush.fill_(rank + 1)
 
-    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to emit
+    sampler = ClockSampler(local) if (rank == 0 and want_clocks) else None      # started early: nvidia-smi needs ~1 s to emit
     # ---- warm-up ----
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         dr.frame()
         stats = dr.finish()
     barrier()
-    rays_local = stats["rays"]
-    rays_t = torch.tensor([rays_local, stats["closest_rays"], stats["shadow_rays"], stats["shaft_culled_requests"],
-                           stats["unlit_skipped_requests"], stats["shadow_rays_traced"]], dtype=torch.int64, device="cuda")
+    keys = ["rays", "closest_rays", "shadow_rays", "shaft_culled_requests", "unlit_skipped_requests", "shadow_rays_traced"]
+    rays_t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device="cuda")
     per_rank_rays = torch.zeros(world, dtype=torch.int64, device="cuda")
-    per_rank_rays[rank] = rays_local
+    per_rank_rays[rank] = stats["closest_rays"] + stats["shadow_rays_traced"]
     if world > 1:
         dist.all_reduce(rays_t)
         dist.all_reduce(per_rank_rays)
     rays_frame, closest_frame, shadow_frame, culled_frame, unlit_frame, shadow_traced_frame = (int(x) for x in rays_t.tolist())
-    # Shadow requests that provably cannot change the image are answered without tracing:
-    # an empty shaft to the area light = 50 lit samples; a light whose shading factors are exactly 0 = coefficient
-    # unused.  `value` counts the frame's rays the way the reference counts them (it traces all of them, SURVEY.md
-    # section 8d: "the reference's own traversal counts are the canonical algorithmic work"); the traced subset
-    # is reported beside it.
+    traced_frame = closest_frame + shadow_traced_frame
+    # Shadow requests that provably cannot change the image are answered without tracing.
+    # `value` counts only the rays the kernels really trace; the reference's own count for the same image (it traces
+    # all of them) is reported beside it as `reference_equivalent`.
 
     # ---- timed: device-resident scene, CUDA events on the launching (current) stream ----
     launches0 = ctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+          for _ in range(steps)]
     barrier()
     t_wall0 = time.time()
-    for k in range(args.steps):
+    for k in range(steps):
         l2_flush()
         if world > 1:
             dist.barrier()
@@ -285,7 +288,7 @@ def run_cuda_arm(args):
     t_wall1 = time.time()
     launches = ctx.launches - launches0
     ms_local = sum(a.elapsed_time(b) for a, b, _ in ev)
-    render_local = sum(a.elapsed_time(c) for a, _, c in ev) / args.steps      # this rank's tiles only, no gather
+    render_local = sum(a.elapsed_time(c) for a, _, c in ev) / steps      # this rank's tiles only, no gather
     rr = torch.zeros(world, dtype=torch.float64, device="cuda")
     rr[rank] = render_local
     if world > 1:
@@ -294,20 +297,20 @@ def run_cuda_arm(args):
     ms_t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_t.item())
-    ms_per_step = ms_total / args.steps
-    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+    ms_per_step = float(ms_t.item()) / steps
+    value = traced_frame / (ms_per_step * 1e-3) / 1e6
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
-    # ---- per-kernel times of one frame (events around every launch; separate, untimed pass) ----
+    # ---- per-kernel times of one frame (events around every launch, launches serialised; separate, untimed pass) ----
     ctx.enable_kernel_timing(True)
-    fam_ms, fam_n = {}, 3
+    fam_ms, fam_launches, fam_n = {}, {}, 3
     for _ in range(fam_n):
         l2_flush()
         dr.frame()
         dr.finish()
         for k2, v in ctx.kernel_times().items():
             fam_ms[k2] = fam_ms.get(k2, 0.0) + v / fam_n
+        fam_launches = ctx.kernel_launches()
     ctx.enable_kernel_timing(False)
     barrier()
 
@@ -336,7 +339,7 @@ def run_cuda_arm(args):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
         if world > 1:
             dist.barrier()
@@ -345,9 +348,8 @@ def run_cuda_arm(args):
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms_per_step = float(e2e_t.item()) / args.steps * 1e3
-    e2e_value = rays_frame / (e2e_ms_per_step * 1e-3) / 1e6
-    launches += 0
+    e2e_ms_per_step = float(e2e_t.item()) / steps * 1e3
+    e2e_value = traced_frame / (e2e_ms_per_step * 1e-3) / 1e6
     checksum = int(host_img.numpy().astype(np.uint64).sum()) if rank == 0 else 0
 
     # ---- roofline of the dominant kernel family ----
@@ -355,81 +357,153 @@ def run_cuda_arm(args):
     dom = max(fam_ms, key=fam_ms.get)
     dom_share = fam_ms[dom] / max(1e-9, sum(fam_ms.values()))
     # units the dominant family processes in one frame on this rank
-    if dom.startswith("shadow"):
+    if dom in ("shadow_soft", "shadow_hard", "shadow_directional"):
         dom_units = stats["shadow_rays_traced"]                  # rays the kernel really traces
-    elif dom == "trace_closest":
+    elif dom == "soft_lists":
+        dom_units = stats["shadow_rays_traced"] // 50            # requests
+    elif dom in ("trace_closest", "surface"):
         dom_units = stats["closest_rays"]
     else:
-        dom_units = stats["rays"]
-    dom_launches = 9 if dom not in ("raygen", "resolve") else 1
+        dom_units = stats["closest_rays"] + stats["shadow_rays_traced"]
+    dom_launches = max(1, int(fam_launches.get(dom, 1)))        # counted by the library during the run
     dom_s = fam_ms[dom] * 1e-3
     fma_tf, muladd_tf = ctx.measure_fp32_peak()
-    fpr = flops_per_ray(args.workload)
+    fpr = flops_per_ray(workload)
     bpu = ALGO_BYTES.get(dom, 112.0)
-    kernel_names = {"shadow_soft": "k_soft_list_rays", "soft_lists": "k_soft_lists", "trace_closest": "k_trace_closest",
-                    "shadow_hard": "k_shadow_hard", "surface": "k_surface_spawn"}
+    kname = KERNEL_NAMES.get(dom, f"k_{dom}")
+    executed = profile_executed(kname)
     roofline = {
-        "kernel": kernel_names.get(dom, f"k_{dom}"), "share_of_step": dom_share, "launches_per_step": dom_launches,
+        "kernel": kname, "share_of_step": dom_share, "launches_per_step": dom_launches,
         "avg_launch_ms": fam_ms[dom] / dom_launches, "units_per_step": dom_units,
         "bound": "hbm", "achieved": dom_units * bpu / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": dom_units * bpu / dom_s / 1e9 / hbm_peak, "peak_source": peak_src,
         "algorithmic_bytes_per_unit": bpu, "algorithmic_bytes_per_launch": dom_units * bpu / dom_launches,
-        "traffic": profile_traffic(kernel_names.get(dom, f"k_{dom}")),
-        "binding_bound": "NOT hbm and not tensor: instruction issue + L1 load latency of a divergent per-lane loop "
-                         "(own-box + triangle tests over the request's candidate list); `bound` says hbm only because the "
-                         "schema offers hbm|tensor — see `fp32` and DESIGN.md section 6",
-        # FP32 work: the reference's own traversal counts per ray x the rays this kernel traces.
-        # (Counting the frame's reference-equivalent rays instead gives `frame_equivalent_tflops`: what the reference's
-        # algorithm would have needed for the same image in the same time.)
-        "fp32": {"algorithmic_flops_per_ray": fpr, "achieved_tflops": dom_units * fpr / dom_s / 1e12,
-                 "frame_equivalent_tflops": rays_frame * fpr / (ms_per_step * 1e-3) / 1e12,
+        "traffic": profile_traffic(kname),
+        "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu "
+                          "capture of this command (cannot be measured outside a profiler)",
+        "binding_bound": "NOT hbm and not tensor: instruction issue + L1 load latency of a divergent per-lane loop; `bound` says "
+                         "hbm only because the schema offers hbm|tensor — `fp32.executed` (ncu counters of the work the kernel "
+                         "really executes) and `lane_issue_frac` are the figures that say how close to the SIMT roof it runs",
+        # FP32, three views: (1) executed — from the committed ncu counters of this kernel (profiles/r02_exec_metrics.json):
+        # FADD+FMUL+2*FFMA thread-instructions / its duration, and lane-issue utilisation = IPC/4 x active lanes/32;
+        # (2) algorithmic — the reference's own traversal counts per ray x the rays this kernel
+        # traces, live time; (3) the measured FP32 peaks of this GPU.
+        "fp32": {"executed": executed,
+                 "algorithmic_flops_per_ray": fpr, "algorithmic_tflops": dom_units * fpr / dom_s / 1e12,
                  "peak_tflops_fma_measured": fma_tf, "peak_tflops_fmul_fadd_measured": muladd_tf,
-                 "frac_of_fma_peak": dom_units * fpr / dom_s / 1e12 / max(fma_tf, 1e-9),
-                 "frac_of_fmul_fadd_peak": dom_units * fpr / dom_s / 1e12 / max(muladd_tf, 1e-9)},
+                 "algorithmic_frac_of_fma_peak": dom_units * fpr / dom_s / 1e12 / max(fma_tf, 1e-9),
+                 "algorithmic_frac_of_fmul_fadd_peak": dom_units * fpr / dom_s / 1e12 / max(muladd_tf, 1e-9)},
     }
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        c = cpu_reference_sample(scene, workdir, args.workload, glass, args.cpu_seconds)
+    if rank == 0 and world == 1 and cpu_seconds > 0:
+        c = cpu_reference_sample(scene, workdir, workload, glass, cpu_seconds)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cpu["seconds"] = c["seconds"]
+        # time to the same image: the reference traces rays_frame rays for this frame
+        cpu["frame_seconds_extrapolated"] = rays_frame / (c["value"] * 1e6)
 
+    line = None
     if rank == 0:
         line = {
-            "metric": METRIC if args.workload == DEFAULT_WORKLOAD else f"Mrays/s (all ray types), {WORKLOAD_DESC[args.workload]}",
-            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC if workload == DEFAULT_WORKLOAD else f"Mrays/s (all ray types), {WORKLOAD_DESC[workload]}",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[args.workload], "width": w, "height": h, "rays_per_frame": rays_frame,
-                       "closest_hit_rays": closest_frame, "shadow_rays": shadow_frame,
+            "value_definition": "rays the kernels traced (closest-hit + shadow) / device time; the same frame costs the reference "
+                                "`reference_equivalent.rays_per_frame` rays (it also traces the shadow rays whose result provably "
+                                "cannot change the image, DESIGN.md section 4b)",
+            "reference_equivalent": {"rays_per_frame": rays_frame, "mrays_per_s": rays_frame / (ms_per_step * 1e-3) / 1e6,
+                                     "e2e_mrays_per_s": rays_frame / (e2e_ms_per_step * 1e-3) / 1e6},
+            "config": {"workload": WORKLOAD_DESC[workload], "width": w, "height": h, "rays_traced_per_frame": traced_frame,
+                       "closest_hit_rays": closest_frame, "shadow_rays_reference": shadow_frame,
                        "shadow_rays_traced": shadow_traced_frame,
                        "request_culling": {"shaft_empty_requests": culled_frame, "unlit_light_requests": unlit_frame,
                                            "note": "shadow requests answered without tracing: whole shaft to the area light "
                                                    "misses every leaf box (=50 lit samples) / light's diffuse+specular factors "
-                                                   "exactly 0 (coefficient unused); bit-identical image; rays_per_frame counts "
-                                                   "them like the reference, which traces them; WRT_SHAFT_CULL=0 "
+                                                   "exactly 0 (coefficient unused); bit-identical image; WRT_SHAFT_CULL=0 "
                                                    "WRT_UNLIT_CULL=0 disable"},
-                       "traced_mrays_per_s": (closest_frame + shadow_traced_frame) / (ms_per_step * 1e-3) / 1e6,
                        "parallelism": f"tiles{tile[0]}x{tile[1]}-interleaved x{world}" + ("+nccl-gather" if world > 1 else ""),
                        "traversal": "pruned", "l2": "flushed between timed steps (256 MiB write)",
                        "scene_bytes": scene.upload_bytes, "image_checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": int(scene.upload_bytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "launches_per_frame": int(launches) // steps,
             "kernel_ms_per_step": fam_ms,
+            "kernel_launches_per_step": fam_launches,
             "per_rank_render_ms": per_rank_render_ms,
-            "per_rank_rays": [int(x) for x in per_rank_rays.tolist()],
+            "per_rank_rays_traced": [int(x) for x in per_rank_rays.tolist()],
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        emit(line)
     barrier()
     dr.close()
+    del flush
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_cuda_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus} (one rank per GPU)")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    env = (world, rank, local)
+    cpu_s = 0.0 if args.no_cpu_baseline else args.cpu_seconds
+    line = measure_workload(args.workload, args.steps, args.warmup, env, cpu_s, True)
+    # The other BASELINE.json configs and the section-8 f4 workloads ride along in the same line (N = 1 only, fewer
+    # steps, a smaller CPU sample each) so that the driver's record carries all of them.
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_per_config:
+        per = {}
+        keep = ("metric", "value", "unit", "ms_per_step", "steps", "reference_equivalent", "e2e", "launches_per_frame",
+                "kernel_ms_per_step", "kernel_launches_per_step", "cpu_baseline")
+        for name in PER_CONFIG:
+            try:
+                r = measure_workload(name, min(args.steps, 5), 3, env, 0.0 if args.no_cpu_baseline else args.per_config_cpu_seconds, False)
+                per[name] = {k: r[k] for k in keep}
+                per[name]["rays_traced_per_frame"] = r["config"]["rays_traced_per_frame"]
+                per[name]["image_checksum"] = r["config"]["image_checksum"]
+                per[name]["dominant_kernel"] = {k: r["roofline"][k] for k in ("kernel", "share_of_step", "avg_launch_ms", "launches_per_step")}
+            except Exception as e:                                  # a failing side workload must not lose the headline
+                per[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["per_config"] = per
+    if rank == 0:
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def profile_executed(kernel):
+    """Executed-work counters of `kernel` from the committed ncu capture (tools/summarize_ncu.py --exec):
+    smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on.sum, smsp__inst_executed.sum,
+    smsp__thread_inst_executed.sum, IPC and duration -> executed TFLOP/s and lane-issue utilisation."""
+    p = REPO / "profiles" / "r02_exec_metrics.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            e = d.get("kernels", {}).get(kernel)
+            if e is not None:
+                e = dict(e)
+                e["source"] = f"profiles/r02_exec_metrics.json ({d.get('command', 'ncu')})"
+            return e
+        except (ValueError, OSError):
+            return None
+    return None
 
 
 def profile_traffic(family):
@@ -467,6 +541,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the other configs' short runs (per_config)")
+    ap.add_argument("--per-config-cpu-seconds", type=float, default=4.0)
     ap.add_argument("--ref-step-seconds", type=float, default=None,
                     help="--impl reference: CPU seconds per step's pixel sample (default: 150 s / (steps + warmup), 1..10 s)")
     args = ap.parse_args()

@@ -43,7 +43,9 @@ typedef struct WrtContext WrtContext;
 /* Development switches read from the environment by wrt_create() (all default to "on"; results are identical
  * either way, the GPU tests compare them): WRT_UNLIT_CULL=0 (queue shadow requests of lights whose Blinn-Phong
  * factors are exactly 0), WRT_SHAFT_CULL=0 (trace soft-shadow requests whose shaft to the light is empty),
- * WRT_SOFT_LISTS=0 (per-ray soft-shadow kernel instead of the candidate-list kernels). */
+ * WRT_SOFT_LISTS=0 (per-ray soft-shadow kernel instead of the candidate-list kernels).
+ * Test hooks: WRT_MAX_BATCH=n (primary slots per batch: forces multi-batch frames), WRT_DEEP_FACTOR=f (initial
+ * automatic deep-level capacity), WRT_LIST_POOL_CAP=n (candidate-list pool entries). */
 
 int  wrt_create(int device, WrtContext** out);
 void wrt_destroy(WrtContext* ctx);
@@ -60,8 +62,10 @@ int wrt_set_tiles(WrtContext* ctx, int tile_w, int tile_h, int rank, int world);
 
 /* traversal: WRT_TRAVERSAL_*; seed: soft-shadow RNG seed (include/wrt_rng.h);
  * queue_factor: capacity of each secondary-ray level as a multiple of the primary
- * level (<= 0 keeps the default 2.0; overflow is detected and re-rendered in
- * smaller batches, never dropped). */
+ * level.  <= 0 keeps the automatic sizing: a quarter of the primary level (a full
+ * level for frames under 1 M pixels), doubled — and kept — whenever a level
+ * overflows.  > 0 fixes it; an overflowing batch is then re-rendered in halves.
+ * Either way overflow is detected and the batch redone, never dropped. */
 int wrt_set_options(WrtContext* ctx, int traversal, uint32_t seed, float queue_factor);
 
 /* Brackets every kernel launch of wrt_render* with CUDA events on the launching
@@ -85,6 +89,9 @@ int wrt_render(WrtContext* ctx, uint8_t* rgb_host, WrtStats* stats);
  * order: wrt_tile_pixel_count(ctx, rank, world) * 3 bytes.  Call wrt_finish_device()
  * before reading statistics. */
 int wrt_render_device(WrtContext* ctx, void* d_rgb_tiles, void* cuda_stream);
+/* Waits for the frame.  A frame that overflowed a ray queue is re-rendered inside this call
+ * (synchronously, into the same d_rgb_tiles); stats->overflow_retries != 0 then tells the caller
+ * to repeat whatever it had already enqueued behind the frame on its stream (e.g. the gather). */
 int wrt_finish_device(WrtContext* ctx, WrtStats* stats);
 int wrt_get_stats(WrtContext* ctx, WrtStats* stats);
 
@@ -112,6 +119,8 @@ int wrt_measure_fp32_peak(WrtContext* ctx, float* tflops_fma, float* tflops_mul_
  * entries written. */
 #define WRT_KERNEL_FAMILIES 10
 int wrt_get_kernel_times(WrtContext* ctx, float* ms, int capacity);
+/* Launches per family behind those times (same order). */
+int wrt_get_kernel_launches(WrtContext* ctx, int32_t* launches, int capacity);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ def _built():
     import __graft_entry__ as g
     g.build_host()
     g.build_cuda()
+    g.build_cuda_debug()
     g.build_cli()
     g.build_oracle()
 

@@ -38,6 +38,8 @@ def oracle():
         lib.orc_primary_rays.argtypes = [C.POINTER(cabi.WrtCamera), vp, vp]
         lib.orc_render.argtypes = [dp, C.POINTER(cabi.WrtCamera), u32, i32, i32, i32, i32, i32, vp, vp,
                                    C.POINTER(cabi.WrtStats)]
+        lib.orc_render_rect.argtypes = [dp, C.POINTER(cabi.WrtCamera), u32, i32, i32, i32, i32, i32, i32, i32, vp, vp,
+                                        C.POINTER(cabi.WrtStats)]
         lib.orc_light_sample_uv.argtypes = [u32, u32, u32, u32, u32, vp]
         _orc = lib
     return _orc
@@ -98,14 +100,16 @@ class OracleScene:
         self.lib.orc_primary_rays(self.scene.camera_ptr, o.ctypes.data, d.ctypes.data)
         return o, d
 
-    def render(self, seed=cabi.WRT_DEFAULT_SEED, rows=None, stride=(1, 1), threads=0, want_float=False):
+    def render(self, seed=cabi.WRT_DEFAULT_SEED, rows=None, stride=(1, 1), threads=0, want_float=False, cols=None):
+        """Whole frame, or the rectangle rows x cols of it (the rest of the returned image stays 0)."""
         cam = self.scene.camera
         y0, y1 = rows if rows else (0, cam.height)
+        x0, x1 = cols if cols else (0, cam.width)
         u8 = np.zeros((cam.height, cam.width, 3), np.uint8)
         fl = np.zeros((cam.height, cam.width, 3), np.float32) if want_float else None
         st = cabi.WrtStats()
-        self.lib.orc_render(self.scene.desc_ptr, self.scene.camera_ptr, seed, y0, y1, stride[0], stride[1], threads,
-                            u8.ctypes.data, None if fl is None else fl.ctypes.data, C.byref(st))
+        self.lib.orc_render_rect(self.scene.desc_ptr, self.scene.camera_ptr, seed, x0, x1, y0, y1, stride[0], stride[1],
+                                 threads, u8.ctypes.data, None if fl is None else fl.ctypes.data, C.byref(st))
         return (u8, fl, st) if want_float else (u8, st)
 
 

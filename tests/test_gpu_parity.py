@@ -389,6 +389,128 @@ def test_4k_soft_shadow_config(workdir):
     r.ctx.close()
 
 
+def test_4k_soft_contiguous_crop_through_the_bunny(workdir):
+    """The same frame: a contiguous 256x256 window through the bunny's body (where the deep ray-tree levels, the
+    candidate lists and the per-ray fall-backs all do their work) equals the oracle's render of that window with the
+    full-size camera and RNG keys."""
+    name = "water_bunny_tex_soft_4k"
+    fixtures.write_config(workdir, name, fixtures.bench_config_text(name))
+    scene = Scene.from_workdir(workdir, name)
+    img, _ = gpu_render(scene)
+    x0, y0, n = 1500, 1700, 256
+    ref, ost = ob.OracleScene(scene).render(rows=(y0, y0 + n), cols=(x0, x0 + n))
+    assert ost.closest_rays > 3 * n * n                      # the window really is on the glass bunny
+    d = image_diff(img[y0:y0 + n, x0:x0 + n], ref[y0:y0 + n, x0:x0 + n])
+    assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+
+
+def test_8k_soft_shadow_config(workdir):
+    """BASELINE.json configs[4]: glass bunny + shadow soft at 7680x4320, one 33 M-slot batch.  Against the oracle's full
+    8K render (tests/golden/full_glass_bunny_soft_8k.npz, tools/gen_full_frame_golden.py: ~10 CPU-minutes, done once):
+    ray counts per depth, every 16th pixel, per-band channel sums of the whole image; a 192x192 window through the bunny
+    against the oracle run here; pruned == exhaustive; an 8-rank tile split reassembles into the 1-rank frame."""
+    name = "glass_bunny_soft_8k"
+    g = np.load(GOLD / f"full_{name}.npz")
+    fixtures.write_config(workdir, name, str(g["config"]))
+    scene = Scene.from_workdir(workdir, name, glass=True)
+    r = Renderer(scene)
+    img = r.render().copy()
+    st = r.last_stats
+    assert st["overflow_retries"] == 0
+    assert (st["closest_rays"], st["shadow_rays"]) == (int(g["closest_rays"]), int(g["shadow_rays"])) == (74904376, 2961802900)
+    assert st["rays_per_depth"] == [int(x) for x in g["rays_per_depth"]]
+    k = int(g["sample_stride"])
+    d = image_diff(img[::k, ::k], g["sample"])
+    assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+    b = int(g["band_rows"])
+    bands = img.reshape(img.shape[0] // b, b, img.shape[1], 3).astype(np.int64).sum(axis=(1, 2))
+    assert np.abs(bands - g["band_sums"]).sum() <= 1e-4 * img.shape[0] * img.shape[1], "whole-frame band sums vs the oracle"
+    x0, y0, n = 3100, 3500, 192
+    ref, _ = ob.OracleScene(scene).render(rows=(y0, y0 + n), cols=(x0, x0 + n))
+    d = image_diff(img[y0:y0 + n, x0:x0 + n], ref[y0:y0 + n, x0:x0 + n])
+    assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+    merged = np.zeros_like(img)
+    rays = 0
+    for kk in range(8):
+        r.ctx.set_tiles(rank=kk, world=8)
+        r.render(out=merged)
+        rays += r.last_stats["rays"]
+    assert np.array_equal(merged, img) and rays == st["rays"]
+    r.ctx.set_tiles(rank=0, world=1)
+    r.ctx.set_options(traversal=TRAVERSAL_EXHAUSTIVE)
+    assert np.array_equal(r.render(), img)
+    r.ctx.close()
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_multi_batch_frames_with_overflow(workdir, monkeypatch, soft):
+    """The batch scheduler (frames larger than one batch; 8K frames used to need it, WRT_MAX_BATCH forces it here): a
+    200x150 bunny frame cut into 4 batches of 8192 slots, with deep levels so small (queue_factor 0.02) that batches
+    overflow and are re-rendered in halves — image, ray counts and per-depth counts equal the single-batch frame's.
+    Then the automatic sizing: deep levels start at WRT_DEEP_FACTOR=0.01 of the batch, overflow, grow, same frame."""
+    name = f"multibatch_{int(soft)}"
+    fixtures.write_config(workdir, name, fixtures.water_bunny_tex_config(200, 150, soft=soft))
+    scene = Scene.from_workdir(workdir, name)
+    one, st_one = gpu_render(scene)
+    assert st_one["overflow_retries"] == 0
+    monkeypatch.setenv("WRT_MAX_BATCH", "8192")
+    r = Renderer(scene)
+    many = r.render().copy()
+    st_many = dict(r.last_stats)
+    r.ctx.set_options(queue_factor=0.02)
+    tight = r.render().copy()
+    st_tight = dict(r.last_stats)
+    r.ctx.close()
+    monkeypatch.setenv("WRT_DEEP_FACTOR", "0.01")
+    monkeypatch.setenv("WRT_MAX_BATCH", "16384")
+    r = Renderer(scene)
+    auto = r.render().copy()
+    st_auto = dict(r.last_stats)
+    again = r.render().copy()                                  # the grown buffers are kept: no retry the second time
+    st_again = dict(r.last_stats)
+    r.ctx.close()
+    monkeypatch.delenv("WRT_MAX_BATCH")
+    monkeypatch.delenv("WRT_DEEP_FACTOR")
+    assert st_many["overflow_retries"] == 0 and st_tight["overflow_retries"] >= 1
+    for img, st in ((many, st_many), (tight, st_tight), (auto, st_auto), (again, st_again)):
+        assert np.array_equal(img, one)
+        for k in ("closest_rays", "shadow_rays", "shadow_requests", "rays_per_depth", "shadow_rays_traced"):
+            assert st[k] == st_one[k], k
+    ref, ost = ob.OracleScene(scene).render()
+    d = image_diff(one, ref)
+    assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+
+
+def test_device_frame_overflow_is_rerendered_in_finish(workdir):
+    """wrt_render_device / wrt_finish_device (the multi-GPU path): a rank whose frame overflows a queue re-renders it
+    inside wrt_finish_device and reports the retry, so that the caller repeats the gather (parallel.py).  Three
+    'ranks' rendered in turn on this GPU with deep levels fixed at 2 % of the batch."""
+    import torch
+    scene, _ = load_golden_scene(workdir, "water_small")
+    full, st_full = gpu_render(scene)
+    h, w = full.shape[:2]
+    world = 3
+    r = Renderer(scene)
+    r.ctx.set_options(queue_factor=0.02)
+    r.ctx.set_tiles(rank=0, world=world)
+    stride = max(r.ctx.tile_pixel_count(k, world) for k in range(world)) * 3
+    gathered = torch.zeros(world * stride, dtype=torch.uint8, device="cuda")
+    rays, retries = 0, 0
+    for k in range(world):
+        r.ctx.set_tiles(rank=k, world=world)
+        r.render_device(gathered[k * stride:(k + 1) * stride].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        st = r.finish_device()
+        rays += st["rays"]
+        retries += st["overflow_retries"]
+    assert retries >= world and rays == st_full["rays"]
+    r.ctx.set_tiles(rank=0, world=world)
+    image = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda")
+    r.scatter_tiles(gathered.data_ptr(), world, stride, image.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(image.cpu().numpy().reshape(h, w, 3), full)
+    r.ctx.close()
+
+
 def test_request_culling_changes_the_work_not_the_result(workdir, monkeypatch):
     """Shadow requests that cannot change the image are answered without tracing: soft-shadow requests
     whose whole shaft to the area light misses every leaf box (50 lit samples, shaft_cull.h) and lights

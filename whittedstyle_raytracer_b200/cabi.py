@@ -90,7 +90,7 @@ CUDA_SYMBOLS = [
     "wrt_create", "wrt_destroy", "wrt_last_error", "wrt_upload_scene", "wrt_set_camera", "wrt_set_tiles",
     "wrt_set_options", "wrt_enable_kernel_timing", "wrt_trace_closest", "wrt_shadow_hard", "wrt_shadow_soft", "wrt_shadow_directional",
     "wrt_render", "wrt_render_device", "wrt_finish_device", "wrt_get_stats", "wrt_tile_pixel_count",
-    "wrt_scatter_tiles", "wrt_kernel_launch_count", "wrt_get_kernel_times", "wrt_measure_fp32_peak",
+    "wrt_scatter_tiles", "wrt_kernel_launch_count", "wrt_get_kernel_times", "wrt_get_kernel_launches", "wrt_measure_fp32_peak",
 ]
 
 _host = None
@@ -165,5 +165,6 @@ def load_cuda() -> C.CDLL:
         lib.wrt_kernel_launch_count.argtypes = [vp]
         lib.wrt_kernel_launch_count.restype = i64
         lib.wrt_get_kernel_times.argtypes = [vp, vp, i32]
+        lib.wrt_get_kernel_launches.argtypes = [vp, vp, i32]
         _cuda = lib
     return _cuda

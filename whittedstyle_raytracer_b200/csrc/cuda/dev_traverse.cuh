@@ -152,12 +152,29 @@ __device__ __forceinline__ bool prim_test(const DevScene& s, int p, const Ray& r
 
 // Per-thread traversal stack in shared memory, column `tid` of a
 // [rows][blockDim.x] array (rows = tree depth + 2): consecutive lanes hit consecutive banks.
+#ifdef WRT_DEBUG_BOUNDS
+__device__ unsigned g_wrt_stack_overflow = 0;       // latched by Stack::push in the bounds-checking build
+#endif
 struct Stack {
     int* base;
     int stride;
     int sp;
+#ifdef WRT_DEBUG_BOUNDS
+    int rows;
+    __device__ __forceinline__ void init(int* smem, int tid, int nthreads) {
+        base = smem + tid; stride = nthreads; sp = 0;
+        unsigned dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        rows = (int)(dyn / (4u * (unsigned)nthreads));
+    }
+    __device__ __forceinline__ void push(int v) {
+        if (sp >= rows) { atomicExch(&g_wrt_stack_overflow, (unsigned)sp + 1u); return; }
+        base[sp * stride] = v; ++sp;
+    }
+#else
     __device__ __forceinline__ void init(int* smem, int tid, int nthreads) { base = smem + tid; stride = nthreads; sp = 0; }
     __device__ __forceinline__ void push(int v) { base[sp * stride] = v; ++sp; }
+#endif
     __device__ __forceinline__ int pop() { --sp; return base[sp * stride]; }
     __device__ __forceinline__ bool empty() const { return sp == 0; }
 };
@@ -414,7 +431,10 @@ __device__ __forceinline__ float directional_product_bvh(const DevScene& s, cons
 // Q provides: bool begin(item, cur, st)  — load + start; false = resolved without a walk
 //             bool step(cur, st)         — one traversal step; false = finished
 //             bool finish(cur, st)       — a walk ended: write results, or start the item's next
-//                                          walk (soft-shadow sample pairs) and return true
+//                                          walk and return true
+//             Q::RETIRES, pending(), retire() — optional second stage: a lane whose walk ended keeps its result
+//                                          (pending() == true) until the warp, converged at its next refill, calls
+//                                          retire() on ALL lanes at once (warp-aggregated appends need the whole warp).
 #ifndef WRT_CHUNK_MIN_PER
 #define WRT_CHUNK_MIN_PER 256
 #endif
@@ -440,36 +460,46 @@ __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned l
     bool active = false, drained = false;
     int cur = 0;
     while (true) {
-        unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (!drained && (idle == 0xffffffffu || __popc(idle) >= refill)) {
-            unsigned cnt = __popc(idle);
-            unsigned long long avail = loc_end - loc_next;
-            unsigned long long first = loc_next, second = 0;   // items [first, first+avail) then [second, ...)
-            if (avail < cnt) {
-                unsigned long long base = 0;
-                const unsigned claim = chunked ? 256u : cnt - (unsigned)avail;
-                if (lane == 0) base = atomicAdd(work, (unsigned long long)claim);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                second = base;
-                loc_next = base + (cnt - avail);
-                loc_end = base + claim;
-                if (base >= n) drained = true;           // nothing left behind this chunk either
-            } else {
-                loc_next += cnt;
-            }
-            if (!active) {
-                unsigned k = __popc(idle & lt_mask);
-                unsigned long long item = k < avail ? first + k : second + (k - avail);
-                if (item < n) {
-                    st.sp = 0;
-                    active = q.begin(item, cur, st);
-                    while (!active && q.finish(cur, st)) active = true;
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        bool service;
+        if (!drained) service = idle == 0xffffffffu || __popc(idle) >= refill;
+        else if (Q::RETIRES) {                          // nothing left to claim: only finished lanes to retire
+            const unsigned pend = __ballot_sync(0xffffffffu, q.pending());
+            service = pend != 0u && (idle == 0xffffffffu || __popc(pend) >= refill);
+        } else service = false;
+        if (service) {
+            if (Q::RETIRES) q.retire();
+            if (!drained) {
+                unsigned cnt = __popc(idle);
+                unsigned long long avail = loc_end - loc_next;
+                unsigned long long first = loc_next, second = 0;   // items [first, first+avail) then [second, ...)
+                if (avail < cnt) {
+                    unsigned long long base = 0;
+                    const unsigned claim = chunked ? 256u : cnt - (unsigned)avail;
+                    if (lane == 0) base = atomicAdd(work, (unsigned long long)claim);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    second = base;
+                    loc_next = base + (cnt - avail);
+                    loc_end = base + claim;
+                    if (base >= n) drained = true;           // nothing left behind this chunk either
+                } else {
+                    loc_next += cnt;
                 }
+                if (!active) {
+                    unsigned k = __popc(idle & lt_mask);
+                    unsigned long long item = k < avail ? first + k : second + (k - avail);
+                    if (item < n) {
+                        st.sp = 0;
+                        active = q.begin(item, cur, st);
+                        while (!active && q.finish(cur, st)) active = true;
+                    }
+                }
+                if (loc_next >= n) drained = true;
             }
-            if (loc_next >= n) drained = true;
             if (!__any_sync(0xffffffffu, active)) {
-                if (drained) break;
-                continue;
+                if (!drained) continue;
+                if (Q::RETIRES && __any_sync(0xffffffffu, q.pending())) q.retire();   // items resolved inside begin()
+                break;
             }
         } else if (idle == 0xffffffffu) {
             break;                                   // drained and nothing in flight

@@ -1,15 +1,20 @@
 // kernels.cuh — the wavefront kernels (sm_100a, SIMT FP32; tensor cores unused:
 // the path is divergent traversal, not a dense contraction).
 //
-// One frame = for each ray-tree level d = 0..8 (Renderer.hpp:25 MAX_DEPTH 9):
-//   k_trace_closest   rays[d]  -> hits              (persistent warps, lane refill, smem stacks)
-//   k_surface_spawn   hits     -> surface records, shadow requests, child rays[d+1], node[d].{fr,kT,children}
-//   k_shadow_*        requests -> coeff[node, light]  (hard product / soft 50-sample count / directional)
-//   k_shade           surface + coeff -> node[d].local
-// (shadow + shade of level d run on a side stream beside closest-hit + surface of level d+1), then
-//   k_combine_resolve bottom-up colour = local + fr*R + (1-fr)(1-alpha)*T in the reference's own
-//                     association (Renderer.hpp:259) and int(255*min(c,1)) (Renderer.hpp:128-130),
-//                     one cooperative launch.
+// One frame (Renderer.hpp:57-137), 15 launches for a soft-shadow frame:
+//   main stream   k_trace_surface<0>        primary rays (generated in registers, Renderer.hpp:104-125) -> closest hit ->
+//                                           surface: hit completion, texture, normal map, Fresnel, child rays of level 1,
+//                                           shadow requests into queue 0
+//                 k_trace_surface<d> x 8    levels 1..8 (Renderer.hpp:25 MAX_DEPTH 9): rays[d] -> closest hit -> surface ->
+//                                           rays[d+1], shadow requests of ALL deep levels into ONE queue (queue 1)
+//                 k_soft_lists(1), k_soft_list_rays(1)   (or k_shadow_hard(1) / k_shadow_directional(1))
+//   side stream   k_soft_lists(0), k_soft_list_rays(0), k_shade(level 0)   beside the deep chain
+//   main stream   k_combine_resolve         shades the deep nodes, then colour = local + fr*R + (1-fr)(1-alpha)*T bottom-up in
+//                                           the reference's own association (Renderer.hpp:259) and int(255*min(c,1))
+//                                           (Renderer.hpp:128-130); one cooperative launch.
+// The only dependent chain is the 9 closest-hit launches; the shadow work of the deep levels — independent of the
+// chain — is not cut into 8 per-level launches with 8 tails, and level 0's shadow work fills the SMs the short deep
+// levels leave idle.
 //
 // Every queue length lives in device memory (Counters); kernels read it there, so
 // the host enqueues the whole frame without synchronising.
@@ -21,29 +26,48 @@
 #include "../../../include/wrt_rng.h"
 #include "../../../include/wrt_tiles.h"
 
-// Traversal kernels: 128-thread CTAs; ptxas settles at 54-56 registers (9 CTAs per SM).  Forcing more
+// Traversal kernels: 128-thread CTAs; ptxas settles at 48-61 registers (8-9 CTAs per SM).  Forcing more
 // CTAs per SM through a minimum-blocks bound spills and is slower (profiles/NOTES.md).
 #ifdef WRT_MIN_BLOCKS
 #define WRT_TRACE_BOUNDS __launch_bounds__(128, WRT_MIN_BLOCKS)
 #else
 #define WRT_TRACE_BOUNDS __launch_bounds__(128)
 #endif
+// The fused closest-hit + surface kernel: the surface code alone wants ~80 registers; the traversal loop, where the
+// time goes, wants ~60.  The bound keeps 8 CTAs per SM; what spills is surface-side state.
+#ifndef WRT_FUSED_MIN_BLOCKS
+#define WRT_FUSED_MIN_BLOCKS 8
+#endif
+#define WRT_FUSED_BOUNDS __launch_bounds__(128, WRT_FUSED_MIN_BLOCKS)
 
 namespace wrt {
 
+// ---- debug build (-DWRT_DEBUG_BOUNDS): every queue / pool / stack / node index is checked before the access; the first
+// failing source line is latched into a device variable the host reads after the frame (wrt_cuda.cu: finish_frame).
+#ifdef WRT_DEBUG_BOUNDS
+__device__ unsigned g_wrt_bounds_line = 0;
+__device__ __forceinline__ bool wrt_bounds_ok(bool ok, unsigned line) {
+    if (!ok) atomicCAS(&g_wrt_bounds_line, 0u, line);
+    return ok;
+}
+#define WRT_IN_BOUNDS(idx, cap) wrt_bounds_ok((unsigned long long)(idx) < (unsigned long long)(cap), (unsigned)__LINE__)
+#else
+#define WRT_IN_BOUNDS(idx, cap) true
+#endif
+
 enum CounterSlot {
-    C_NRAYS = 0,                 // [WRT_MAX_DEPTH + 1] level 0: primary rays; level d >= 1: reflection rays
-    C_NTRAYS = 112,              // [WRT_MAX_DEPTH + 1] level d >= 1: transmission rays (second half of the level's arrays)
-    C_NPREQ = 16,                // [9] point-light shadow requests per level
-    C_NDREQ = 32,                // [9] directional-light shadow requests per level
+    C_NRAYS = 0,                 // [WRT_MAX_DEPTH + 1] level d >= 1: reflection rays (first half of the level's arrays)
+    C_NTRAYS = 112,              // [WRT_MAX_DEPTH + 1] level d >= 1: transmission rays (second half)
+    C_NPREQ = 16,                // [2] point-light shadow requests: queue 0 = level 0, queue 1 = levels 1..8
+    C_NDREQ = 32,                // [2] directional-light shadow requests, same two queues
     C_VALID0 = 48,               // valid (non-padding) primary rays
     C_OVERFLOW = 49,             // set when a queue append was dropped
-    C_NEMPTY = 50,               // [9] queued soft-shadow requests whose candidate list came out empty (= 50 lit samples)
-    C_WORK = 192,                // [<= 32 x 2] work-distribution counters (64-bit), one per persistent launch
+    C_NEMPTY = 50,               // queued soft-shadow requests whose candidate list came out empty (= 50 lit samples)
     C_NCULL = 128,               // [9] soft-shadow requests answered by the shaft test (shaft_cull.h), never queued
     C_NSKIP = 144,               // [9] point-light requests whose light terms vanish (dev_shade.cuh), never queued
     C_NDSKIP = 160,              // [9] the same for directional lights
-    C_POOL = 176,                // [9] fill level of the candidate-list pool (k_soft_lists)
+    C_POOL = 176,                // [2] fill level of the candidate-list pools (k_soft_lists)
+    C_WORK = 192,                // [<= 32 x 2] work-distribution counters (64-bit), one per persistent launch
     C_TOTAL = 256
 };
 
@@ -53,32 +77,39 @@ struct TileMap : WrtTileMap {     // include/wrt_tiles.h
     }
 };
 
-#ifndef WRT_SIDE_STREAMS
-#define WRT_SIDE_STREAMS 2
-#endif
-#define WRT_SETS (WRT_SIDE_STREAMS + 1)
-
-struct FrameBuffers {
-    float4* ray_o[2];            // {o.xyz, pixel id}
-    float4* ray_d[2];            // {d.xyz, path id}
-    float4* hit;                 // {t, prim, b1, b2}
-    float4* surf[WRT_SETS];      // by level % WRT_SETS, 4 per node: {pos, prim} {nDir, material} {Od, -} {ray origin, -}
-    float4* node_a[WRT_MAX_DEPTH];   // {local.rgb -> colour.rgb, fr}
-    float4* node_b[WRT_MAX_DEPTH];   // {kT, childR, childT, composite flag}
-    // Shadow requests, coefficients and surface records exist in WRT_SETS copies indexed by level % WRT_SETS:
-    // shadow + shade of level d run on side stream d % WRT_SIDE_STREAMS, beside closest-hit + surface of level d+1 (main
-    // stream) and beside the straggling long rays of level d-1's shadow kernel (the other side stream).
-    float4* preq_o[WRT_SETS];    // point-light request: {shadow ray origin, node}
-    uint4*  preq_k[WRT_SETS];    //                      {light, pixel, path, -}
-    float4* dreq_o[WRT_SETS];    // directional request: {pos, node}
-    uint4*  dreq_k[WRT_SETS];    //                      {light, self prim, -, -}
-    float*  coeff[WRT_SETS];     // [node * n_lights + light]
-    unsigned* counters;
-    unsigned cap;                // capacity of every per-level array
-    unsigned preq_cap, dreq_cap;
+// Everything a kernel needs to (re)generate the primary ray of a slot: level-0 rays never exist in memory.
+struct PrimaryGen {
+    WrtCamera cam;
+    TileMap tm;
+    long long slot0;             // first slot of the batch
 };
 
-// ---- warp-aggregated queue append: k in {0,1,2} slots per lane, one atomic per warp ----
+// Per-frame buffers.  A ray-tree node is addressed by ONE global id: level 0 -> its slot in the batch,
+// level d >= 1 -> cap0 + (d-1)*capd + slot.  Deep levels are sized capd (default a quarter of the batch: in the bunny
+// frames <= 16 % of the pixels spawn children); an overflow is detected, the buffers grow and the batch is re-rendered.
+struct FrameBuffers {
+    float4* ray_o[2];            // deep levels, by level & 1: {o.xyz, pixel id}
+    float4* ray_d[2];            //                            {d.xyz, path id}
+    float4* hit;                 // unfused path only: {t, prim, b1, b2} by slot
+    float4* surf;                // 4 per node: {pos, prim} {nDir, material} {Od, -} {ray origin, -}
+    float4* node_a;              // per node {local.rgb -> colour.rgb, fr}
+    float4* node_b;              // per node {kT, childR, childT, composite flag}  (children as node ids)
+    float4* preq_o[2];           // point-light request: {shadow ray origin, node}
+    uint4*  preq_k[2];           //                      {light, pixel, path, -}
+    float4* dreq_o[2];           // directional request: {pos, node}
+    uint4*  dreq_k[2];           //                      {light, self prim, -, -}
+    float*  coeff;               // [node * n_lights + light]
+    unsigned* counters;
+    unsigned cap0, capd;         // slots of level 0 (batch capacity) and of every deeper level
+    unsigned preq_cap[2], dreq_cap[2];
+    unsigned n_node_cap;         // cap0 + (WRT_MAX_DEPTH-1) * capd
+};
+
+__device__ __forceinline__ unsigned node_id(const FrameBuffers& fb, int level, unsigned slot) {
+    return level == 0 ? slot : fb.cap0 + (unsigned)(level - 1) * fb.capd + slot;
+}
+
+// ---- warp-aggregated queue append: k in {0,1,2,...} slots per lane, one atomic per warp ----
 __device__ __forceinline__ unsigned warp_alloc(unsigned* counter, int k, unsigned cap, unsigned* overflow) {
     unsigned lane = threadIdx.x & 31;
     int incl = k;
@@ -92,7 +123,7 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned* counter, int k, unsigne
     if (lane == 31 && total > 0) base = atomicAdd(counter, (unsigned)total);
     base = __shfl_sync(0xffffffffu, base, 31);
     unsigned mine = base + (unsigned)(incl - k);
-    if (k > 0 && mine + (unsigned)k > cap) { *overflow = 1u; return 0xffffffffu; }
+    if (k > 0 && (mine > cap || (unsigned)k > cap - mine)) { *overflow = 1u; return 0xffffffffu; }
     return mine;
 }
 
@@ -105,15 +136,16 @@ struct LevelSpan {
     __device__ __forceinline__ unsigned count() const { return nR + nT; }
     __device__ __forceinline__ unsigned slot(unsigned item) const { return item < nR ? item : half + (item - nR); }
 };
-__device__ __forceinline__ LevelSpan level_span(const unsigned* counters, int level, unsigned cap) {
+__device__ __forceinline__ LevelSpan level_span(const FrameBuffers& fb, int level, unsigned n0) {
     LevelSpan sp;
     if (level == 0) {
-        sp.half = cap; sp.nT = 0;
-        sp.nR = counters[C_NRAYS] < cap ? counters[C_NRAYS] : cap;
+        sp.half = fb.cap0; sp.nT = 0;
+        sp.nR = n0 < fb.cap0 ? n0 : fb.cap0;
     } else {
-        sp.half = cap / 2;
+        const unsigned* counters = fb.counters;
+        sp.half = fb.capd / 2;
         sp.nR = counters[C_NRAYS + level] < sp.half ? counters[C_NRAYS + level] : sp.half;
-        sp.nT = counters[C_NTRAYS + level] < cap - sp.half ? counters[C_NTRAYS + level] : cap - sp.half;
+        sp.nT = counters[C_NTRAYS + level] < fb.capd - sp.half ? counters[C_NTRAYS + level] : fb.capd - sp.half;
     }
     return sp;
 }
@@ -123,61 +155,219 @@ __device__ __forceinline__ unsigned queue_len(const unsigned* counters, int slot
     return n < cap ? n : cap;
 }
 
-// ---- K1: primary rays, Renderer.hpp:104-125 ----
-__global__ void k_raygen(WrtCamera cam, TileMap tm, long long slot0, unsigned n, FrameBuffers fb) {
-    unsigned valid = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int x, y;
-        float4 ro, rd;
-        if (tm.slot_to_pixel(slot0 + i, tm.rank, x, y)) {
-            f3 ul = mk3(cam.ul[0], cam.ul[1], cam.ul[2]);
-            f3 v_off = (float)y * mk3(cam.delta_v[0], cam.delta_v[1], cam.delta_v[2]);
-            f3 h_off = (float)x * mk3(cam.delta_h[0], cam.delta_h[1], cam.delta_h[2]);
-            f3 pixelPos = ul + h_off + v_off + mk3(cam.c_off_h[0], cam.c_off_h[1], cam.c_off_h[2]) +
-                          mk3(cam.c_off_v[0], cam.c_off_v[1], cam.c_off_v[2]);
-            f3 eye = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
-            f3 nrm = mk3(cam.n[0], cam.n[1], cam.n[2]);
-            f3 dir, org;
-            if (!cam.parallel) { dir = normalized(pixelPos - eye); org = eye; }
-            else { dir = nrm; org = pixelPos - cam.d * nrm; }
-            ro = make_float4(org.x, org.y, org.z, __uint_as_float((unsigned)(y * cam.width + x)));
-            rd = make_float4(dir.x, dir.y, dir.z, __uint_as_float(1u));
-            ++valid;
-        } else {
-            ro = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));   // dead slot
-            rd = make_float4(0.f, 0.f, 1.f, __uint_as_float(0u));
-        }
-        fb.ray_o[0][i] = ro;
-        fb.ray_d[0][i] = rd;
+// ---- primary ray of a slot, Renderer.hpp:104-125.  false = padding slot of a clipped border tile ----
+__device__ __forceinline__ bool primary_ray(const PrimaryGen& pg, unsigned item, f3& org, f3& dir, unsigned& pixel) {
+    const WrtCamera& cam = pg.cam;
+    int x, y;
+    if (!pg.tm.slot_to_pixel(pg.slot0 + item, pg.tm.rank, x, y)) {
+        org = mk3(0.f, 0.f, 0.f); dir = mk3(0.f, 0.f, 1.f); pixel = 0xffffffffu;
+        return false;
     }
-    valid = __reduce_add_sync(0xffffffffu, valid);
-    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(fb.counters + C_VALID0, valid);
-    if (blockIdx.x == 0 && threadIdx.x == 0) fb.counters[C_NRAYS + 0] = n;
+    f3 ul = mk3(cam.ul[0], cam.ul[1], cam.ul[2]);
+    f3 v_off = (float)y * mk3(cam.delta_v[0], cam.delta_v[1], cam.delta_v[2]);
+    f3 h_off = (float)x * mk3(cam.delta_h[0], cam.delta_h[1], cam.delta_h[2]);
+    f3 pixelPos = ul + h_off + v_off + mk3(cam.c_off_h[0], cam.c_off_h[1], cam.c_off_h[2]) +
+                  mk3(cam.c_off_v[0], cam.c_off_v[1], cam.c_off_v[2]);
+    f3 eye = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
+    f3 nrm = mk3(cam.n[0], cam.n[1], cam.n[2]);
+    if (!cam.parallel) { dir = normalized(pixelPos - eye); org = eye; }
+    else { dir = nrm; org = pixelPos - cam.d * nrm; }
+    pixel = (unsigned)(y * cam.width + x);
+    return true;
+}
+
+// ---- hit -> surface, shadow requests, child rays (Renderer.hpp:170-257); called by a whole, converged warp ----
+// `cull`: shadow requests that provably cannot change the image are answered here and never queued.
+//   WRT_CULL_UNLIT  the light's diffuse AND specular factors at this point are exactly 0 (dev_shade.cuh,
+//                   light_terms_vanish): whatever the coefficient, the light adds +-0;
+//   WRT_CULL_SHAFT  (soft shadows) the whole shaft origin -> area light misses every leaf box: all 50
+//                   samples are lit, coefficient = 50 (shaft_cull.h).
+// The reference traces these rays; WrtStats keeps counting them and reports how many were answered this way.
+// `live`: this lane carries a finished closest-hit query (prim: -1 miss, -2 padding slot, >= 0 hit).
+#define WRT_CULL_UNLIT 1
+#define WRT_CULL_SHAFT 2
+__device__ __forceinline__ void surface_warp(const DevScene& s, const FrameBuffers& fb, int level, int cull, bool live,
+                                             f3 org, f3 dir, unsigned pixel, unsigned path, float hit_t, int prim,
+                                             float b1, float b2, unsigned slot) {
+    const unsigned child_half = fb.capd / 2;
+    const int q = level == 0 ? 0 : 1;
+    float4* nray_o = fb.ray_o[(level + 1) & 1];
+    float4* nray_d = fb.ray_d[(level + 1) & 1];
+    unsigned* overflow = fb.counters + C_OVERFLOW;
+    const unsigned g = node_id(fb, level, slot);
+    bool shade = false;
+    bool spawnT = false, spawnR = false;
+    float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nb = make_float4(0.f, __int_as_float(-1), __int_as_float(-1), 0.f);
+    f3 pos = mk3(0.f, 0.f, 0.f), nDir = pos, N = pos;
+    f3 refractDir = pos, reflectDir = pos, refRayOrig = pos, traRayOrig = pos;
+    float shade_n = 0.f;                                   // Phong exponent of the shaded material
+    unsigned lit_mask = 0, skip_mask = 0;                  // lights (< 32) answered without a request
+    if (live) {
+        if (prim == -1) {
+            na = make_float4(s.bkg[0], s.bkg[1], s.bkg[2], 0.f);            // miss: bkgcolor, :170
+        } else if (prim >= 0) {
+            Surface sf = complete_hit(s, org, dir, hit_t, prim, b1, b2);
+            Mtl m = load_material(s, sf.material);
+            if (sf.flags & WRT_PRIM_LIGHT) {
+                na = make_float4(m.diffuse.x, m.diffuse.y, m.diffuse.z, 0.f); // light avatar, :172
+            } else {
+                shade = true;
+                shade_n = m.n;
+                f3 Od = m.diffuse;
+                if (!float_equal(-1.f, (float)sf.textureIndex) && !float_equal(-1.f, sf.u) && !float_equal(-1.f, sf.v))
+                    Od = texture_at(s, s.textures + sf.textureIndex, sf.u, sf.v);      // :176-180
+                if (sf.normalMapIndex != -1) sf.nDir = change_normal_dir(s, sf);        // :182-184
+                pos = sf.pos; nDir = sf.nDir;
+                if (WRT_IN_BOUNDS(g, fb.n_node_cap)) {
+                    float4* sv = fb.surf + 4 * (size_t)g;
+                    sv[0] = make_float4(pos.x, pos.y, pos.z, __int_as_float(prim));
+                    sv[1] = make_float4(nDir.x, nDir.y, nDir.z, __int_as_float(sf.material));
+                    sv[2] = make_float4(Od.x, Od.y, Od.z, 0.f);
+                    sv[3] = make_float4(org.x, org.y, org.z, 0.f);          // p_eye_dir needs the ray origin, :267
+                }
+                // ---- reflection / transmission, :194-257 ----
+                refRayOrig = pos; traRayOrig = pos;
+                N = normalized(nDir);
+                float fr, eta_i, eta_t;
+                float cosN_Dir = dot(N, -dir);
+                if (cosN_Dir > 0) { eta_i = s.eta; eta_t = m.eta; }
+                else { eta_i = m.eta; eta_t = s.eta; }
+                fr = fresnel(dir, N, eta_i, eta_t);
+                refractDir = normalized(refraction_dir(dir, N, eta_i, eta_t));
+                reflectDir = normalized(reflection_dir(dir, nDir));
+                float cos_refle_N = dot(reflectDir, N);
+                float cos_refra_N = dot(refractDir, N);
+                const float EPSILON = 0.00005f;
+                if (cos_refle_N < 0) refRayOrig = refRayOrig - EPSILON * N;
+                else refRayOrig = refRayOrig + EPSILON * N;
+                if (cos_refra_N < 0) traRayOrig = traRayOrig - EPSILON * N;
+                else traRayOrig = traRayOrig + EPSILON * N;
+                if (float_equal(0.f, norm(refractDir))) fr = 1.f;
+                spawnT = !float_equal(1.f, m.alpha) && !float_equal(fr, 1.f);
+                spawnR = m.ks != 0;
+                if (level + 1 >= WRT_MAX_DEPTH) { spawnT = false; spawnR = false; }    // traceRay depth cut, :152
+                na.w = fr;
+                nb.x = (1 - fr) * (1 - m.alpha);
+                nb.w = 1.f;                                                    // composite node
+            }
+        }
+    }
+    if (live && !shade && WRT_IN_BOUNDS(g, fb.n_node_cap)) fb.surf[4 * (size_t)g] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    // child rays: reflections into the first half of the next level, transmissions into the second
+    unsigned rslot = warp_alloc(fb.counters + C_NRAYS + level + 1, spawnR ? 1 : 0, child_half, overflow);
+    unsigned tslot = warp_alloc(fb.counters + C_NTRAYS + level + 1, spawnT ? 1 : 0, fb.capd - child_half, overflow);
+    if (spawnR && rslot != 0xffffffffu && WRT_IN_BOUNDS(rslot, fb.capd)) {
+        nray_o[rslot] = make_float4(refRayOrig.x, refRayOrig.y, refRayOrig.z, __uint_as_float(pixel));
+        nray_d[rslot] = make_float4(reflectDir.x, reflectDir.y, reflectDir.z, __uint_as_float(path * 2u));
+        nb.y = __int_as_float((int)node_id(fb, level + 1, rslot));
+    }
+    if (spawnT && tslot != 0xffffffffu && WRT_IN_BOUNDS(child_half + tslot, fb.capd)) {
+        unsigned c = child_half + tslot;
+        nray_o[c] = make_float4(traRayOrig.x, traRayOrig.y, traRayOrig.z, __uint_as_float(pixel));
+        nray_d[c] = make_float4(refractDir.x, refractDir.y, refractDir.z, __uint_as_float(path * 2u + 1u));
+        nb.z = __int_as_float((int)node_id(fb, level + 1, c));
+    }
+    // shadow requests: one per (shaded hit, light) — minus the ones that cannot change the image
+    const f3 sorig = pos + 0.0005f * nDir;                             // BVHStrategy.hpp:15, Renderer.hpp:349
+    int n_preq = shade ? s.n_point_lights : 0, n_dreq = shade ? s.n_dir_lights : 0;
+    if (shade && cull) {
+        const float so[3] = {sorig.x, sorig.y, sorig.z};
+        const f3 p_eye_dir = normalized(org - pos);                    // as blinn_phong() will compute it
+        for (int li = 0; li < s.n_lights && li < 32; li++) {
+            const WrtLight* L = s.lights + li;
+            const bool point = float_equal(L->pos[3], 1.f);
+            if ((cull & WRT_CULL_UNLIT) && light_terms_vanish(L, p_eye_dir, pos, nDir, shade_n)) {
+                skip_mask |= 1u << li;                                 // coefficient is multiplied by 0 twice
+                if (point) --n_preq; else --n_dreq;
+            } else if ((cull & WRT_CULL_SHAFT) && point) {
+                float tri[9];
+                for (int k = 0; k < 9; k++) tri[k] = L->tri[k];
+                if (wrt_shaft_is_empty(s.onodes, s.n_nodes, so, tri)) { lit_mask |= 1u << li; --n_preq; }
+            }
+        }
+    }
+    unsigned pslot = warp_alloc(fb.counters + C_NPREQ + q, n_preq, fb.preq_cap[q], overflow);
+    unsigned dslot = 0xffffffffu;
+    if (s.n_dir_lights > 0) dslot = warp_alloc(fb.counters + C_NDREQ + q, n_dreq, fb.dreq_cap[q], overflow);
+    if (cull) {                                                        // statistics: the reference traces these rays
+        unsigned n_lit = __reduce_add_sync(0xffffffffu, (unsigned)__popc(lit_mask));
+        unsigned n_skip_p = __reduce_add_sync(0xffffffffu, (unsigned)((shade ? s.n_point_lights : 0) - n_preq - __popc(lit_mask)));
+        unsigned n_skip_d = __reduce_add_sync(0xffffffffu, (unsigned)((shade ? s.n_dir_lights : 0) - n_dreq));
+        if ((threadIdx.x & 31) == 0) {
+            if (n_lit) atomicAdd(fb.counters + C_NCULL + level, n_lit);
+            if (n_skip_p) atomicAdd(fb.counters + C_NSKIP + level, n_skip_p);
+            if (n_skip_d) atomicAdd(fb.counters + C_NDSKIP + level, n_skip_d);
+        }
+    }
+    if (shade) {
+        for (int li = 0; li < s.n_lights; li++) {
+            const bool lit = li < 32 && ((lit_mask >> li) & 1u), skip = li < 32 && ((skip_mask >> li) & 1u);
+            if (WRT_IN_BOUNDS(g, fb.n_node_cap)) fb.coeff[(size_t)g * s.n_lights + li] = lit ? (float)WRT_SOFT_SAMPLES : 0.f;
+            if (lit || skip) continue;
+            bool point = float_equal(s.lights[li].pos[3], 1.f);
+            if (point && pslot != 0xffffffffu) {
+                if (WRT_IN_BOUNDS(pslot, fb.preq_cap[q])) {
+                    fb.preq_o[q][pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(g));
+                    fb.preq_k[q][pslot] = make_uint4((unsigned)li, pixel, path, 0u);
+                }
+                ++pslot;
+            } else if (!point && dslot != 0xffffffffu) {
+                if (WRT_IN_BOUNDS(dslot, fb.dreq_cap[q])) {
+                    fb.dreq_o[q][dslot] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(g));
+                    fb.dreq_k[q][dslot] = make_uint4((unsigned)li, (unsigned)prim, 0u, 0u);
+                }
+                ++dslot;
+            }
+        }
+    }
+    if (live && WRT_IN_BOUNDS(g, fb.n_node_cap)) {
+        fb.node_a[g] = na;
+        fb.node_b[g] = nb;
+    }
 }
 
 // ---- K2: closest hit; persistent warps, per-lane refill (dev_traverse.cuh run_queue) ----
+// FUSED: the lane keeps its finished hit in registers and the warp runs surface_warp() for all finished lanes together at
+// the next refill (run_queue's retire hook) — no hit record, no second pass over the rays, one launch per level.
+template <bool LEVEL0, bool FUSED>
 struct ClosestQuery {
+    static constexpr bool RETIRES = FUSED;
     const DevScene& s;
     const FrameBuffers& fb;
+    const PrimaryGen& pg;
     const float4* ray_o;
     const float4* ray_d;
     float prune_cfg;
+    int level, cull;
     // per-lane state
     Ray r;
     ClosestState cs;
     const float4* nodes;
-    unsigned idx;
+    unsigned idx, pixel, path;
+    bool has_result;
+    unsigned valid;                      // level 0: non-padding primary rays this lane retired
     LevelSpan span;
-    __device__ __forceinline__ ClosestQuery(const DevScene& s_, const FrameBuffers& fb_, int level, float prune)
-        : s(s_), fb(fb_), ray_o(fb_.ray_o[level & 1]), ray_d(fb_.ray_d[level & 1]), prune_cfg(prune),
-          span(level_span(fb_.counters, level, fb_.cap)) {}
+    __device__ __forceinline__ ClosestQuery(const DevScene& s_, const FrameBuffers& fb_, const PrimaryGen& pg_, int level_,
+                                            unsigned n0, float prune, int cull_)
+        : s(s_), fb(fb_), pg(pg_), ray_o(fb_.ray_o[level_ & 1]), ray_d(fb_.ray_d[level_ & 1]), prune_cfg(prune), level(level_),
+          cull(cull_), has_result(false), valid(0), span(level_span(fb_, level_, n0)) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
         idx = span.slot((unsigned)item);
-        float4 o = ray_o[idx], d = ray_d[idx];
+        f3 o, d;
         cs.reset(prune_cfg);
-        if (__float_as_uint(o.w) == 0xffffffffu) { cs.best.prim = -2; return false; }       // dead slot
+        if (LEVEL0) {
+            path = 1u;
+            const bool ok = primary_ray(pg, (unsigned)item, o, d, pixel);
+            r = make_ray(o, d);
+            if (!ok) { cs.best.prim = -2; return false; }                                   // padding slot
+        } else {
+            float4 o4 = ray_o[idx], d4 = ray_d[idx];
+            o = mk3(o4); d = mk3(d4);
+            pixel = __float_as_uint(o4.w); path = __float_as_uint(d4.w);
+            r = make_ray(o, d);
+        }
         if (s.n_nodes == 0) return false;
-        r = make_ray(mk3(o), mk3(d));
         float prune = prune_cfg;
         const bool ref_tree = prune < 0.f || degenerate_dir(r.d);       // literal walk / axis-degenerate ray
         if (ref_tree) prune = -1.f;
@@ -194,198 +384,104 @@ struct ClosestQuery {
         return traverse_step<true, true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
-        fb.hit[idx] = make_float4(cs.best.t, __int_as_float(cs.best.prim), cs.best.u, cs.best.v);
+        if (FUSED) has_result = true;
+        else if (WRT_IN_BOUNDS(idx, fb.cap0 > fb.capd ? fb.cap0 : fb.capd))
+            fb.hit[idx] = make_float4(cs.best.t, __int_as_float(cs.best.prim), cs.best.u, cs.best.v);
         return false;
+    }
+    __device__ __forceinline__ bool pending() const { return FUSED && has_result; }
+    __device__ __forceinline__ void retire() {
+        if (LEVEL0 && has_result && cs.best.prim != -2) ++valid;
+        surface_warp(s, fb, level, cull, has_result, r.o, r.d, pixel, path, cs.best.t, cs.best.prim, cs.best.u, cs.best.v, idx);
+        has_result = false;
+    }
+    __device__ __forceinline__ void done() {
+        if (LEVEL0) {
+            unsigned v = __reduce_add_sync(0xffffffffu, valid);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(fb.counters + C_VALID0, v);
+        }
     }
 };
 
-__global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
-                                                       float prune_rel, int refill) {
+// Fused closest hit + surface of one level (primary rays generated in begin() on level 0).
+template <bool LEVEL0>
+__global__ void WRT_FUSED_BOUNDS k_trace_surface(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
+                                                 const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int work_slot,
+                                                 float prune_rel, int refill, int cull) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
-    ClosestQuery q(s, fb, level, prune_rel);
-    const unsigned n = q.span.count();
-    run_queue(q, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
+    ClosestQuery<LEVEL0, true> q(s, fb, pg, level, n0, prune_rel, cull);
+    run_queue(q, q.span.count(), reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
+    q.done();
 }
 
-// ---- K3: hit -> surface, shadow requests, child rays (Renderer.hpp:170-257) ----
-// `cull`: shadow requests that provably cannot change the image are answered here and never queued.
-//   WRT_CULL_UNLIT  the light's diffuse AND specular factors at this point are exactly 0 (dev_shade.cuh,
-//                   light_terms_vanish): whatever the coefficient, the light adds +-0;
-//   WRT_CULL_SHAFT  (soft shadows) the whole shaft origin -> area light misses every leaf box: all 50
-//                   samples are lit, coefficient = 50 (shaft_cull.h).
-// The reference traces these rays; WrtStats keeps counting them and reports how many were answered this way.
-#define WRT_CULL_UNLIT 1
-#define WRT_CULL_SHAFT 2
-__global__ void __launch_bounds__(256) k_surface_spawn(DevScene s, FrameBuffers fb, int level, int cull) {
-    const LevelSpan span = level_span(fb.counters, level, fb.cap);
+// Unfused pair (WRT_FUSE_FROM): closest hit -> hit records, then one streaming pass over them.
+template <bool LEVEL0>
+__global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
+                                                 const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int work_slot,
+                                                 float prune_rel, int refill) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    ClosestQuery<LEVEL0, false> q(s, fb, pg, level, n0, prune_rel, 0);
+    run_queue(q, q.span.count(), reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
+}
+
+__global__ void __launch_bounds__(256) k_surface_spawn(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
+                                                       const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int cull) {
+    const LevelSpan span = level_span(fb, level, n0);
     const unsigned n = span.count();
-    const unsigned child_half = fb.cap / 2;
-    const float4* ray_o = fb.ray_o[level & 1];
-    const float4* ray_d = fb.ray_d[level & 1];
-    float4* nray_o = fb.ray_o[(level + 1) & 1];
-    float4* nray_d = fb.ray_d[(level + 1) & 1];
-    unsigned* overflow = fb.counters + C_OVERFLOW;
     const unsigned n_round = (n + 31u) & ~31u;         // whole warps stay converged for the aggregated appends
+    unsigned valid = 0;
     for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += gridDim.x * blockDim.x) {
-        const unsigned i = span.slot(item < n ? item : 0);       // slot in this level's arrays
         const bool live = item < n;
-        bool shade = false;
-        bool spawnT = false, spawnR = false;
-        float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 nb = make_float4(0.f, __int_as_float(-1), __int_as_float(-1), 0.f);
-        f3 org = mk3(0.f, 0.f, 0.f), dir = org, pos = org, nDir = org, N = org;
-        f3 refractDir = org, reflectDir = org, refRayOrig = org, traRayOrig = org;
+        const unsigned i = span.slot(live ? item : 0);
+        f3 org = mk3(0.f, 0.f, 0.f), dir = org;
         unsigned pixel = 0, path = 0;
-        int prim = -1;
-        float shade_n = 0.f;                                   // Phong exponent of the shaded material
-        unsigned lit_mask = 0, skip_mask = 0;                  // lights (< 32) answered without a request
+        float4 h = make_float4(0.f, __int_as_float(-2), 0.f, 0.f);
         if (live) {
-            float4 o4 = ray_o[i], d4 = ray_d[i], h = fb.hit[i];
-            org = mk3(o4); dir = mk3(d4);
-            pixel = __float_as_uint(o4.w); path = __float_as_uint(d4.w);
-            prim = __float_as_int(h.y);
-            if (prim == -1) {
-                na = make_float4(s.bkg[0], s.bkg[1], s.bkg[2], 0.f);            // miss: bkgcolor, :170
-            } else if (prim >= 0) {
-                Surface sf = complete_hit(s, org, dir, h.x, prim, h.z, h.w);
-                Mtl m = load_material(s, sf.material);
-                if (sf.flags & WRT_PRIM_LIGHT) {
-                    na = make_float4(m.diffuse.x, m.diffuse.y, m.diffuse.z, 0.f); // light avatar, :172
-                } else {
-                    shade = true;
-                    shade_n = m.n;
-                    f3 Od = m.diffuse;
-                    if (!float_equal(-1.f, (float)sf.textureIndex) && !float_equal(-1.f, sf.u) && !float_equal(-1.f, sf.v))
-                        Od = texture_at(s, s.textures + sf.textureIndex, sf.u, sf.v);      // :176-180
-                    if (sf.normalMapIndex != -1) sf.nDir = change_normal_dir(s, sf);        // :182-184
-                    pos = sf.pos; nDir = sf.nDir;
-                    float4* sv = fb.surf[level % WRT_SETS] + 4 * (size_t)i;
-                    sv[0] = make_float4(pos.x, pos.y, pos.z, __int_as_float(prim));
-                    sv[1] = make_float4(nDir.x, nDir.y, nDir.z, __int_as_float(sf.material));
-                    sv[2] = make_float4(Od.x, Od.y, Od.z, 0.f);
-                    sv[3] = make_float4(org.x, org.y, org.z, 0.f);          // p_eye_dir needs the ray origin, :267
-                    // ---- reflection / transmission, :194-257 ----
-                    refRayOrig = pos; traRayOrig = pos;
-                    N = normalized(nDir);
-                    float fr, eta_i, eta_t;
-                    float cosN_Dir = dot(N, -dir);
-                    if (cosN_Dir > 0) { eta_i = s.eta; eta_t = m.eta; }
-                    else { eta_i = m.eta; eta_t = s.eta; }
-                    fr = fresnel(dir, N, eta_i, eta_t);
-                    refractDir = normalized(refraction_dir(dir, N, eta_i, eta_t));
-                    reflectDir = normalized(reflection_dir(dir, nDir));
-                    float cos_refle_N = dot(reflectDir, N);
-                    float cos_refra_N = dot(refractDir, N);
-                    const float EPSILON = 0.00005f;
-                    if (cos_refle_N < 0) refRayOrig = refRayOrig - EPSILON * N;
-                    else refRayOrig = refRayOrig + EPSILON * N;
-                    if (cos_refra_N < 0) traRayOrig = traRayOrig - EPSILON * N;
-                    else traRayOrig = traRayOrig + EPSILON * N;
-                    if (float_equal(0.f, norm(refractDir))) fr = 1.f;
-                    spawnT = !float_equal(1.f, m.alpha) && !float_equal(fr, 1.f);
-                    spawnR = m.ks != 0;
-                    if (level + 1 >= WRT_MAX_DEPTH) { spawnT = false; spawnR = false; }    // traceRay depth cut, :152
-                    na.w = fr;
-                    nb.x = (1 - fr) * (1 - m.alpha);
-                    nb.w = 1.f;                                                    // composite node
-                }
+            h = fb.hit[i];
+            if (level == 0) {
+                path = 1u;
+                if (primary_ray(pg, item, org, dir, pixel)) ++valid;
+            } else {
+                float4 o4 = fb.ray_o[level & 1][i], d4 = fb.ray_d[level & 1][i];
+                org = mk3(o4); dir = mk3(d4);
+                pixel = __float_as_uint(o4.w); path = __float_as_uint(d4.w);
             }
         }
-        if (live && !shade) fb.surf[level % WRT_SETS][4 * (size_t)i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        // child rays: reflections into the first half of the next level, transmissions into the second
-        unsigned rslot = warp_alloc(fb.counters + C_NRAYS + level + 1, spawnR ? 1 : 0, child_half, overflow);
-        unsigned tslot = warp_alloc(fb.counters + C_NTRAYS + level + 1, spawnT ? 1 : 0, fb.cap - child_half, overflow);
-        if (spawnR && rslot != 0xffffffffu) {
-            nray_o[rslot] = make_float4(refRayOrig.x, refRayOrig.y, refRayOrig.z, __uint_as_float(pixel));
-            nray_d[rslot] = make_float4(reflectDir.x, reflectDir.y, reflectDir.z, __uint_as_float(path * 2u));
-            nb.y = __int_as_float((int)rslot);
-        }
-        if (spawnT && tslot != 0xffffffffu) {
-            unsigned c = child_half + tslot;
-            nray_o[c] = make_float4(traRayOrig.x, traRayOrig.y, traRayOrig.z, __uint_as_float(pixel));
-            nray_d[c] = make_float4(refractDir.x, refractDir.y, refractDir.z, __uint_as_float(path * 2u + 1u));
-            nb.z = __int_as_float((int)c);
-        }
-        // shadow requests: one per (shaded hit, light) — minus the ones that cannot change the image
-        const f3 sorig = pos + 0.0005f * nDir;                             // BVHStrategy.hpp:15, Renderer.hpp:349
-        int n_preq = shade ? s.n_point_lights : 0, n_dreq = shade ? s.n_dir_lights : 0;
-        if (shade && cull) {
-            const float so[3] = {sorig.x, sorig.y, sorig.z};
-            const f3 p_eye_dir = normalized(org - pos);                    // as blinn_phong() will compute it
-            for (int li = 0; li < s.n_lights && li < 32; li++) {
-                const WrtLight* L = s.lights + li;
-                const bool point = float_equal(L->pos[3], 1.f);
-                if ((cull & WRT_CULL_UNLIT) && light_terms_vanish(L, p_eye_dir, pos, nDir, shade_n)) {
-                    skip_mask |= 1u << li;                                 // coefficient is multiplied by 0 twice
-                    if (point) --n_preq; else --n_dreq;
-                } else if ((cull & WRT_CULL_SHAFT) && point) {
-                    float tri[9];
-                    for (int k = 0; k < 9; k++) tri[k] = L->tri[k];
-                    if (wrt_shaft_is_empty(s.onodes, s.n_nodes, so, tri)) { lit_mask |= 1u << li; --n_preq; }
-                }
-            }
-        }
-        unsigned pslot = warp_alloc(fb.counters + C_NPREQ + level, n_preq, fb.preq_cap, overflow);
-        unsigned dslot = 0xffffffffu;
-        if (s.n_dir_lights > 0) dslot = warp_alloc(fb.counters + C_NDREQ + level, n_dreq, fb.dreq_cap, overflow);
-        if (cull) {                                                        // statistics: the reference traces these rays
-            unsigned n_lit = __reduce_add_sync(0xffffffffu, (unsigned)__popc(lit_mask));
-            unsigned n_skip_p = __reduce_add_sync(0xffffffffu, (unsigned)((shade ? s.n_point_lights : 0) - n_preq - __popc(lit_mask)));
-            unsigned n_skip_d = __reduce_add_sync(0xffffffffu, (unsigned)((shade ? s.n_dir_lights : 0) - n_dreq));
-            if ((threadIdx.x & 31) == 0) {
-                if (n_lit) atomicAdd(fb.counters + C_NCULL + level, n_lit);
-                if (n_skip_p) atomicAdd(fb.counters + C_NSKIP + level, n_skip_p);
-                if (n_skip_d) atomicAdd(fb.counters + C_NDSKIP + level, n_skip_d);
-            }
-        }
-        if (shade) {
-            for (int li = 0; li < s.n_lights; li++) {
-                const bool lit = li < 32 && ((lit_mask >> li) & 1u), skip = li < 32 && ((skip_mask >> li) & 1u);
-                fb.coeff[level % WRT_SETS][(size_t)i * s.n_lights + li] = lit ? (float)WRT_SOFT_SAMPLES : 0.f;
-                if (lit || skip) continue;
-                bool point = float_equal(s.lights[li].pos[3], 1.f);
-                if (point && pslot != 0xffffffffu) {
-                    fb.preq_o[level % WRT_SETS][pslot] = make_float4(sorig.x, sorig.y, sorig.z, __uint_as_float(i));
-                    fb.preq_k[level % WRT_SETS][pslot] = make_uint4((unsigned)li, pixel, path, 0u);
-                    ++pslot;
-                } else if (!point && dslot != 0xffffffffu) {
-                    fb.dreq_o[level % WRT_SETS][dslot] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(i));
-                    fb.dreq_k[level % WRT_SETS][dslot] = make_uint4((unsigned)li, (unsigned)prim, 0u, 0u);
-                    ++dslot;
-                }
-            }
-        }
-        if (live) {
-            fb.node_a[level][i] = na;
-            fb.node_b[level][i] = nb;
-        }
+        surface_warp(s, fb, level, cull, live, org, dir, pixel, path, h.x, __float_as_int(h.y), h.z, h.w, i);
+    }
+    if (level == 0) {
+        valid = __reduce_add_sync(0xffffffffu, valid);
+        if ((threadIdx.x & 31) == 0 && valid) atomicAdd(fb.counters + C_VALID0, valid);
     }
 }
 
 // ---- K4a: hard shadows, BVHStrategy::getShadowCoeffi ----
 struct HardShadowQuery {
+    static constexpr bool RETIRES = false;
     const DevScene& s;
     const FrameBuffers& fb;
     Ray r;
     const float4* nodes;
     float dis, res;
-    unsigned out;
-    int par;
+    size_t out;
+    int q;
     bool literal;              // WRT_TRAVERSAL_EXHAUSTIVE: walk the reference-topology tree (its left-to-right product order)
-    __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int level, bool literal_)
-        : s(s_), fb(fb_), par(level % WRT_SETS), literal(literal_) {}
+    __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int q_, bool literal_)
+        : s(s_), fb(fb_), q(q_), literal(literal_) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
-        float4 o4 = fb.preq_o[par][item];
-        uint4 k = fb.preq_k[par][item];
+        float4 o4 = fb.preq_o[q][item];
+        uint4 k = fb.preq_k[q][item];
         const WrtLight* L = s.lights + k.x;
         f3 orig = mk3(o4);
         f3 lightPos = mk3(L->pos[0], L->pos[1], L->pos[2]);
         f3 raydir = normalized(lightPos - orig);
         dis = norm(lightPos - orig);
         r = make_ray(orig, raydir);
-        out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
+        out = (size_t)__float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
         res = 1.f;
         if (s.n_nodes == 0) return false;
         nodes = ((literal || degenerate_dir(raydir)) ? s.ronodes : s.onodes) + (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
@@ -401,17 +497,22 @@ struct HardShadowQuery {
         bool more = traverse_step<false, true>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
         return more && res != 0.f;
     }
-    __device__ __forceinline__ bool finish(int&, Stack&) { fb.coeff[par][out] = res; return false; }
+    __device__ __forceinline__ bool finish(int&, Stack&) {
+        if (WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) fb.coeff[out] = res;
+        return false;
+    }
+    __device__ __forceinline__ bool pending() const { return false; }
+    __device__ __forceinline__ void retire() {}
 };
 
-__global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot, int refill,
-                                                     int literal) {
+__global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q, int work_slot, int refill,
+                                               int literal) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
-    const unsigned n = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    HardShadowQuery q(s, fb, level, literal != 0);
-    run_queue(q, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
+    const unsigned n = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
+    HardShadowQuery hq(s, fb, q, literal != 0);
+    run_queue(hq, n, reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
 }
 
 // ---- K4b: soft shadows: 50 area-light samples per request (Renderer.hpp:405-414) ----
@@ -421,6 +522,7 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene 
 // (Tracing a sample pair per lane from one Philox block was tried: 16 % slower — register
 // pressure and a less coherent second walk; profiles/NOTES.md.)
 struct SoftShadowQuery {
+    static constexpr bool RETIRES = false;
     const DevScene& s;
     const FrameBuffers& fb;
     unsigned seed;
@@ -428,17 +530,17 @@ struct SoftShadowQuery {
     const float4* nodes;
     float dis;
     bool occ;
-    unsigned out;
-    int par;
+    size_t out;
+    int q;
     int last_occ;              // occluder cache: primitive that blocked this lane's previous ray, or -1
     bool use_cache;
-    __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_, int level, bool cache)
-        : s(s_), fb(fb_), seed(seed_), par(level % WRT_SETS), last_occ(-1), use_cache(cache && !s_.has_light_prims) {}
+    __device__ __forceinline__ SoftShadowQuery(const DevScene& s_, const FrameBuffers& fb_, unsigned seed_, int q_, bool cache)
+        : s(s_), fb(fb_), seed(seed_), q(q_), last_occ(-1), use_cache(cache && !s_.has_light_prims) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack& st) {
         unsigned req = (unsigned)(item / WRT_SOFT_SAMPLES);
         unsigned sample = (unsigned)(item - (unsigned long long)req * WRT_SOFT_SAMPLES);
-        float4 o4 = fb.preq_o[par][req];
-        uint4 k = fb.preq_k[par][req];
+        float4 o4 = fb.preq_o[q][req];
+        uint4 k = fb.preq_k[q][req];
         f3 v0, v1, v2;
         if (k.x < WRT_INLINE_LIGHTS) {                 // kernel-parameter constant bank
             const WrtLight& L = s.lights_c[k.x];
@@ -455,7 +557,7 @@ struct SoftShadowQuery {
         f3 raydir = normalized(lightPos - orig);
         dis = norm(lightPos - orig);
         r = make_ray(orig, raydir);
-        out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
+        out = (size_t)__float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
         const bool degenerate = degenerate_dir(raydir);
         // octant copy: ray_octant() uses `d < 0` exactly like the reference's swap, so +-0 components pick the
         // unswapped planes and the presorted slab test equals BoundBox::IntersectRay for every ray
@@ -476,19 +578,21 @@ struct SoftShadowQuery {
         return more && !occ;
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
-        if (!occ) atomicAdd(fb.coeff[par] + out, 1.0f);
+        if (!occ && WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) atomicAdd(fb.coeff + out, 1.0f);
         return false;
     }
+    __device__ __forceinline__ bool pending() const { return false; }
+    __device__ __forceinline__ void retire() {}
 };
 
-__global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level, int work_slot,
+__global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q, int work_slot,
                                                unsigned seed, int refill, int occluder_cache) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
-    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    SoftShadowQuery q(s, fb, seed, level, occluder_cache != 0);
-    run_queue(q, (unsigned long long)nreq * WRT_SOFT_SAMPLES, reinterpret_cast<unsigned long long*>(fb.counters + work_slot),
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
+    SoftShadowQuery sq(s, fb, seed, q, occluder_cache != 0);
+    run_queue(sq, (unsigned long long)nreq * WRT_SOFT_SAMPLES, reinterpret_cast<unsigned long long*>(fb.counters + work_slot),
               st, refill);
 }
 
@@ -500,7 +604,7 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 //                     and writes the primitives whose leaf box some ray of the shaft may hit, nearest first, to a
 //                     pool (bump allocation, one atomic per warp); the request keeps {offset, count}, count < 0 =
 //                     trace ray by ray.
-//   k_soft_list_rays  the level's nreq x 50 rays are cut into warp passes of 32 consecutive rays, handed out 8 passes
+//   k_soft_list_rays  the queue's nreq x 50 rays are cut into warp passes of 32 consecutive rays, handed out 8 passes
 //                     at a time from a global counter (balanced to ~10 us).  A ray tests only its request's list:
 //                     own-box test (exact BoundBox::IntersectRay) + intersection test, first blocker ends it.
 // Exact: a non-degenerate ray tests precisely the primitives whose own box it hits, and
@@ -527,17 +631,16 @@ struct SoftListBuffers {
 // (Phase 1 as a run_queue query with per-lane refill was tried — walk lengths differ a lot, 7-13 of 32 lanes are
 // active — and was slower, 19.5 vs 18.3 ms per frame: the refilled lanes run the ~200-instruction shaft set-up a few
 // lanes at a time, and lists allocated out of request order scatter phase 2's reads.)
-__global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
+__global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                               int work_slot, int stack_rows, SoftListBuffers lb) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);
-    const int par = level % WRT_SETS;
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
     int* mine = lb.scratch + (((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane) * WRT_LIST_CAP;
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
-    unsigned* pool_head = fb.counters + C_POOL + level;
+    unsigned* pool_head = fb.counters + C_POOL + q;
     while (true) {
         unsigned long long claimed = 0;
         if (lane == 0) claimed = atomicAdd(work, 32ull);
@@ -547,8 +650,8 @@ __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s
         int cnt = 0;
         if (req < nreq) {
             cnt = -1;
-            float4 o4 = fb.preq_o[par][req];
-            uint4 k = fb.preq_k[par][req];
+            float4 o4 = fb.preq_o[q][req];
+            uint4 k = fb.preq_k[q][req];
             const WrtLight* L = s.lights + k.x;
             float tri[9];
             for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
@@ -572,23 +675,23 @@ __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s
         const unsigned off = base + (unsigned)(incl - n);
         if (total > 0 && (base > lb.pool_cap || total > lb.pool_cap - base) && cnt > 0) cnt = -1;     // pool full: per-ray walk
         if (req < nreq) {
-            for (int i = 0; i < cnt; i++) lb.pool[off + i] = mine[i];
-            lb.ref[req] = make_int2((int)off, cnt);
+            for (int i = 0; i < cnt; i++)
+                if (WRT_IN_BOUNDS(off + i, lb.pool_cap)) lb.pool[off + i] = mine[i];
+            if (WRT_IN_BOUNDS(req, fb.preq_cap[q])) lb.ref[req] = make_int2((int)off, cnt);
         }
         // an empty list is an empty shaft: the ray kernel answers "lit" without building the rays (statistics only here)
         const unsigned n_empty = __popc(__ballot_sync(0xffffffffu, req < nreq && cnt == 0));
-        if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY + level, n_empty);
+        if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);
     }
 }
 
-__global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int level,
+__global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                   int work_slot, unsigned seed, SoftListBuffers lb) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned lane = threadIdx.x & 31;
-    const unsigned nreq = queue_len(fb.counters, C_NPREQ + level, fb.preq_cap);      // host guarantees nreq * 50 < 2^32
-    const int par = level % WRT_SETS;
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);      // host guarantees nreq * 50 < 2^32
     const unsigned n_rays = nreq * WRT_SOFT_SAMPLES, n_pass = (n_rays + 31u) / 32u;
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
     while (true) {
@@ -602,16 +705,16 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
             const unsigned j = pass * 32u + lane;
             const unsigned req = j / WRT_SOFT_SAMPLES, sample = j - req * WRT_SOFT_SAMPLES;
             bool lit = false;
-            unsigned out = 0;
+            size_t out = 0;
             const int2 ref = req < nreq ? lb.ref[req] : make_int2(0, 0);
             if (req < nreq && ref.y == 0) {
                 // empty list = no leaf box can be hit by any sample of this request (shaft_cull.h, axis-degenerate
                 // samples included): lit, and the ray itself is never needed
-                out = __float_as_uint(fb.preq_o[par][req].w) * (unsigned)s.n_lights + fb.preq_k[par][req].x;
+                out = (size_t)__float_as_uint(fb.preq_o[q][req].w) * (unsigned)s.n_lights + fb.preq_k[q][req].x;
                 lit = true;
             } else if (req < nreq) {
-                float4 o4 = fb.preq_o[par][req];
-                uint4 k = fb.preq_k[par][req];
+                float4 o4 = fb.preq_o[q][req];
+                uint4 k = fb.preq_k[q][req];
                 f3 v0, v1, v2;
                 if (k.x < WRT_INLINE_LIGHTS) {
                     const WrtLight& L = s.lights_c[k.x];
@@ -627,7 +730,7 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
                 f3 raydir = normalized(lightPos - orig);
                 const float dis = norm(lightPos - orig);
                 const Ray r = make_ray(orig, raydir);
-                out = __float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
+                out = (size_t)__float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
                 bool occ = false;
                 if (ref.y < 0 || degenerate_dir(raydir)) {
                     occ = occluded(s, degenerate_dir(raydir) ? s.nodes : s.fnodes, r, dis, st);
@@ -643,65 +746,79 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
             const unsigned first = __ballot_sync(0xffffffffu, req == rq0);       // lanes of the pass's first request
             const unsigned mine = req == rq0 ? first : ~first;
             const unsigned n_lit = __popc(lit_mask & mine);
-            if (n_lit && lane == (unsigned)(__ffs(mine) - 1)) atomicAdd(fb.coeff[par] + out, (float)n_lit);
+            if (n_lit && lane == (unsigned)(__ffs(mine) - 1) && WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights))
+                atomicAdd(fb.coeff + out, (float)n_lit);
         }
     }
 }
 
 // ---- K4c: directional-light shadows, Renderer.hpp:381-400 (dilated-tree culling, dev_traverse.cuh) ----
+// literal != 0 (WRT_TRAVERSAL_EXHAUSTIVE): the reference's own O(N) loop over objList.
 __global__ void __launch_bounds__(128) k_shadow_directional(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
-                                                            int level) {
+                                                            int q, int literal) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
-    const unsigned n = queue_len(fb.counters, C_NDREQ + level, fb.dreq_cap);
+    const unsigned n = queue_len(fb.counters, C_NDREQ + q, fb.dreq_cap[q]);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o4 = fb.dreq_o[level % WRT_SETS][i];
-        uint4 k = fb.dreq_k[level % WRT_SETS][i];
+        float4 o4 = fb.dreq_o[q][i];
+        uint4 k = fb.dreq_k[q][i];
         const WrtLight* L = s.lights + k.x;
         f3 negDir = mk3(-L->pos[0], -L->pos[1], -L->pos[2]);
         Ray r = make_ray(mk3(o4), normalized(negDir));
-        fb.coeff[level % WRT_SETS][(size_t)__float_as_uint(o4.w) * s.n_lights + k.x] = directional_product_bvh(s, r, (int)k.y, st);
+        const size_t out = (size_t)__float_as_uint(o4.w) * s.n_lights + k.x;
+        const float c = literal ? directional_product(s, r, (int)k.y) : directional_product_bvh(s, r, (int)k.y, st);
+        if (WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) fb.coeff[out] = c;
     }
 }
 
 // ---- K5: local shading, Renderer::blinnPhongShader ----
-#define WRT_MAX_LIGHTS_FAST 8
-__global__ void __launch_bounds__(256) k_shade(DevScene s, FrameBuffers fb, int level) {
-    const LevelSpan span = level_span(fb.counters, level, fb.cap);
-    const unsigned n = span.count();
-    for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
-        const unsigned i = span.slot(item);
-        const float4* sv = fb.surf[level % WRT_SETS] + 4 * (size_t)i;
-        float4 s0 = sv[0];
-        if (__float_as_int(s0.w) < 0) continue;
-        float4 s1 = sv[1], s2 = sv[2], s3 = sv[3];
-        Mtl m = load_material(s, __float_as_int(s1.w));
-        m.diffuse = mk3(s2);
-        f3 local = blinn_phong(s, mk3(s3), mk3(s0), mk3(s1), m, fb.coeff[level % WRT_SETS] + (size_t)i * s.n_lights);
-        float4 na = fb.node_a[level][i];
-        na.x = local.x; na.y = local.y; na.z = local.z;
-        fb.node_a[level][i] = na;
+__device__ __forceinline__ void shade_node(const DevScene& s, const FrameBuffers& fb, unsigned g) {
+    const float4* sv = fb.surf + 4 * (size_t)g;
+    float4 s0 = sv[0];
+    if (__float_as_int(s0.w) < 0) return;
+    float4 s1 = sv[1], s2 = sv[2], s3 = sv[3];
+    Mtl m = load_material(s, __float_as_int(s1.w));
+    m.diffuse = mk3(s2);
+    f3 local = blinn_phong(s, mk3(s3), mk3(s0), mk3(s1), m, fb.coeff + (size_t)g * s.n_lights);
+    float4 na = fb.node_a[g];
+    na.x = local.x; na.y = local.y; na.z = local.z;
+    fb.node_a[g] = na;
+}
+
+// Shades the nodes of levels [level_lo, level_hi] in one sweep (the levels' spans concatenated).
+__device__ __forceinline__ void shade_levels(const DevScene& s, const FrameBuffers& fb, unsigned n0, int level_lo, int level_hi) {
+    for (int level = level_lo; level <= level_hi; level++) {
+        const LevelSpan span = level_span(fb, level, n0);
+        const unsigned n = span.count();
+        for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x)
+            shade_node(s, fb, node_id(fb, level, span.slot(item)));
     }
 }
 
+__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, unsigned n0,
+                                               int level_lo, int level_hi) {
+    shade_levels(s, fb, n0, level_lo, level_hi);
+}
+
 // ---- K6 + K7: bottom-up combine (Renderer.hpp:259) and 8-bit resolve (Renderer.hpp:128-130) ----
-// One cooperative launch walks the levels 8 -> 0 with a grid-wide barrier between them (each
-// level reads the finished colours of the level below), then quantises level 0.
-__device__ __forceinline__ void combine_level(const FrameBuffers& fb, int level) {
-    const LevelSpan span = level_span(fb.counters, level, fb.cap);
+// One cooperative launch: shade the levels no k_shade launch has covered (shade_from .. 8), then walk the levels
+// 8 -> 0 with a grid-wide barrier between them (each level reads the finished colours of the level below), then
+// quantise level 0.
+__device__ __forceinline__ void combine_level(const FrameBuffers& fb, int level, unsigned n0) {
+    const LevelSpan span = level_span(fb, level, n0);
     const unsigned n = span.count();
     for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
-        const unsigned i = span.slot(item);
-        float4 nb = fb.node_b[level][i];
+        const unsigned g = node_id(fb, level, span.slot(item));
+        float4 nb = fb.node_b[g];
         if (nb.w == 0.f) continue;                       // miss / light avatar: returned as is
-        float4 na = fb.node_a[level][i];
+        float4 na = fb.node_a[g];
         int cR = __float_as_int(nb.y), cT = __float_as_int(nb.z);
         f3 R = mk3(0.f, 0.f, 0.f), T = R;
-        if (cR >= 0) R = mk3(fb.node_a[level + 1][cR]);
-        if (cT >= 0) T = mk3(fb.node_a[level + 1][cT]);
+        if (cR >= 0) R = mk3(fb.node_a[cR]);
+        if (cT >= 0) T = mk3(fb.node_a[cT]);
         f3 c = mk3(na) + na.w * R + nb.x * T;            // blinnPhongRes + fr * R_lambda + (1-fr)(1-alpha) * T_lambda
-        fb.node_a[level][i] = make_float4(c.x, c.y, c.z, na.w);
+        fb.node_a[g] = make_float4(c.x, c.y, c.z, na.w);
     }
 }
 
@@ -711,16 +828,25 @@ __device__ __forceinline__ unsigned char quantize(float c) {   // int(255 * std:
     return (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
-// image != nullptr: row-major image; packed != nullptr: tile-order buffer (multi-GPU gather)
-__global__ void __launch_bounds__(256) k_combine_resolve(const __grid_constant__ FrameBuffers fb, const __grid_constant__ TileMap tm,
-                                                         long long slot0, unsigned n, unsigned char* image, unsigned char* packed) {
+// image != nullptr: row-major image (may live on a peer GPU: multi-GPU contexts store straight into device 0's
+// frame over NVLink); packed != nullptr: tile-order buffer (NCCL gather)
+__global__ void __launch_bounds__(256) k_combine_resolve(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
+                                                         const __grid_constant__ TileMap tm, long long slot0, unsigned n, int shade_from,
+                                                         unsigned char* image, unsigned char* packed) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    for (int level = WRT_MAX_DEPTH - 1; level >= 0; level--) {
-        combine_level(fb, level);
+    if (shade_from < WRT_MAX_DEPTH) {
+        shade_levels(s, fb, n, shade_from, WRT_MAX_DEPTH - 1);
         grid.sync();
     }
+    for (int level = WRT_MAX_DEPTH - 1; level >= 0; level--) {
+        // (a level without rays has nothing to combine and nothing below it either, but every CTA must take
+        // part in the same number of barriers)
+        combine_level(fb, level, n);
+        if (level > 0) grid.sync();
+    }
+    // level 0: every thread quantises the nodes it has just combined (same grid-stride mapping), no barrier needed
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 c = fb.node_a[0][i];
+        float4 c = fb.node_a[i];
         unsigned char r = quantize(c.x), g = quantize(c.y), b = quantize(c.z);
         if (packed) {
             unsigned char* p = packed + 3 * (size_t)(slot0 + i);

@@ -45,9 +45,11 @@ struct TimedLaunch {
 struct WrtContext {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t side_stream[WRT_SIDE_STREAMS] = {};    // shadow + shade kernels of level d run on side_stream[d % WRT_SIDE_STREAMS]
-    cudaEvent_t ev_surface[WRT_MAX_DEPTH] = {}, ev_shade[WRT_MAX_DEPTH] = {};
+    // All frame work runs on two internal streams: `chain` (high priority: the dependent closest-hit chain, the deep
+    // levels' shadow kernels, combine + resolve) and `side` (level 0's shadow + shade kernels).  A caller-provided stream
+    // (wrt_render_device) is joined to them by two events, nothing else runs on it.
+    cudaStream_t chain = nullptr, side = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_lvl0 = nullptr, ev_side = nullptr, ev_out = nullptr;
     bool overlap = true;
 
     // scene
@@ -66,30 +68,35 @@ struct WrtContext {
     int tile_w = 8, tile_h = 4, rank = 0, world = 1;   // one warp-sized 8x4 block per tile: finest interleave
     int traversal = WRT_TRAVERSAL_PRUNED;
     uint32_t seed = WRT_DEFAULT_SEED;
-    float queue_factor = 2.0f;
+    float queue_factor = 0.f;          // > 0: caller-fixed deep-level capacity (multiple of the batch); 0: automatic
+    float deep_factor = 0.25f;         // automatic mode: current deep-level capacity factor (grows on overflow)
     float prune_rel = 1e-3f;
     bool kernel_timing = false;
     int refill = 16;                   // idle lanes that trigger a refill on deep ray-tree levels
     int refill_soft = 24;
     bool shaft_cull = true;            // soft shadows: answer requests whose light shaft is empty without tracing (shaft_cull.h)
     bool soft_lists = true;            // soft shadows: per-request candidate lists (k_soft_lists + k_soft_list_rays) instead of per-ray walks
-    int lists_from_level = 0;
     long long list_pool_cap_override = 0;
-    int shaft_cull_max_level = 0;      // deepest ray-tree level whose surface kernel runs the shaft test (when lists are on)
-    wrt::SoftListBuffers list_bufs[WRT_SIDE_STREAMS] = {};
+    int shaft_cull_max_level = 0;      // deepest ray-tree level whose surface stage runs the shaft test (when lists are on)
+    wrt::SoftListBuffers list_bufs[2] = {};
     wrt::FastBvhBuilder fbvh;          // host scratch of wrt_upload_scene, kept between uploads
     std::vector<WrtNode> h_oct;
     bool unlit_cull = true;            // drop shadow requests of lights whose shading terms are exactly 0 at the point
-    int cache_from_level = 0;          // soft shadows: occluder cache on levels >= this (99 = off)
+    int cache_from_level = 0;          // per-ray soft-shadow kernel: occluder cache (99 = off)
     int chunk_div = 16;                // work claiming: 0 = one atomic per refill, k = chunks of n/(warps*k) items
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
-    int smem_rows_cap = 64;
-    int trace_blocks_per_sm = 10;
+    int trace_blocks_per_sm = 10;      // persistent shadow / unfused closest-hit kernels
+    int fused_blocks_per_sm = WRT_FUSED_MIN_BLOCKS;
+    int fuse_from = 99;                // levels >= this run the fused closest-hit + surface kernel (99: never; experimental, see kernels.cuh)
+    bool shade0_separate = true;       // level 0 is shaded by its own launch on the side stream (else inside combine)
+    bool small_batch_full_levels = true; // automatic sizing: batches under 1 M slots get full-size deep levels
+    long long max_batch = 1ll << 25;   // primary slots per batch (8K = 33.2 M slots fits)
 
     // frame buffers
     wrt::FrameBuffers fb{};
     std::vector<void*> frame_allocs;
     unsigned batch_slots = 0;          // primary slots the buffers were sized for
+    unsigned deep_slots = 0;           // slots of each deeper level
     int fb_lights = -1, fb_point = -1, fb_dir = -1;
     unsigned* h_counters = nullptr;    // pinned
     uint8_t* d_image = nullptr;        // full image, row-major (wrt_render)
@@ -110,8 +117,12 @@ struct WrtContext {
     std::vector<cudaEvent_t> event_pool;
     size_t event_next = 0;
     float family_ms[WRT_KERNEL_FAMILIES] = {0};
+    int family_launches[WRT_KERNEL_FAMILIES] = {0};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    cudaStream_t last_stream = nullptr;
+    cudaStream_t user_stream = nullptr;
+    bool user_stream_joined = false;
+    uint8_t* last_image = nullptr;     // targets of the frame in flight (needed again if an overflowed batch is redone)
+    uint8_t* last_packed = nullptr;
     bool frame_pending = false;
     bool has_frame = false;
 
@@ -145,7 +156,7 @@ int dev_upload(WrtContext* c, const T* src, size_t count, const T** dst) {
         c->scene_alloc_bytes[slot] = bytes;
     }
     void* p = c->scene_allocs[slot];
-    if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->own_stream));
+    if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->chain));
     *dst = (const T*)p;
     return 0;
 }
@@ -161,6 +172,7 @@ void free_frame(WrtContext* c) {
     for (void* p : c->frame_allocs) cudaFree(p);
     c->frame_allocs.clear();
     c->batch_slots = 0;
+    c->deep_slots = 0;
     memset(&c->fb, 0, sizeof c->fb);
 }
 
@@ -188,51 +200,70 @@ int frame_alloc(WrtContext* c, T** p, size_t count) {
     return 0;
 }
 
+// Slots of each deeper level for a batch of `slots` primary slots.  Caller-fixed factor: factor x slots.  Automatic:
+// small batches get a full-size level (memory is no object there), large ones `deep_factor` of the batch — in the bunny
+// frames <= 16 % of the pixels spawn secondary rays; the factor doubles when a level overflows.
+unsigned deep_slots_for(const WrtContext* c, unsigned slots) {
+    double want;
+    if (c->queue_factor > 0.f) want = (double)slots * c->queue_factor;
+    else want = std::max((double)slots * c->deep_factor, c->small_batch_full_levels ? std::min((double)slots, 1048576.0) : 0.0);
+    want = std::min(want, 2.0e9);
+    return ((unsigned)std::max(want, 64.0) + 63u) & ~63u;
+}
+
 int ensure_frame_buffers(WrtContext* c, unsigned slots) {
     const wrt::DevScene& ds = c->ds;
-    if (c->batch_slots >= slots && c->fb_lights == ds.n_lights && c->fb_point == ds.n_point_lights &&
+    const unsigned capd = deep_slots_for(c, slots);
+    if (c->batch_slots >= slots && c->deep_slots >= capd && c->fb_lights == ds.n_lights && c->fb_point == ds.n_point_lights &&
         c->fb_dir == ds.n_dir_lights)
         return 0;
+    CK(cudaDeviceSynchronize());
     free_frame(c);
     FrameBuffers& fb = c->fb;
-    double f = c->queue_factor > 0 ? c->queue_factor : 2.0;
-    unsigned long long cap64 = (unsigned long long)((double)slots * std::max(1.0, f)) + 64;
-    if (cap64 > 0x7fffff00ull) return fail("frame batch too large for 32-bit queue indices");
-    unsigned cap = (unsigned)cap64;
-    fb.cap = cap;
-    fb.preq_cap = cap * (unsigned)std::max(1, ds.n_point_lights);
-    fb.dreq_cap = cap * (unsigned)std::max(1, ds.n_dir_lights);
-    if ((unsigned long long)cap * std::max(1, ds.n_lights) > 0xffffff00ull) return fail("too many (node, light) pairs");
+    const unsigned cap0 = slots + 64;
+    const unsigned long long nodes64 = (unsigned long long)cap0 + (unsigned long long)(WRT_MAX_DEPTH - 1) * capd;
+    if (nodes64 > 0x7fffff00ull) return fail("frame batch too large for 32-bit node indices");
+    if (nodes64 * std::max(1, ds.n_lights) > 0xffffffffffull) return fail("too many (node, light) pairs");
+    fb.cap0 = cap0; fb.capd = capd; fb.n_node_cap = (unsigned)nodes64;
+    const unsigned long long deep_nodes = (unsigned long long)(WRT_MAX_DEPTH - 1) * capd;
+    auto req_cap = [](unsigned long long nodes, int lights) {
+        return (unsigned)std::min<unsigned long long>(nodes * (unsigned long long)std::max(1, lights), 0xffffff00ull);
+    };
+    fb.preq_cap[0] = req_cap(cap0, ds.n_point_lights); fb.preq_cap[1] = req_cap(deep_nodes, ds.n_point_lights);
+    fb.dreq_cap[0] = req_cap(cap0, ds.n_dir_lights);   fb.dreq_cap[1] = req_cap(deep_nodes, ds.n_dir_lights);
     for (int k = 0; k < 2; k++) {
-        if (frame_alloc(c, &fb.ray_o[k], cap)) return 1;
-        if (frame_alloc(c, &fb.ray_d[k], cap)) return 1;
+        if (frame_alloc(c, &fb.ray_o[k], capd)) return 1;
+        if (frame_alloc(c, &fb.ray_d[k], capd)) return 1;
     }
-    if (frame_alloc(c, &fb.hit, cap)) return 1;
-    for (int k = 0; k < WRT_SETS; k++) if (frame_alloc(c, &fb.surf[k], 4 * (size_t)cap)) return 1;
-    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
-        if (frame_alloc(c, &fb.node_a[d], cap)) return 1;
-        if (frame_alloc(c, &fb.node_b[d], cap)) return 1;
-    }
-    for (int k = 0; k < WRT_SETS; k++) {
-        if (frame_alloc(c, &fb.preq_o[k], ds.n_point_lights ? fb.preq_cap : 1)) return 1;
-        if (frame_alloc(c, &fb.preq_k[k], ds.n_point_lights ? fb.preq_cap : 1)) return 1;
-        if (frame_alloc(c, &fb.dreq_o[k], ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
-        if (frame_alloc(c, &fb.dreq_k[k], ds.n_dir_lights ? fb.dreq_cap : 1)) return 1;
-        if (frame_alloc(c, &fb.coeff[k], (size_t)cap * std::max(1, ds.n_lights))) return 1;
+    if (frame_alloc(c, &fb.hit, std::max(cap0, capd))) return 1;
+    if (frame_alloc(c, &fb.surf, 4 * (size_t)nodes64)) return 1;
+    if (frame_alloc(c, &fb.node_a, (size_t)nodes64)) return 1;
+    if (frame_alloc(c, &fb.node_b, (size_t)nodes64)) return 1;
+    if (frame_alloc(c, &fb.coeff, (size_t)nodes64 * std::max(1, ds.n_lights))) return 1;
+    for (int q = 0; q < 2; q++) {
+        if (frame_alloc(c, &fb.preq_o[q], ds.n_point_lights ? fb.preq_cap[q] : 1)) return 1;
+        if (frame_alloc(c, &fb.preq_k[q], ds.n_point_lights ? fb.preq_cap[q] : 1)) return 1;
+        if (frame_alloc(c, &fb.dreq_o[q], ds.n_dir_lights ? fb.dreq_cap[q] : 1)) return 1;
+        if (frame_alloc(c, &fb.dreq_k[q], ds.n_dir_lights ? fb.dreq_cap[q] : 1)) return 1;
     }
     if (frame_alloc(c, &fb.counters, wrt::C_TOTAL)) return 1;
-    // candidate lists of the soft-shadow path (kernels.cuh, K4b'), one set per side stream (launches on different
-    // side streams overlap): walk scratch per thread, list pool, per-request {offset, count}.  A full pool only
-    // means per-ray walks for the remaining requests.
-    for (int k = 0; k < WRT_SIDE_STREAMS; k++) {
-        wrt::SoftListBuffers& lb = c->list_bufs[k];
-        lb.pool_cap = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(8ull << 20, 2ull * fb.preq_cap), 1ull << 30);
+    // candidate lists of the soft-shadow path (kernels.cuh, K4b'), one set per request queue (their launches overlap):
+    // walk scratch per thread, list pool, per-request {offset, count}.  A full pool only means per-ray walks for the
+    // remaining requests.  Level-0 requests that survive the shaft test at spawn time have 1-2 candidates; deep-level
+    // ones (origins on the bunny) ~30.
+    for (int q = 0; q < 2; q++) {
+        wrt::SoftListBuffers& lb = c->list_bufs[q];
+        const unsigned long long per_req = q == 0 ? 2ull : 12ull;
+        lb.pool_cap = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(8ull << 20, per_req * fb.preq_cap[q]), 1ull << 30);
+        if (!ds.n_point_lights || ds.shadow_type == 0) lb.pool_cap = 64;
         if (c->list_pool_cap_override > 0) lb.pool_cap = (unsigned)c->list_pool_cap_override;     // tests: force the pool-full path
-        if (frame_alloc(c, &lb.scratch, (size_t)c->num_sms * c->trace_blocks_per_sm * 128 * WRT_LIST_CAP)) return 1;
+        const bool lists_possible = ds.n_point_lights && ds.shadow_type != 0;
+        if (frame_alloc(c, &lb.scratch, lists_possible ? (size_t)c->num_sms * c->trace_blocks_per_sm * 128 * WRT_LIST_CAP : 1)) return 1;
         if (frame_alloc(c, &lb.pool, lb.pool_cap)) return 1;
-        if (frame_alloc(c, &lb.ref, ds.n_point_lights ? fb.preq_cap : 1)) return 1;
+        if (frame_alloc(c, &lb.ref, lists_possible ? fb.preq_cap[q] : 1)) return 1;
     }
     c->batch_slots = slots;
+    c->deep_slots = capd;
     c->fb_lights = ds.n_lights; c->fb_point = ds.n_point_lights; c->fb_dir = ds.n_dir_lights;
     return 0;
 }
@@ -284,99 +315,119 @@ size_t stack_bytes(WrtContext* c, int threads) { return (size_t)c->stack_rows * 
 
 float prune_value(const WrtContext* c) { return c->traversal == WRT_TRAVERSAL_PRUNED ? c->prune_rel : -1.f; }
 
-// Enqueues one batch of primary slots [slot0, slot0+n) on `st`.
-int enqueue_batch(WrtContext* c, cudaStream_t st, long long slot0, unsigned n, uint8_t* d_image, uint8_t* d_packed) {
+// The shadow kernels of request queue q (0: level 0, 1: levels 1..8 together) on stream `st`.
+int enqueue_shadows(WrtContext* c, cudaStream_t st, int q, int& work_seq) {
     using namespace wrt;
     FrameBuffers& fb = c->fb;
     const DevScene& ds = c->ds;
-    TileMap tm = c->tilemap();
-    CK(cudaMemsetAsync(fb.counters, 0, C_TOTAL * sizeof(unsigned), st));
-    c->work_seq = 0;
-    auto work_slot = [&]() { int s = C_WORK + 2 * c->work_seq; ++c->work_seq; return s; };
     const int TB = 128;
     const int trace_grid = grid_for(c, c->trace_blocks_per_sm), wide_grid = grid_for(c, 8);
     const size_t sb = stack_bytes(c, TB);
-    const float prune = prune_value(c);
-    {
-        LaunchScope ls(c, st, F_RAYGEN);
-        k_raygen<<<wide_grid, 256, 0, st>>>(c->cam, tm, slot0, n, fb);
-    }
-    // Level d: closest hit + surface on the caller's stream; its shadow + shade kernels on side stream
-    // d % WRT_SIDE_STREAMS.  They overlap level d+1's closest hit + surface (which only need surface(d)'s output) and the
-    // tail of level d-1's shadow kernel on the other side stream: a persistent traversal kernel ends with
-    // its longest ray (hundreds of node steps along the bunny's silhouette, ~150 us measured per launch),
-    // during which the SMs would otherwise idle.  Request / coefficient / surface buffers rotate over
-    // WRT_SETS levels.
-    const bool overlap = c->overlap && !c->kernel_timing;
-    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
-        cudaStream_t ss = overlap ? c->side_stream[d % WRT_SIDE_STREAMS] : st;
-        if (overlap && d >= WRT_SETS) CK(cudaStreamWaitEvent(st, c->ev_shade[d - WRT_SETS], 0));   // buffer set free again
-        {
-            LaunchScope ls(c, st, F_TRACE);
-            k_trace_closest<<<trace_grid, TB, sb, st>>>(ds, fb, d, work_slot(), prune, (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8));
-        }
-        {
-            LaunchScope ls(c, st, F_SURFACE);
-            // request culling belongs to the pruned mode; WRT_TRAVERSAL_EXHAUSTIVE traces every ray the reference traces
-            int cull = 0;
-            if (c->traversal == WRT_TRAVERSAL_PRUNED) {
-                if (c->unlit_cull) cull |= WRT_CULL_UNLIT;
-                // The shaft test at spawn time pays where most shafts are empty (primary hits: 79 % in the metric frame); on
-                // deeper levels (~8 %) k_soft_lists finds the empty ones anyway (an empty list), off the critical
-                // closest-hit -> surface chain.  Without the list kernels the test runs on every level.
-                const bool lists_on = c->soft_lists && !ds.has_light_prims;
-                if (c->shaft_cull && ds.shadow_type != 0 && (d <= c->shaft_cull_max_level || !lists_on)) cull |= WRT_CULL_SHAFT;
-            }
-            k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, d, cull);
-        }
-        if (overlap) {
-            CK(cudaEventRecord(c->ev_surface[d], st));
-            CK(cudaStreamWaitEvent(ss, c->ev_surface[d], 0));
-        }
-        if (ds.n_point_lights > 0) {
-            if (ds.shadow_type == 0) {
-                LaunchScope ls(c, ss, F_SHADOW_HARD);
-                k_shadow_hard<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8),
-                                                          c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
-            } else {
-                // per-request candidate lists (kernels.cuh, K4b'); scenes with light avatars keep the per-ray kernel,
-                // whose literal hasIntersection path they need, and so does WRT_TRAVERSAL_EXHAUSTIVE
-                const bool lists = c->soft_lists && !ds.has_light_prims && ds.n_nodes > 0 && c->traversal == WRT_TRAVERSAL_PRUNED &&
-                                   d >= c->lists_from_level && (unsigned long long)fb.preq_cap * WRT_SOFT_SAMPLES < (1ull << 32);
-                if (lists) {
-                    const SoftListBuffers& lb = c->list_bufs[d % WRT_SIDE_STREAMS];
-                    {
-                        LaunchScope ls(c, ss, F_SOFT_LISTS);
-                        k_soft_lists<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->stack_rows, lb);
-                    }
-                    LaunchScope ls(c, ss, F_SHADOW_SOFT);
-                    k_soft_list_rays<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, lb);
-                } else {
-                    LaunchScope ls(c, ss, F_SHADOW_SOFT);
-                    k_shadow_soft<<<trace_grid, TB, sb, ss>>>(ds, fb, d, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
-                                                              d >= c->cache_from_level ? 1 : 0);
+    auto work_slot = [&]() { int s = C_WORK + 2 * work_seq; ++work_seq; return s; };
+    const int refill = (q == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8);
+    if (ds.n_point_lights > 0) {
+        if (ds.shadow_type == 0) {
+            LaunchScope ls(c, st, F_SHADOW_HARD);
+            k_shadow_hard<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), refill, c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
+        } else {
+            // per-request candidate lists (kernels.cuh, K4b'); scenes with light avatars keep the per-ray kernel,
+            // whose literal hasIntersection path they need, and so does WRT_TRAVERSAL_EXHAUSTIVE
+            const bool lists = c->soft_lists && !ds.has_light_prims && ds.n_nodes > 0 && c->traversal == WRT_TRAVERSAL_PRUNED &&
+                               (unsigned long long)fb.preq_cap[q] * WRT_SOFT_SAMPLES < (1ull << 32);
+            if (lists) {
+                const SoftListBuffers& lb = c->list_bufs[q];
+                {
+                    LaunchScope ls(c, st, F_SOFT_LISTS);
+                    k_soft_lists<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->stack_rows, lb);
                 }
+                LaunchScope ls(c, st, F_SHADOW_SOFT);
+                k_soft_list_rays<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->seed, lb);
+            } else {
+                LaunchScope ls(c, st, F_SHADOW_SOFT);
+                k_shadow_soft<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
+                                                          c->cache_from_level <= (q == 0 ? 0 : 1) ? 1 : 0);
             }
         }
-        if (ds.n_dir_lights > 0) {
-            LaunchScope ls(c, ss, F_SHADOW_DIR);
-            k_shadow_directional<<<wide_grid, TB, sb, ss>>>(ds, fb, d);
-        }
-        {
-            LaunchScope ls(c, ss, F_SHADE);
-            k_shade<<<wide_grid, 256, 0, ss>>>(ds, fb, d);
-        }
-        if (overlap) CK(cudaEventRecord(c->ev_shade[d], ss));
     }
-    if (overlap)
-        for (int k = 1; k <= WRT_SIDE_STREAMS; k++) CK(cudaStreamWaitEvent(st, c->ev_shade[WRT_MAX_DEPTH - k], 0));
+    if (ds.n_dir_lights > 0) {
+        LaunchScope ls(c, st, F_SHADOW_DIR);
+        k_shadow_directional<<<wide_grid, TB, sb, st>>>(ds, fb, q, c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
+    }
+    return 0;
+}
+
+// Enqueues one batch of primary slots [slot0, slot0+n): closest-hit chain + deep shadows on `chain`, level 0's shadow
+// work on `side`.
+int enqueue_batch(WrtContext* c, long long slot0, unsigned n, uint8_t* d_image, uint8_t* d_packed) {
+    using namespace wrt;
+    FrameBuffers& fb = c->fb;
+    const DevScene& ds = c->ds;
+    cudaStream_t st = c->chain;
+    const bool overlap = c->overlap && !c->kernel_timing;
+    cudaStream_t ss = overlap ? c->side : st;
+    PrimaryGen pg;
+    pg.cam = c->cam; pg.tm = c->tilemap(); pg.slot0 = slot0;
+    CK(cudaMemsetAsync(fb.counters, 0, C_TOTAL * sizeof(unsigned), st));
+    int work_seq = 0;
+    auto work_slot = [&]() { int s = C_WORK + 2 * work_seq; ++work_seq; return s; };
+    const int TB = 128;
+    const int trace_grid = grid_for(c, c->trace_blocks_per_sm), fused_grid = grid_for(c, c->fused_blocks_per_sm), wide_grid = grid_for(c, 8);
+    const size_t sb = stack_bytes(c, TB);
+    const float prune = prune_value(c);
+    auto cull_for = [&](int d) {
+        // request culling belongs to the pruned mode; WRT_TRAVERSAL_EXHAUSTIVE traces every ray the reference traces
+        int cull = 0;
+        if (c->traversal == WRT_TRAVERSAL_PRUNED) {
+            if (c->unlit_cull) cull |= WRT_CULL_UNLIT;
+            // The shaft test at spawn time pays where most shafts are empty (primary hits: 79 % in the metric frame); on
+            // deeper levels (~8 %) k_soft_lists finds the empty ones anyway (an empty list), off the critical
+            // closest-hit chain.  Without the list kernels the test runs on every level.
+            const bool lists_on = c->soft_lists && !ds.has_light_prims;
+            if (c->shaft_cull && ds.shadow_type != 0 && (d <= c->shaft_cull_max_level || !lists_on)) cull |= WRT_CULL_SHAFT;
+        }
+        return cull;
+    };
+    auto level_kernels = [&](int d) {
+        const int refill = (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8);
+        if (d >= c->fuse_from) {
+            LaunchScope ls(c, st, F_TRACE);
+            if (d == 0) k_trace_surface<true><<<fused_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill, cull_for(d));
+            else k_trace_surface<false><<<fused_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill, cull_for(d));
+        } else {
+            {
+                LaunchScope ls(c, st, F_TRACE);
+                if (d == 0) k_trace_closest<true><<<trace_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill);
+                else k_trace_closest<false><<<trace_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill);
+            }
+            LaunchScope ls(c, st, F_SURFACE);
+            k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, pg, d, n, cull_for(d));
+        }
+    };
+    level_kernels(0);
+    if (overlap) {
+        CK(cudaEventRecord(c->ev_lvl0, st));
+        CK(cudaStreamWaitEvent(ss, c->ev_lvl0, 0));
+    }
+    // level 0's shadow + shade kernels run beside the deep chain: a deep level holds few, long, incoherent rays and
+    // leaves most of the SMs idle; a persistent traversal kernel ends with its longest ray
+    if (enqueue_shadows(c, ss, 0, work_seq)) return 1;
+    if (c->shade0_separate) {
+        LaunchScope ls(c, ss, F_SHADE);
+        k_shade<<<wide_grid, 256, 0, ss>>>(ds, fb, n, 0, 0);
+    }
+    if (overlap) CK(cudaEventRecord(c->ev_side, ss));
+    for (int d = 1; d < WRT_MAX_DEPTH; d++) level_kernels(d);
+    if (enqueue_shadows(c, st, 1, work_seq)) return 1;
+    if (overlap) CK(cudaStreamWaitEvent(st, c->ev_side, 0));
     {
         LaunchScope ls(c, st, F_COMBINE);
-        void* args[] = {(void*)&fb, (void*)&tm, (void*)&slot0, (void*)&n, (void*)&d_image, (void*)&d_packed};
+        int shade_from = c->shade0_separate ? 1 : 0;
+        TileMap tm = pg.tm;
+        void* args[] = {(void*)&ds, (void*)&fb, (void*)&tm, (void*)&slot0, (void*)&n, (void*)&shade_from, (void*)&d_image, (void*)&d_packed};
         CK(cudaLaunchCooperativeKernel((const void*)k_combine_resolve, dim3(c->coop_grid), dim3(256), args, 0, st));
     }
     CK(cudaGetLastError());
-    if (C_WORK + 2 * c->work_seq > C_TOTAL) return fail("internal: work counters exceed the counter block");
+    if (C_WORK + 2 * work_seq > C_TOTAL) return fail("internal: work counters exceed the counter block");
     return 0;
 }
 
@@ -389,115 +440,154 @@ void add_batch_stats(WrtContext* c, const unsigned* cnt) {
         s.rays_per_depth[d] += cnt[wrt::C_NRAYS + d] + cnt[wrt::C_NTRAYS + d];
         s.closest_rays += cnt[wrt::C_NRAYS + d] + cnt[wrt::C_NTRAYS + d];
     }
-    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
-        // requests answered without tracing count like the reference counts them (it traces them)
-        int64_t culled = cnt[wrt::C_NCULL + d], skip_p = cnt[wrt::C_NSKIP + d], skip_d = cnt[wrt::C_NDSKIP + d];
-        int64_t empty = cnt[wrt::C_NEMPTY + d];        // queued, but their candidate list came out empty: no rays built
-        int64_t p = cnt[wrt::C_NPREQ + d] + culled + skip_p, q = cnt[wrt::C_NDREQ + d] + skip_d;
-        const int64_t per = ds.shadow_type ? WRT_SOFT_SAMPLES : 1;
-        s.shadow_requests += p + q;
-        s.shadow_rays += p * per + q;
-        s.shaft_culled_requests += culled + empty;
-        s.unlit_skipped_requests += skip_p + skip_d;
-        s.shadow_rays_traced += (cnt[wrt::C_NPREQ + d] - empty) * per + cnt[wrt::C_NDREQ + d];
-    }
+    // requests answered without tracing count like the reference counts them (it traces them)
+    int64_t culled = 0, skip_p = 0, skip_d = 0;
+    for (int d = 0; d < WRT_MAX_DEPTH; d++) { culled += cnt[wrt::C_NCULL + d]; skip_p += cnt[wrt::C_NSKIP + d]; skip_d += cnt[wrt::C_NDSKIP + d]; }
+    const int64_t queued_p = (int64_t)cnt[wrt::C_NPREQ] + cnt[wrt::C_NPREQ + 1], queued_d = (int64_t)cnt[wrt::C_NDREQ] + cnt[wrt::C_NDREQ + 1];
+    const int64_t empty = cnt[wrt::C_NEMPTY];          // queued, but their candidate list came out empty: no rays built
+    const int64_t p = queued_p + culled + skip_p, q = queued_d + skip_d;
+    const int64_t per = ds.shadow_type ? WRT_SOFT_SAMPLES : 1;
+    s.shadow_requests += p + q;
+    s.shadow_rays += p * per + q;
+    s.shaft_culled_requests += culled + empty;
+    s.unlit_skipped_requests += skip_p + skip_d;
+    s.shadow_rays_traced += (queued_p - empty) * per + queued_d;
 }
 
-// Renders all local slots.  Batches that overflow a queue are re-rendered in halves.
-int render_all(WrtContext* c, cudaStream_t st, uint8_t* d_image, uint8_t* d_packed) {
+#ifdef WRT_DEBUG_BOUNDS
+int check_debug_bounds() {
+    unsigned line = 0, stack = 0;
+    CK(cudaMemcpyFromSymbol(&line, wrt::g_wrt_bounds_line, sizeof line));
+    CK(cudaMemcpyFromSymbol(&stack, wrt::g_wrt_stack_overflow, sizeof stack));
+    if (line || stack) {                                // report once, then re-arm
+        const unsigned zero = 0;
+        cudaMemcpyToSymbol(wrt::g_wrt_bounds_line, &zero, sizeof zero);
+        cudaMemcpyToSymbol(wrt::g_wrt_stack_overflow, &zero, sizeof zero);
+    }
+    if (line) return fail("WRT_DEBUG_BOUNDS: index out of bounds at kernels.cuh:" + std::to_string(line));
+    if (stack) return fail("WRT_DEBUG_BOUNDS: traversal stack overflow (sp " + std::to_string(stack - 1) + ")");
+    return 0;
+}
+#else
+int check_debug_bounds() { return 0; }
+#endif
+
+// A batch overflowed a deep-level queue.  Automatic sizing: double the deep-level capacity (kept for the following
+// frames) while it is below 2x the batch; otherwise (or with a caller-fixed factor) the batch is split in halves.
+// Returns true when the buffers grew and the same batch should simply be rendered again.
+bool grow_after_overflow(WrtContext* c) {
+    const float effective = (float)c->deep_slots / (float)std::max(1u, c->batch_slots);
+    if (c->queue_factor > 0.f || effective >= 2.f) return false;
+    const float old = c->deep_factor;
+    c->deep_factor = std::min(2.f, std::max(old, effective) * 2.f);
+    if (ensure_frame_buffers(c, c->batch_slots) == 0) return true;
+    c->deep_factor = old;                              // out of memory: fall back to halving
+    cudaGetLastError();
+    return false;
+}
+
+// Renders the spans on `todo` (popped from the back) synchronously, re-rendering what overflows.
+int render_spans_sync(WrtContext* c, std::vector<std::pair<long long, long long>>& todo, uint8_t* d_image, uint8_t* d_packed) {
+    cudaStream_t st = c->chain;
+    while (!todo.empty()) {
+        auto [s0, n] = todo.back();
+        todo.pop_back();
+        if (n <= 0) continue;
+        if (enqueue_batch(c, s0, (unsigned)n, d_image, d_packed)) return 1;
+        CK(cudaMemcpyAsync(c->h_counters, c->fb.counters, wrt::C_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (c->h_counters[wrt::C_OVERFLOW]) {
+            ++c->stats.overflow_retries;
+            if (grow_after_overflow(c)) { todo.push_back({s0, n}); continue; }
+            if (n <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
+            long long half = ((n / 2 + 31) / 32) * 32;
+            todo.push_back({s0 + half, n - half});
+            todo.push_back({s0, half});
+            continue;
+        }
+        add_batch_stats(c, c->h_counters);
+    }
+    return 0;
+}
+
+// Renders all local slots.  A single-batch frame (the common case) is enqueued without any host synchronisation;
+// overflow is checked — and the frame redone — in finish_frame.
+int render_all(WrtContext* c, cudaStream_t user, bool join_user, uint8_t* d_image, uint8_t* d_packed) {
     if (!c->has_scene) return fail("wrt_render: no scene uploaded");
     if (!c->has_cam) return fail("wrt_render: no camera set");
     if (c->cam.width <= 0 || c->cam.height <= 0) return fail("wrt_render: empty image");
     if (!c->textures_complete) return fail("wrt_render: a primitive references a texture / normal map that was not uploaded");
     const long long total = c->local_slots(c->rank, c->world);
-    const long long max_batch = 1ll << 24;
+    const long long max_batch = c->max_batch;
     memset(&c->stats, 0, sizeof c->stats);
     c->timed.clear();
     c->event_next = 0;
-    c->last_stream = st;
+    c->user_stream = user;
+    c->user_stream_joined = join_user;
+    c->last_image = d_image; c->last_packed = d_packed;
     c->has_frame = true;
-    CK(cudaEventRecord(c->ev_begin, st));
+    cudaStream_t st = c->chain;
     if (total > 0) {
         unsigned want = (unsigned)std::min(total, max_batch);
         if (ensure_frame_buffers(c, want)) return 1;
     }
-    struct Span { long long s0; long long n; };
-    std::vector<Span> todo;
+    if (join_user) {                                    // everything the caller enqueued before is visible to the frame
+        CK(cudaEventRecord(c->ev_in, user));
+        CK(cudaStreamWaitEvent(st, c->ev_in, 0));
+    }
+    CK(cudaEventRecord(c->ev_begin, st));
+    std::vector<std::pair<long long, long long>> todo;
     for (long long s0 = total; s0 > 0;) {              // push in reverse so spans pop in order
         long long b = (s0 - 1) / max_batch * max_batch;
         todo.push_back({b, s0 - b});
         s0 = b;
     }
-    const bool single = todo.size() <= 1;
-    while (!todo.empty()) {
-        Span sp = todo.back();
-        todo.pop_back();
-        if (enqueue_batch(c, st, sp.s0, (unsigned)sp.n, d_image, d_packed)) return 1;
+    if (todo.size() == 1) {                            // stay asynchronous, check in finish
+        if (enqueue_batch(c, todo[0].first, (unsigned)todo[0].second, d_image, d_packed)) return 1;
         CK(cudaMemcpyAsync(c->h_counters, c->fb.counters, wrt::C_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        if (single) {                                  // common case: stay asynchronous, check in finish
-            c->frame_pending = true;
-            CK(cudaEventRecord(c->ev_end, st));
-            return 0;
-        }
-        CK(cudaStreamSynchronize(st));
-        if (c->h_counters[wrt::C_OVERFLOW]) {
-            if (sp.n <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
-            long long half = ((sp.n / 2 + 31) / 32) * 32;
-            ++c->stats.overflow_retries;
-            todo.push_back({sp.s0 + half, sp.n - half});
-            todo.push_back({sp.s0, half});
-            continue;
-        }
-        add_batch_stats(c, c->h_counters);
-    }
+        c->frame_pending = true;
+    } else if (render_spans_sync(c, todo, d_image, d_packed)) return 1;
     CK(cudaEventRecord(c->ev_end, st));
+    if (join_user) {
+        CK(cudaEventRecord(c->ev_out, st));
+        CK(cudaStreamWaitEvent(user, c->ev_out, 0));
+    }
     return 0;
 }
 
-int finish_frame(WrtContext* c, uint8_t* d_image, uint8_t* d_packed) {
-    cudaStream_t st = c->last_stream;
+int finish_frame(WrtContext* c) {
+    cudaStream_t st = c->chain;
     CK(cudaStreamSynchronize(st));
     if (c->frame_pending) {
         c->frame_pending = false;
         if (c->h_counters[wrt::C_OVERFLOW]) {
-            // single-batch frame overflowed: redo it synchronously in halves
+            // the single-batch frame overflowed a queue: redo it synchronously (larger deep levels, or in halves)
             const long long total = c->local_slots(c->rank, c->world);
-            int retries = 1;
-            std::vector<std::pair<long long, long long>> todo;
-            long long half = ((total / 2 + 31) / 32) * 32;
-            todo.push_back({half, total - half});
-            todo.push_back({0, half});
             memset(&c->stats, 0, sizeof c->stats);
-            while (!todo.empty()) {
-                auto [s0, n] = todo.back();
-                todo.pop_back();
-                if (n <= 0) continue;
-                if (enqueue_batch(c, st, s0, (unsigned)n, d_image, d_packed)) return 1;
-                CK(cudaMemcpyAsync(c->h_counters, c->fb.counters, wrt::C_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (c->h_counters[wrt::C_OVERFLOW]) {
-                    if (n <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
-                    long long h2 = ((n / 2 + 31) / 32) * 32;
-                    ++retries;
-                    todo.push_back({s0 + h2, n - h2});
-                    todo.push_back({s0, h2});
-                    continue;
-                }
-                add_batch_stats(c, c->h_counters);
+            c->stats.overflow_retries = 1;
+            std::vector<std::pair<long long, long long>> todo;
+            if (grow_after_overflow(c)) todo.push_back({0, total});
+            else {
+                if (total <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
+                long long half = ((total / 2 + 31) / 32) * 32;
+                todo.push_back({half, total - half});
+                todo.push_back({0, half});
             }
-            c->stats.overflow_retries = retries;
+            if (render_spans_sync(c, todo, c->last_image, c->last_packed)) return 1;
             CK(cudaEventRecord(c->ev_end, st));
             CK(cudaStreamSynchronize(st));
         } else {
             add_batch_stats(c, c->h_counters);
         }
     }
+    if (check_debug_bounds()) return 1;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) c->stats.gpu_ms = ms;
     for (float& f : c->family_ms) f = 0.f;
+    for (int& n : c->family_launches) n = 0;
     for (const TimedLaunch& tl : c->timed) {
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, tl.e0, tl.e1) == cudaSuccess) c->family_ms[tl.family] += t;
+        if (cudaEventElapsedTime(&t, tl.e0, tl.e1) == cudaSuccess) { c->family_ms[tl.family] += t; ++c->family_launches[tl.family]; }
     }
     return 0;
 }
@@ -526,13 +616,13 @@ int wrt_create(int device, WrtContext** out) {
     WrtContext* c = new WrtContext();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    bool ev_ok = true;
-    for (int k = 0; k < WRT_SIDE_STREAMS && ev_ok; k++)
-        ev_ok = cudaStreamCreateWithFlags(&c->side_stream[k], cudaStreamNonBlocking) == cudaSuccess;
-    for (int d = 0; d < WRT_MAX_DEPTH && ev_ok; d++)
-        ev_ok = cudaEventCreateWithFlags(&c->ev_surface[d], cudaEventDisableTiming) == cudaSuccess &&
-                cudaEventCreateWithFlags(&c->ev_shade[d], cudaEventDisableTiming) == cudaSuccess;
-    if (!ev_ok || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    bool ev_ok = cudaStreamCreateWithPriority(&c->chain, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+                 cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_least) == cudaSuccess;
+    for (cudaEvent_t* e : {&c->ev_in, &c->ev_lvl0, &c->ev_side, &c->ev_out})
+        ev_ok = ev_ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok ||
         cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_counters, wrt::C_TOTAL * sizeof(unsigned)) != cudaSuccess) {
         delete c;
@@ -556,12 +646,15 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_SHAFT_CULL")) c->shaft_cull = atoi(e) != 0;
     if (const char* e = getenv("WRT_UNLIT_CULL")) c->unlit_cull = atoi(e) != 0;
     if (const char* e = getenv("WRT_SOFT_LISTS")) c->soft_lists = atoi(e) != 0;
-    if (const char* e = getenv("WRT_LISTS_FROM")) c->lists_from_level = atoi(e);
     if (const char* e = getenv("WRT_LIST_POOL_CAP")) c->list_pool_cap_override = atoll(e);
     if (const char* e = getenv("WRT_SHAFT_LEVELS")) c->shaft_cull_max_level = atoi(e);
     if (const char* e = getenv("WRT_CHUNK_DIV")) c->chunk_div = std::max(0, std::min(255, atoi(e)));
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
-    if (const char* e = getenv("WRT_SMEM_ROWS")) c->smem_rows_cap = std::max(2, std::min(64, atoi(e)));
+    if (const char* e = getenv("WRT_FUSED_BLOCKS")) c->fused_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("WRT_FUSE_FROM")) c->fuse_from = atoi(e);
+    if (const char* e = getenv("WRT_SHADE0_SEPARATE")) c->shade0_separate = atoi(e) != 0;
+    if (const char* e = getenv("WRT_DEEP_FACTOR")) { c->deep_factor = std::max(0.001f, std::min(2.f, (float)atof(e))); c->small_batch_full_levels = false; }
+    if (const char* e = getenv("WRT_MAX_BATCH")) c->max_batch = std::max(64ll, (atoll(e) + 31) / 32 * 32);   // tests: force multi-batch frames
     *out = c;
     return 0;
 }
@@ -579,12 +672,9 @@ void wrt_destroy(WrtContext* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
-    for (int d = 0; d < WRT_MAX_DEPTH; d++) {
-        if (c->ev_surface[d]) cudaEventDestroy(c->ev_surface[d]);
-        if (c->ev_shade[d]) cudaEventDestroy(c->ev_shade[d]);
-    }
-    for (int k = 0; k < WRT_SIDE_STREAMS; k++) if (c->side_stream[k]) cudaStreamDestroy(c->side_stream[k]);
-    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (cudaEvent_t e : {c->ev_in, c->ev_lvl0, c->ev_side, c->ev_out}) if (e) cudaEventDestroy(e);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->chain) cudaStreamDestroy(c->chain);
     delete c;
 }
 
@@ -682,9 +772,12 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     ds.amin = s->amin; ds.amax = s->amax; ds.distmin = s->distmin; ds.distmax = s->distmax;
     c->bvh_depth = tree_depth(s);
     c->stack_rows = std::max(c->bvh_depth, fbvh.max_depth) + 2;
+#ifdef WRT_DEBUG_BOUNDS
+    if (const char* e = getenv("WRT_DEBUG_STACK_ROWS")) c->stack_rows = std::max(1, atoi(e));   // provoke the stack check (tests)
+#endif
     if (c->stack_rows > 90)     // 90 rows x 128 threads x 4 B = 45 KB of dynamic shared memory per CTA
         return fail("wrt_upload_scene: acceleration tree deeper than 88 levels (degenerate geometry?)");
-    CK(cudaStreamSynchronize(c->own_stream));          // host staging vectors go out of scope here
+    CK(cudaStreamSynchronize(c->chain));          // host staging vectors go out of scope here
     c->has_scene = true;
     if (getenv("WRT_VERBOSE"))
         fprintf(stderr, "[wrt] upload: %d prims, reference tree depth %d, SAH tree depth %d (built in %.2f ms)\n", np,
@@ -714,7 +807,7 @@ int wrt_set_options(WrtContext* c, int traversal, uint32_t seed, float queue_fac
     c->traversal = traversal;
     c->seed = seed;
     if (queue_factor > 0 && queue_factor != c->queue_factor) {
-        c->queue_factor = queue_factor;
+        c->queue_factor = queue_factor;                // caller-fixed deep-level capacity: no automatic growth
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
         free_frame(c);
@@ -741,7 +834,7 @@ static int batch_common(WrtContext* c, int64_t n) {
 int wrt_trace_closest(WrtContext* c, const float* orig, const float* dir, int64_t n, WrtHit* hits) {
     if (batch_common(c, n)) return 1;
     if (n == 0) return 0;
-    cudaStream_t st = c->own_stream;
+    cudaStream_t st = c->chain;
     size_t vb = (size_t)n * 3 * sizeof(float);
     if (ensure_scratch(c, 0, vb) || ensure_scratch(c, 1, vb) || ensure_scratch(c, 2, (size_t)n * sizeof(WrtHit))) return 1;
     CK(cudaMemcpyAsync(c->d_scratch[0], orig, vb, cudaMemcpyHostToDevice, st));
@@ -761,7 +854,7 @@ static int batch_shadow(WrtContext* c, const float* pos, const float* ndir, cons
                         float* coeff, int mode) {
     if (batch_common(c, n)) return 1;
     if (n == 0) return 0;
-    cudaStream_t st = c->own_stream;
+    cudaStream_t st = c->chain;
     size_t vb = (size_t)n * 3 * sizeof(float);
     for (int k = 0; k < 3; k++) if (ensure_scratch(c, k, std::max(vb, c->scratch_bytes[k]))) return 1;
     if (ensure_scratch(c, 3, (size_t)n * sizeof(float))) return 1;
@@ -792,7 +885,7 @@ int wrt_shadow_directional(WrtContext* c, const float* pos, const int32_t* self_
                            int64_t n, float* coeff) {
     if (batch_common(c, n)) return 1;
     if (n == 0) return 0;
-    cudaStream_t st = c->own_stream;
+    cudaStream_t st = c->chain;
     if (ensure_scratch(c, 0, (size_t)n * 12) || ensure_scratch(c, 1, (size_t)n * 4) ||
         ensure_scratch(c, 2, (size_t)n * 16) || ensure_scratch(c, 3, (size_t)n * 4))
         return 1;
@@ -830,10 +923,10 @@ int wrt_render(WrtContext* c, uint8_t* rgb_host, WrtStats* stats) {
         CK(cudaMallocHost((void**)&c->h_image, bytes));
         c->h_image_bytes = bytes;
     }
-    cudaStream_t st = c->own_stream;
+    cudaStream_t st = c->chain;
     if (c->world > 1) CK(cudaMemsetAsync(c->d_image, 0, bytes, st));
-    if (render_all(c, st, c->d_image, nullptr)) return 1;
-    if (finish_frame(c, c->d_image, nullptr)) return 1;
+    if (render_all(c, nullptr, false, c->d_image, nullptr)) return 1;
+    if (finish_frame(c)) return 1;
     cudaPointerAttributes attr;
     bool user_pinned = c->world == 1 && cudaPointerGetAttributes(&attr, rgb_host) == cudaSuccess &&
                        attr.type == cudaMemoryTypeHost;
@@ -867,19 +960,17 @@ int wrt_render_device(WrtContext* c, void* d_rgb_tiles, void* cuda_stream) {
     if (!c || !d_rgb_tiles) return fail("wrt_render_device: null argument");
     CK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;        // NULL = the legacy default stream, as in CUDA
-    return render_all(c, st, nullptr, (uint8_t*)d_rgb_tiles);
+    return render_all(c, st, true, nullptr, (uint8_t*)d_rgb_tiles);
 }
 
 int wrt_finish_device(WrtContext* c, WrtStats* stats) {
     if (!c) return fail("wrt_finish_device: null context");
     CK(cudaSetDevice(c->device));
     if (!c->has_frame) return fail("wrt_finish_device: no frame in flight");
-    // the packed pointer is only needed again if an overflowed frame must be re-rendered
-    if (c->frame_pending && c->h_counters) {
-        CK(cudaStreamSynchronize(c->last_stream));
-        if (c->h_counters[wrt::C_OVERFLOW]) return fail("ray queue overflow in wrt_render_device: raise queue_factor via wrt_set_options");
-    }
-    if (finish_frame(c, nullptr, nullptr)) return 1;
+    // A frame that overflowed a queue is re-rendered here (synchronously, into the same device buffer): when
+    // stats->overflow_retries != 0 the caller must repeat whatever it had already enqueued behind the frame on
+    // its own stream (parallel.py: the gather).
+    if (finish_frame(c)) return 1;
     if (stats) *stats = c->stats;
     return 0;
 }
@@ -917,7 +1008,7 @@ int64_t wrt_kernel_launch_count(WrtContext* c) { return c ? c->launches : 0; }
 int wrt_measure_fp32_peak(WrtContext* c, float* tflops_fma, float* tflops_mul_add) {
     if (!c || !tflops_fma || !tflops_mul_add) return fail("wrt_measure_fp32_peak: null argument");
     CK(cudaSetDevice(c->device));
-    cudaStream_t st = c->own_stream;
+    cudaStream_t st = c->chain;
     if (ensure_scratch(c, 4, 256)) return 1;
     const int iters = 1 << 15, blocks = c->num_sms * 8, threads = 256;
     cudaEvent_t e0, e1;
@@ -948,6 +1039,13 @@ int wrt_get_kernel_times(WrtContext* c, float* ms, int capacity) {
     if (!c || !ms) return 0;
     int n = std::min(capacity, (int)WRT_KERNEL_FAMILIES);
     for (int i = 0; i < n; i++) ms[i] = c->family_ms[i];
+    return n;
+}
+
+int wrt_get_kernel_launches(WrtContext* c, int32_t* launches, int capacity) {
+    if (!c || !launches) return 0;
+    int n = std::min(capacity, (int)WRT_KERNEL_FAMILIES);
+    for (int i = 0; i < n; i++) launches[i] = c->family_launches[i];
     return n;
 }
 

@@ -297,6 +297,51 @@ def write_config(workdir: os.PathLike | str, name: str, text: str) -> Path:
     return p
 
 
+# ---- the rarely used branches "at speed" (4K bench workloads) ----
+
+def f4_directional_config(w: int = 3840, h: int = 2160, soft: bool = False) -> str:
+    """The textured-wall bunny scene lit by a point light AND a directional light (w = 0): every shaded hit runs the
+    box-free directional shadow loop of Renderer.hpp:381-400 over 4970 objects."""
+    return water_bunny_tex_config(w, h, soft).replace("light -20 70 20 1 1 1 1",
+                                                      "light -20 70 20 1 1 1 1\nlight 0.3 -1 -0.4 0 0.9 0.9 0.8")
+
+
+def f4_bump_config(w: int = 3840, h: int = 2160, soft: bool = False) -> str:
+    """The same scene with a normal map on both wall triangles (changeNormalDir, Renderer.hpp:417-474, on ~90 % of
+    the primary hits; `bump` is one-shot, so it is repeated per face)."""
+    t = water_bunny_tex_config(w, h, soft)
+    return t.replace("texture textures/harbor.ppm\nf 1/1 2/2 3/3\nf 1/1 4/4 2/2",
+                     "texture textures/harbor.ppm\nbump textures/bumps.ppm\nf 1/1 2/2 3/3\nbump textures/bumps.ppm\nf 1/1 4/4 2/2")
+
+
+def f4_spheres_config(w: int = 3840, h: int = 2160, soft: bool = False) -> str:
+    """1024 spheres (Sphere::intersect, Sphere.hpp:25-120, with its double-precision `C`) over a floor: a quarter
+    glass, a quarter mirror-ish, a quarter textured; one plain and one attenuated point light; no bunny."""
+    rng = np.random.default_rng(1024)
+    lines = [f"imsize {w} {h}", "eye 0 6 16", "viewdir 0 -0.35 -1", "hfov 60", "updir 0 1 0", "bkgcolor 0.25 0.35 0.55 1.0",
+             "light 12 30 14 1 0.8 0.8 0.8", "attlight -10 14 6 1 0.6 0.6 0.5 0.6 0.01 0.0005"]
+    if soft:
+        lines.append("shadow soft")
+    mats = ["mtlcolor 0.8 0.3 0.2 1 1 1 0.2 0.7 0.3 32 1 1.0",
+            "mtlcolor 0.9 0.95 1.0 1 1 1 0.05 0.2 0.4 60 0.25 1.45",
+            "mtlcolor 0.7 0.7 0.75 1 1 1 0.1 0.4 0.7 80 1 1.0",
+            "mtlcolor 0.6 0.6 0.6 1 1 1 0.2 0.8 0.2 20 1 1.0\ntexture textures/harbor.ppm"]
+    k = 0
+    for gy in range(32):
+        for gx in range(32):
+            if k % 256 == 0:
+                lines.append(mats[k // 256])
+            r = 0.22 + 0.16 * rng.random()
+            x = (gx - 15.5) * 0.95 + 0.25 * (rng.random() - 0.5)
+            z = -(gy * 0.95) + 4 + 0.25 * (rng.random() - 0.5)
+            y = r - 1.0 + (1.2 * rng.random() if rng.random() < 0.3 else 0.0)
+            lines.append("sphere %.4f %.4f %.4f %.4f" % (x, y, z, r))
+            k += 1
+    lines += ["mtlcolor 0.5 0.55 0.5 1 1 1 0.3 0.7 0.1 10 1 1.0", "v -40 -1 20", "v 40 -1 20", "v 40 -1 -60", "v -40 -1 -60",
+              "f 1 2 3", "f 1 3 4"]
+    return "\n".join(lines) + "\n"
+
+
 # BASELINE.json `configs`, in order.  (name, config text builder kwargs, uses bunny, soft)
 BENCH_CONFIGS = {
     "config": dict(builder=bunny_shadow_config, w=800, h=600, soft=False),
@@ -304,6 +349,10 @@ BENCH_CONFIGS = {
     "gla_bunny_tex_4k": dict(builder=water_bunny_tex_config, w=3840, h=2160, soft=False),
     "water_bunny_tex_soft_4k": dict(builder=water_bunny_tex_config, w=3840, h=2160, soft=True),
     "glass_bunny_soft_8k": dict(builder=water_bunny_tex_config, w=7680, h=4320, soft=True, glass=True),
+    # SURVEY.md section 8 f4 (not BASELINE configs): directional light / normal maps / spheres at 4K
+    "f4_directional_4k": dict(builder=f4_directional_config, w=3840, h=2160, soft=False),
+    "f4_bump_4k": dict(builder=f4_bump_config, w=3840, h=2160, soft=False),
+    "f4_spheres_1k_4k": dict(builder=f4_spheres_config, w=3840, h=2160, soft=False, bunny=False),
 }
 
 

@@ -98,13 +98,28 @@ class DistributedRenderer:
         self.renderer.render_device(self.packed.data_ptr(), stream)
         if self.render_done is not None:
             self.render_done.record()                  # this rank's own tiles are finished here
+        self._gather_scatter(stream)
+        return self.image
+
+    def _gather_scatter(self, stream):
         g = self.tg.gather(self.packed, self.gathered)
         if self.rank == 0:
             self.renderer.scatter_tiles(g.data_ptr(), self.world, self.tg.stride, self.image.data_ptr(), stream)
-        return self.image
 
     def finish(self) -> dict:
-        return self.renderer.finish_device()
+        """Waits for this rank's frame.  A rank whose frame overflowed a ray queue has re-rendered it inside
+        finish_device() — after frame() had already gathered its incomplete tiles — so the ranks agree (one flag
+        all-reduce, N > 1 only) on whether the gather + scatter must be repeated."""
+        stats = self.renderer.finish_device()
+        if self.world > 1:
+            import torch.distributed as dist
+            flag = self.torch.tensor([1 if stats["overflow_retries"] else 0], dtype=self.torch.int32,
+                                     device=self.packed.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()):
+                self._gather_scatter(self.torch.cuda.current_stream().cuda_stream)
+                self.torch.cuda.current_stream().synchronize()
+        return stats
 
     def close(self):
         self.renderer.ctx.close()

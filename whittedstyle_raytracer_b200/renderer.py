@@ -97,6 +97,11 @@ class Context:
         n = self.lib.wrt_get_kernel_times(self.h, ms, len(KERNEL_FAMILIES))
         return {KERNEL_FAMILIES[i]: float(ms[i]) for i in range(n)}
 
+    def kernel_launches(self) -> dict:
+        n = (C.c_int32 * len(KERNEL_FAMILIES))()
+        k = self.lib.wrt_get_kernel_launches(self.h, n, len(KERNEL_FAMILIES))
+        return {KERNEL_FAMILIES[i]: int(n[i]) for i in range(k)}
+
     def measure_fp32_peak(self) -> tuple[float, float]:
         """(TFLOP/s with FFMA, TFLOP/s with separate FMUL+FADD) measured on this GPU."""
         a, b = C.c_float(0), C.c_float(0)

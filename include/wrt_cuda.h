@@ -122,6 +122,22 @@ int wrt_get_kernel_times(WrtContext* ctx, float* ms, int capacity);
 /* Launches per family behind those times (same order). */
 int wrt_get_kernel_launches(WrtContext* ctx, int32_t* launches, int capacity);
 
+/* ---- multi-GPU in one process: `Renderer::render()` over n GPUs (what `wrt --gpus n` uses) ----
+ * The scene is replicated, the image is sharded as interleaved tiles (wrt_tiles.h), one host thread drives each GPU.
+ * With peer access (NVLink / NVSwitch) there is no gather step: every GPU's resolve kernel stores its 8-bit pixels
+ * straight into device devices[0]'s frame, which is then copied to rgb_host.  The image is identical to the 1-GPU
+ * image (every pixel is independent; the soft-shadow RNG is keyed on the global pixel). */
+typedef struct WrtMulti WrtMulti;
+int  wrt_multi_create(const int* devices, int n, WrtMulti** out);
+void wrt_multi_destroy(WrtMulti* m);
+int  wrt_multi_device_count(WrtMulti* m);
+WrtContext* wrt_multi_context(WrtMulti* m, int rank);      /* rank's own context (options, timing, batch queries) */
+int  wrt_multi_uses_peer_stores(WrtMulti* m);              /* 1: pixels cross NVLink from the resolve kernels; 0: copy + scatter */
+int  wrt_multi_upload_scene(WrtMulti* m, const WrtSceneDesc* scene);
+int  wrt_multi_set_camera(WrtMulti* m, const WrtCamera* cam);
+int  wrt_multi_set_options(WrtMulti* m, int traversal, uint32_t seed, float queue_factor);
+int  wrt_multi_render(WrtMulti* m, uint8_t* rgb_host, WrtStats* stats);   /* stats: sums over the GPUs, gpu_ms = slowest GPU */
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ import pytest
 
 import oracle_bindings as ob
 from conftest import GOLD, IMG_SCENES, RAY_SCENES, SOFT_SCENES, REPO, image_diff, load_golden_scene, psnr, ulp_diff
-from whittedstyle_raytracer_b200 import Renderer, Scene, fixtures, read_ppm_p3
+from whittedstyle_raytracer_b200 import MultiRenderer, Renderer, Scene, fixtures, read_ppm_p3
 from whittedstyle_raytracer_b200.renderer import TRAVERSAL_EXHAUSTIVE, TRAVERSAL_PRUNED
 
 pytestmark = pytest.mark.gpu
@@ -613,3 +613,121 @@ def test_soft_shadow_list_path_corner_cases(workdir, monkeypatch, name, text):
     plain, _ = gpu_render(scene)
     monkeypatch.delenv("WRT_SOFT_LISTS")
     assert np.array_equal(plain, img)
+
+
+# ---------------- device BVH build, re-upload, multi-GPU contexts ----------------
+
+@pytest.mark.parametrize("name", ["water_small", "spheres", "bump"])
+def test_device_built_tree_equals_host_built_tree_in_every_result(workdir, monkeypatch, name):
+    """The kernels walk a tree built on the device (PLOC, csrc/cuda/bvh_build.cuh).  Results do not depend on the
+    topology: with WRT_HOST_BVH=1 (the host's binned-SAH tree) image, ray counts and every strategy
+    query are bit-identical."""
+    scene, _ = load_golden_scene(workdir, name)
+    g = np.load(GOLD / f"rays_{name}.npz")
+    out = {}
+    for host in ("0", "1"):
+        monkeypatch.setenv("WRT_HOST_BVH", host)
+        r = Renderer(scene)
+        img = r.render().copy()
+        h = r.interStrategy.UpdateInter(g["orig"], g["dir"])
+        hard = r.interStrategy.getShadowCoeffi(g["sh_pos"], g["sh_ndir"], g["sh_light"])
+        dirc = r.interStrategy.getDirectionalShadowCoeffi(g["sh_pos"], g["sh_self"], g["sh_ldir"])
+        out[host] = (img, dict(r.last_stats), h, hard, dirc)
+        r.ctx.close()
+    monkeypatch.delenv("WRT_HOST_BVH")
+    a, b = out["0"], out["1"]
+    assert np.array_equal(a[0], b[0])
+    for k in ("closest_rays", "shadow_rays", "rays_per_depth", "shadow_requests"):
+        assert a[1][k] == b[1][k], k
+    assert a[2].tobytes() == b[2].tobytes()
+    assert np.array_equal(a[4], b[4])
+    assert ulp_diff(a[3], b[3]).max() <= 4               # product order follows the walked tree (DESIGN.md section 3)
+
+
+def test_scene_reupload_switches_scenes_without_residue(workdir):
+    """wrt_upload_scene on a live context: a larger scene, a smaller one, the first again — each frame equals the frame
+    of a fresh context (device arrays are reused or regrown, the tree is rebuilt on the device every time)."""
+    names = ["water_small", "spheres", "config_small", "water_small"]
+    scenes = {n: load_golden_scene(workdir, n)[0] for n in set(names)}
+    fresh = {n: gpu_render(sc)[0] for n, sc in scenes.items()}
+    r = Renderer(scenes[names[0]])
+    for n in names:
+        r.ctx.upload_scene(scenes[n])
+        r.scene = scenes[n]
+        assert np.array_equal(r.render(), fresh[n]), n
+    r.ctx.close()
+
+
+def test_malformed_scene_descriptions_are_rejected(workdir):
+    """Indices in a hand-filled WrtSceneDesc are validated at upload: material / leaf / child links."""
+    import ctypes as C
+    from whittedstyle_raytracer_b200 import cabi
+    from whittedstyle_raytracer_b200.renderer import Context, CudaError
+    scene, _ = load_golden_scene(workdir, "spheres")
+    ctx = Context()
+    d = cabi.WrtSceneDesc.from_buffer_copy(scene.desc)
+
+    def upload_bad(field, idx, value, match):
+        arr = getattr(scene.desc, field)
+        n = scene.desc.n_nodes if field == "nodes" else scene.desc.n_prims
+        copy = (arr._type_ * n)(*[arr[i] for i in range(n)])
+        if field == "nodes":
+            copy[idx].link = value
+        else:
+            copy[idx] = value
+        bad = cabi.WrtSceneDesc.from_buffer_copy(d)
+        setattr(bad, field, C.cast(copy, type(arr)))
+        with pytest.raises(CudaError, match=match):
+            ctx._check(ctx.lib.wrt_upload_scene(ctx.h, C.byref(bad)))
+
+    upload_bad("prim_material", 3, 10_000, "material index")
+    leaf = next(i for i in range(2, scene.desc.n_nodes) if scene.desc.nodes[i].link < 0)
+    upload_bad("nodes", leaf, ~(scene.desc.n_prims + 5), "leaf link")
+    inner = next(i for i in range(2, scene.desc.n_nodes) if scene.desc.nodes[i].link >= 0)
+    upload_bad("nodes", inner, scene.desc.n_nodes + 7, "child link")
+    ctx.upload_scene(scene)                              # and the context is still usable
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
+def test_multi_gpu_contexts_in_one_process(workdir, monkeypatch, n_gpus):
+    """wrt_multi_* (what `wrt --gpus N` uses): N contexts on N host threads, interleaved tiles, pixels stored straight
+    into GPU 0's frame over NVLink — image and ray counts equal the single-GPU frame's; likewise through the
+    copy + scatter path (WRT_MULTI_NO_PEER) and for soft shadows."""
+    import torch
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    for kind, name in (("img", "water_small"), ("soft", "water_soft")):
+        scene, _ = load_golden_scene(workdir, name, kind=kind)
+        full, st_full = gpu_render(scene)
+        for no_peer in (False, True):
+            if no_peer:
+                monkeypatch.setenv("WRT_MULTI_NO_PEER", "1")
+            m = MultiRenderer(scene, list(range(n_gpus)))
+            assert m.uses_peer_stores == (not no_peer)
+            img = m.render()
+            st = m.last_stats
+            again = m.render()
+            m.close()
+            if no_peer:
+                monkeypatch.delenv("WRT_MULTI_NO_PEER")
+            assert np.array_equal(img, full) and np.array_equal(again, full), (name, n_gpus, no_peer)
+            for k in ("closest_rays", "shadow_rays", "rays_per_depth", "shadow_requests"):
+                assert st[k] == st_full[k], k
+
+
+def test_drop_in_executable_on_several_gpus(workdir):
+    """`wrt --gpus N config.txt` writes byte for byte the PPM of the 1-GPU run."""
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = REPO / "whittedstyle_raytracer_b200" / "wrt"
+    fixtures.write_config(workdir, "cli_multi", fixtures.water_bunny_tex_config(320, 200, soft=True))
+    out = []
+    for args in ([], ["--gpus", str(n)]):
+        p = subprocess.run([str(exe), "cli_multi.txt"] + args, cwd=workdir, capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout + p.stderr
+        out.append((workdir / "cli_multi.ppm").read_bytes())
+        (workdir / "cli_multi.ppm").unlink()
+    assert out[0] == out[1]

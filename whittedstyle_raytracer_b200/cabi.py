@@ -91,6 +91,8 @@ CUDA_SYMBOLS = [
     "wrt_set_options", "wrt_enable_kernel_timing", "wrt_trace_closest", "wrt_shadow_hard", "wrt_shadow_soft", "wrt_shadow_directional",
     "wrt_render", "wrt_render_device", "wrt_finish_device", "wrt_get_stats", "wrt_tile_pixel_count",
     "wrt_scatter_tiles", "wrt_kernel_launch_count", "wrt_get_kernel_times", "wrt_get_kernel_launches", "wrt_measure_fp32_peak",
+    "wrt_multi_create", "wrt_multi_destroy", "wrt_multi_device_count", "wrt_multi_context", "wrt_multi_uses_peer_stores",
+    "wrt_multi_upload_scene", "wrt_multi_set_camera", "wrt_multi_set_options", "wrt_multi_render",
 ]
 
 _host = None
@@ -166,5 +168,16 @@ def load_cuda() -> C.CDLL:
         lib.wrt_kernel_launch_count.restype = i64
         lib.wrt_get_kernel_times.argtypes = [vp, vp, i32]
         lib.wrt_get_kernel_launches.argtypes = [vp, vp, i32]
+        lib.wrt_multi_create.argtypes = [C.POINTER(C.c_int), i32, C.POINTER(vp)]
+        lib.wrt_multi_destroy.argtypes = [vp]
+        lib.wrt_multi_destroy.restype = None
+        lib.wrt_multi_device_count.argtypes = [vp]
+        lib.wrt_multi_context.argtypes = [vp, i32]
+        lib.wrt_multi_context.restype = vp
+        lib.wrt_multi_uses_peer_stores.argtypes = [vp]
+        lib.wrt_multi_upload_scene.argtypes = [vp, C.POINTER(WrtSceneDesc)]
+        lib.wrt_multi_set_camera.argtypes = [vp, C.POINTER(WrtCamera)]
+        lib.wrt_multi_set_options.argtypes = [vp, i32, u32, C.c_float]
+        lib.wrt_multi_render.argtypes = [vp, vp, C.POINTER(WrtStats)]
         _cuda = lib
     return _cuda

@@ -432,9 +432,6 @@ __device__ __forceinline__ float directional_product_bvh(const DevScene& s, cons
 //             bool step(cur, st)         — one traversal step; false = finished
 //             bool finish(cur, st)       — a walk ended: write results, or start the item's next
 //                                          walk and return true
-//             Q::RETIRES, pending(), retire() — optional second stage: a lane whose walk ended keeps its result
-//                                          (pending() == true) until the warp, converged at its next refill, calls
-//                                          retire() on ALL lanes at once (warp-aggregated appends need the whole warp).
 #ifndef WRT_CHUNK_MIN_PER
 #define WRT_CHUNK_MIN_PER 256
 #endif
@@ -461,15 +458,8 @@ __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned l
     int cur = 0;
     while (true) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        bool service;
-        if (!drained) service = idle == 0xffffffffu || __popc(idle) >= refill;
-        else if (Q::RETIRES) {                          // nothing left to claim: only finished lanes to retire
-            const unsigned pend = __ballot_sync(0xffffffffu, q.pending());
-            service = pend != 0u && (idle == 0xffffffffu || __popc(pend) >= refill);
-        } else service = false;
-        if (service) {
-            if (Q::RETIRES) q.retire();
-            if (!drained) {
+        if (!drained && (idle == 0xffffffffu || __popc(idle) >= refill)) {
+            {
                 unsigned cnt = __popc(idle);
                 unsigned long long avail = loc_end - loc_next;
                 unsigned long long first = loc_next, second = 0;   // items [first, first+avail) then [second, ...)
@@ -497,9 +487,8 @@ __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned l
                 if (loc_next >= n) drained = true;
             }
             if (!__any_sync(0xffffffffu, active)) {
-                if (!drained) continue;
-                if (Q::RETIRES && __any_sync(0xffffffffu, q.pending())) q.retire();   // items resolved inside begin()
-                break;
+                if (drained) break;
+                continue;
             }
         } else if (idle == 0xffffffffu) {
             break;                                   // drained and nothing in flight

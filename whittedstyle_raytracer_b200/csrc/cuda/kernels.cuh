@@ -1,17 +1,20 @@
 // kernels.cuh — the wavefront kernels (sm_100a, SIMT FP32; tensor cores unused:
 // the path is divergent traversal, not a dense contraction).
 //
-// One frame (Renderer.hpp:57-137), 15 launches for a soft-shadow frame:
-//   main stream   k_trace_surface<0>        primary rays (generated in registers, Renderer.hpp:104-125) -> closest hit ->
-//                                           surface: hit completion, texture, normal map, Fresnel, child rays of level 1,
-//                                           shadow requests into queue 0
-//                 k_trace_surface<d> x 8    levels 1..8 (Renderer.hpp:25 MAX_DEPTH 9): rays[d] -> closest hit -> surface ->
-//                                           rays[d+1], shadow requests of ALL deep levels into ONE queue (queue 1)
-//                 k_soft_lists(1), k_soft_list_rays(1)   (or k_shadow_hard(1) / k_shadow_directional(1))
+// One frame (Renderer.hpp:57-137), 25 launches for a soft-shadow frame:
+//   chain stream  for each ray-tree level d = 0..8 (Renderer.hpp:25 MAX_DEPTH 9)
+//                   k_trace_closest   rays[d] -> hits (level 0: primary rays generated in registers, Renderer.hpp:104-125)
+//                   k_surface_spawn   hits -> surface records, child rays[d+1], shadow requests: level 0 into queue 0, ALL
+//                                     deeper levels into ONE queue (queue 1)
+//                 k_soft_lists(1), k_soft_list_rays(1)   (or k_shadow_hard(1); + k_shadow_directional(1))
 //   side stream   k_soft_lists(0), k_soft_list_rays(0), k_shade(level 0)   beside the deep chain
-//   main stream   k_combine_resolve         shades the deep nodes, then colour = local + fr*R + (1-fr)(1-alpha)*T bottom-up in
+//   chain stream  k_combine_resolve         shades the deep nodes, then colour = local + fr*R + (1-fr)(1-alpha)*T bottom-up in
 //                                           the reference's own association (Renderer.hpp:259) and int(255*min(c,1))
 //                                           (Renderer.hpp:128-130); one cooperative launch.
+// (Fusing the surface stage into the closest-hit kernel — finished lanes keep their hit and the warp runs the surface code
+// at its next refill — was built and measured: 21.0 vs 18.0 ms per frame.  The surface code wants ~100 registers; under
+// the 64 the traversal needs for its occupancy, ptxas spills the ray's 1/d and the node pointer inside the hot loop
+// (profiles/NOTES.md).)
 // The only dependent chain is the 9 closest-hit launches; the shadow work of the deep levels — independent of the
 // chain — is not cut into 8 per-level launches with 8 tails, and level 0's shadow work fills the SMs the short deep
 // levels leave idle.
@@ -33,13 +36,6 @@
 #else
 #define WRT_TRACE_BOUNDS __launch_bounds__(128)
 #endif
-// The fused closest-hit + surface kernel: the surface code alone wants ~80 registers; the traversal loop, where the
-// time goes, wants ~60.  The bound keeps 8 CTAs per SM; what spills is surface-side state.
-#ifndef WRT_FUSED_MIN_BLOCKS
-#define WRT_FUSED_MIN_BLOCKS 8
-#endif
-#define WRT_FUSED_BOUNDS __launch_bounds__(128, WRT_FUSED_MIN_BLOCKS)
-
 namespace wrt {
 
 // ---- debug build (-DWRT_DEBUG_BOUNDS): every queue / pool / stack / node index is checked before the access; the first
@@ -328,46 +324,36 @@ __device__ __forceinline__ void surface_warp(const DevScene& s, const FrameBuffe
 }
 
 // ---- K2: closest hit; persistent warps, per-lane refill (dev_traverse.cuh run_queue) ----
-// FUSED: the lane keeps its finished hit in registers and the warp runs surface_warp() for all finished lanes together at
-// the next refill (run_queue's retire hook) — no hit record, no second pass over the rays, one launch per level.
-template <bool LEVEL0, bool FUSED>
+template <bool LEVEL0>
 struct ClosestQuery {
-    static constexpr bool RETIRES = FUSED;
     const DevScene& s;
     const FrameBuffers& fb;
     const PrimaryGen& pg;
     const float4* ray_o;
     const float4* ray_d;
     float prune_cfg;
-    int level, cull;
     // per-lane state
     Ray r;
     ClosestState cs;
     const float4* nodes;
-    unsigned idx, pixel, path;
-    bool has_result;
-    unsigned valid;                      // level 0: non-padding primary rays this lane retired
+    unsigned idx;
     LevelSpan span;
-    __device__ __forceinline__ ClosestQuery(const DevScene& s_, const FrameBuffers& fb_, const PrimaryGen& pg_, int level_,
-                                            unsigned n0, float prune, int cull_)
-        : s(s_), fb(fb_), pg(pg_), ray_o(fb_.ray_o[level_ & 1]), ray_d(fb_.ray_d[level_ & 1]), prune_cfg(prune), level(level_),
-          cull(cull_), has_result(false), valid(0), span(level_span(fb_, level_, n0)) {}
+    __device__ __forceinline__ ClosestQuery(const DevScene& s_, const FrameBuffers& fb_, const PrimaryGen& pg_, int level,
+                                            unsigned n0, float prune)
+        : s(s_), fb(fb_), pg(pg_), ray_o(fb_.ray_o[level & 1]), ray_d(fb_.ray_d[level & 1]), prune_cfg(prune),
+          span(level_span(fb_, level, n0)) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
         idx = span.slot((unsigned)item);
         f3 o, d;
         cs.reset(prune_cfg);
         if (LEVEL0) {
-            path = 1u;
-            const bool ok = primary_ray(pg, (unsigned)item, o, d, pixel);
-            r = make_ray(o, d);
-            if (!ok) { cs.best.prim = -2; return false; }                                   // padding slot
+            unsigned pixel;
+            if (!primary_ray(pg, (unsigned)item, o, d, pixel)) { cs.best.prim = -2; return false; }     // padding slot
         } else {
-            float4 o4 = ray_o[idx], d4 = ray_d[idx];
-            o = mk3(o4); d = mk3(d4);
-            pixel = __float_as_uint(o4.w); path = __float_as_uint(d4.w);
-            r = make_ray(o, d);
+            o = mk3(ray_o[idx]); d = mk3(ray_d[idx]);
         }
         if (s.n_nodes == 0) return false;
+        r = make_ray(o, d);
         float prune = prune_cfg;
         const bool ref_tree = prune < 0.f || degenerate_dir(r.d);       // literal walk / axis-degenerate ray
         if (ref_tree) prune = -1.f;
@@ -384,39 +370,12 @@ struct ClosestQuery {
         return traverse_step<true, true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
-        if (FUSED) has_result = true;
-        else if (WRT_IN_BOUNDS(idx, fb.cap0 > fb.capd ? fb.cap0 : fb.capd))
+        if (WRT_IN_BOUNDS(idx, fb.cap0 > fb.capd ? fb.cap0 : fb.capd))
             fb.hit[idx] = make_float4(cs.best.t, __int_as_float(cs.best.prim), cs.best.u, cs.best.v);
         return false;
     }
-    __device__ __forceinline__ bool pending() const { return FUSED && has_result; }
-    __device__ __forceinline__ void retire() {
-        if (LEVEL0 && has_result && cs.best.prim != -2) ++valid;
-        surface_warp(s, fb, level, cull, has_result, r.o, r.d, pixel, path, cs.best.t, cs.best.prim, cs.best.u, cs.best.v, idx);
-        has_result = false;
-    }
-    __device__ __forceinline__ void done() {
-        if (LEVEL0) {
-            unsigned v = __reduce_add_sync(0xffffffffu, valid);
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(fb.counters + C_VALID0, v);
-        }
-    }
 };
 
-// Fused closest hit + surface of one level (primary rays generated in begin() on level 0).
-template <bool LEVEL0>
-__global__ void WRT_FUSED_BOUNDS k_trace_surface(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
-                                                 const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int work_slot,
-                                                 float prune_rel, int refill, int cull) {
-    extern __shared__ int smem[];
-    Stack st;
-    st.init(smem, threadIdx.x, blockDim.x);
-    ClosestQuery<LEVEL0, true> q(s, fb, pg, level, n0, prune_rel, cull);
-    run_queue(q, q.span.count(), reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
-    q.done();
-}
-
-// Unfused pair (WRT_FUSE_FROM): closest hit -> hit records, then one streaming pass over them.
 template <bool LEVEL0>
 __global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
                                                  const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int work_slot,
@@ -424,10 +383,11 @@ __global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScen
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
-    ClosestQuery<LEVEL0, false> q(s, fb, pg, level, n0, prune_rel, 0);
+    ClosestQuery<LEVEL0> q(s, fb, pg, level, n0, prune_rel);
     run_queue(q, q.span.count(), reinterpret_cast<unsigned long long*>(fb.counters + work_slot), st, refill);
 }
 
+// ---- K3: hit -> surface, shadow requests, child rays: one streaming pass, whole warps call surface_warp() ----
 __global__ void __launch_bounds__(256) k_surface_spawn(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
                                                        const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int cull) {
     const LevelSpan span = level_span(fb, level, n0);
@@ -461,7 +421,6 @@ __global__ void __launch_bounds__(256) k_surface_spawn(const __grid_constant__ D
 
 // ---- K4a: hard shadows, BVHStrategy::getShadowCoeffi ----
 struct HardShadowQuery {
-    static constexpr bool RETIRES = false;
     const DevScene& s;
     const FrameBuffers& fb;
     Ray r;
@@ -501,8 +460,6 @@ struct HardShadowQuery {
         if (WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) fb.coeff[out] = res;
         return false;
     }
-    __device__ __forceinline__ bool pending() const { return false; }
-    __device__ __forceinline__ void retire() {}
 };
 
 __global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q, int work_slot, int refill,
@@ -522,7 +479,6 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_hard(const __grid_constant__ DevScene 
 // (Tracing a sample pair per lane from one Philox block was tried: 16 % slower — register
 // pressure and a less coherent second walk; profiles/NOTES.md.)
 struct SoftShadowQuery {
-    static constexpr bool RETIRES = false;
     const DevScene& s;
     const FrameBuffers& fb;
     unsigned seed;
@@ -581,8 +537,6 @@ struct SoftShadowQuery {
         if (!occ && WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) atomicAdd(fb.coeff + out, 1.0f);
         return false;
     }
-    __device__ __forceinline__ bool pending() const { return false; }
-    __device__ __forceinline__ void retire() {}
 };
 
 __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q, int work_slot,

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -14,6 +15,7 @@
 #include "../../../include/wrt_cuda.h"
 #include "fast_bvh.hpp"
 #include "kernels.cuh"
+#include "bvh_build.cuh"
 
 namespace {
 
@@ -79,18 +81,23 @@ struct WrtContext {
     long long list_pool_cap_override = 0;
     int shaft_cull_max_level = 0;      // deepest ray-tree level whose surface stage runs the shaft test (when lists are on)
     wrt::SoftListBuffers list_bufs[2] = {};
-    wrt::FastBvhBuilder fbvh;          // host scratch of wrt_upload_scene, kept between uploads
-    std::vector<WrtNode> h_oct;
+    wrt::FastBvhBuilder fbvh;          // WRT_HOST_BVH=1 only: the host's binned-SAH build (development A/B)
+    bool host_bvh = false;
+    uint8_t* h_stage = nullptr;        // pinned staging of the scene description: one H2D per upload
+    size_t h_stage_bytes = 0;
+    int ploc_coop_grid = 1;            // co-resident CTAs of k_bvh_ploc
+    int fast_depth = 0, build_passes = 0;
     bool unlit_cull = true;            // drop shadow requests of lights whose shading terms are exactly 0 at the point
     int cache_from_level = 0;          // per-ray soft-shadow kernel: occluder cache (99 = off)
     int chunk_div = 16;                // work claiming: 0 = one atomic per refill, k = chunks of n/(warps*k) items
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
     int trace_blocks_per_sm = 10;      // persistent shadow / unfused closest-hit kernels
-    int fused_blocks_per_sm = WRT_FUSED_MIN_BLOCKS;
-    int fuse_from = 99;                // levels >= this run the fused closest-hit + surface kernel (99: never; experimental, see kernels.cuh)
     bool shade0_separate = true;       // level 0 is shaded by its own launch on the side stream (else inside combine)
     bool small_batch_full_levels = true; // automatic sizing: batches under 1 M slots get full-size deep levels
     long long max_batch = 1ll << 25;   // primary slots per batch (8K = 33.2 M slots fits)
+    long long learned_batch = 1ll << 40; // a batch size that overflowed with the deep levels at their largest: later frames of
+                                       // the same scene / image size start with the halved batches right away
+    long long learned_key[4] = {0, 0, 0, 0};
 
     // frame buffers
     wrt::FrameBuffers fb{};
@@ -142,22 +149,22 @@ namespace {
 using wrt::FrameBuffers;
 
 // Scene arrays keep their device allocation across uploads when the new array fits
-// (re-uploading a scene of the same size costs copies only, no cudaMalloc/cudaFree).
-template <class T>
-int dev_upload(WrtContext* c, const T* src, size_t count, const T** dst) {
-    *dst = nullptr;
-    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+// (re-uploading a scene of the same size costs copies and kernels only, no cudaMalloc/cudaFree).
+int dev_alloc(WrtContext* c, size_t bytes, void** out) {
+    *out = nullptr;
+    bytes = std::max<size_t>(bytes, 256);
     size_t slot = c->scene_slot++;
     if (slot >= c->scene_allocs.size()) { c->scene_allocs.push_back(nullptr); c->scene_alloc_bytes.push_back(0); }
     if (c->scene_alloc_bytes[slot] < bytes) {
-        if (c->scene_allocs[slot]) cudaFree(c->scene_allocs[slot]);
+        if (c->scene_allocs[slot]) {
+            CK(cudaDeviceSynchronize());               // a frame in flight may still read the old array
+            cudaFree(c->scene_allocs[slot]);
+        }
         c->scene_allocs[slot] = nullptr; c->scene_alloc_bytes[slot] = 0;
         CK(cudaMalloc(&c->scene_allocs[slot], bytes));
         c->scene_alloc_bytes[slot] = bytes;
     }
-    void* p = c->scene_allocs[slot];
-    if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->chain));
-    *dst = (const T*)p;
+    *out = c->scene_allocs[slot];
     return 0;
 }
 
@@ -371,7 +378,7 @@ int enqueue_batch(WrtContext* c, long long slot0, unsigned n, uint8_t* d_image, 
     int work_seq = 0;
     auto work_slot = [&]() { int s = C_WORK + 2 * work_seq; ++work_seq; return s; };
     const int TB = 128;
-    const int trace_grid = grid_for(c, c->trace_blocks_per_sm), fused_grid = grid_for(c, c->fused_blocks_per_sm), wide_grid = grid_for(c, 8);
+    const int trace_grid = grid_for(c, c->trace_blocks_per_sm), wide_grid = grid_for(c, 8);
     const size_t sb = stack_bytes(c, TB);
     const float prune = prune_value(c);
     auto cull_for = [&](int d) {
@@ -389,19 +396,13 @@ int enqueue_batch(WrtContext* c, long long slot0, unsigned n, uint8_t* d_image, 
     };
     auto level_kernels = [&](int d) {
         const int refill = (d == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8);
-        if (d >= c->fuse_from) {
+        {
             LaunchScope ls(c, st, F_TRACE);
-            if (d == 0) k_trace_surface<true><<<fused_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill, cull_for(d));
-            else k_trace_surface<false><<<fused_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill, cull_for(d));
-        } else {
-            {
-                LaunchScope ls(c, st, F_TRACE);
-                if (d == 0) k_trace_closest<true><<<trace_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill);
-                else k_trace_closest<false><<<trace_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill);
-            }
-            LaunchScope ls(c, st, F_SURFACE);
-            k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, pg, d, n, cull_for(d));
+            if (d == 0) k_trace_closest<true><<<trace_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill);
+            else k_trace_closest<false><<<trace_grid, TB, sb, st>>>(ds, fb, pg, d, n, work_slot(), prune, refill);
         }
+        LaunchScope ls(c, st, F_SURFACE);
+        k_surface_spawn<<<wide_grid, 256, 0, st>>>(ds, fb, pg, d, n, cull_for(d));
     };
     level_kernels(0);
     if (overlap) {
@@ -477,9 +478,10 @@ int check_debug_bounds() { return 0; }
 // Returns true when the buffers grew and the same batch should simply be rendered again.
 bool grow_after_overflow(WrtContext* c) {
     const float effective = (float)c->deep_slots / (float)std::max(1u, c->batch_slots);
-    if (c->queue_factor > 0.f || effective >= 2.f) return false;
+    const float limit = 4.f;                           // (per-level capacity in primary-batch units; beyond it: smaller batches)
+    if (c->queue_factor > 0.f || effective >= limit) return false;
     const float old = c->deep_factor;
-    c->deep_factor = std::min(2.f, std::max(old, effective) * 2.f);
+    c->deep_factor = std::min(limit, std::max(old, effective) * 2.f);
     if (ensure_frame_buffers(c, c->batch_slots) == 0) return true;
     c->deep_factor = old;                              // out of memory: fall back to halving
     cudaGetLastError();
@@ -501,6 +503,7 @@ int render_spans_sync(WrtContext* c, std::vector<std::pair<long long, long long>
             if (grow_after_overflow(c)) { todo.push_back({s0, n}); continue; }
             if (n <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
             long long half = ((n / 2 + 31) / 32) * 32;
+            if (c->queue_factor <= 0.f) c->learned_batch = std::min(c->learned_batch, half);
             todo.push_back({s0 + half, n - half});
             todo.push_back({s0, half});
             continue;
@@ -518,7 +521,12 @@ int render_all(WrtContext* c, cudaStream_t user, bool join_user, uint8_t* d_imag
     if (c->cam.width <= 0 || c->cam.height <= 0) return fail("wrt_render: empty image");
     if (!c->textures_complete) return fail("wrt_render: a primitive references a texture / normal map that was not uploaded");
     const long long total = c->local_slots(c->rank, c->world);
-    const long long max_batch = c->max_batch;
+    {
+        const long long key[4] = {c->cam.width, c->cam.height, ((long long)c->ds.n_prims << 8) | (c->ds.n_lights << 1) | (c->ds.shadow_type & 1),
+                                  ((long long)c->world << 32) | (unsigned)c->traversal};
+        if (memcmp(key, c->learned_key, sizeof key)) { memcpy(c->learned_key, key, sizeof key); c->learned_batch = 1ll << 40; }
+    }
+    const long long max_batch = std::min(c->max_batch, c->learned_batch);
     memset(&c->stats, 0, sizeof c->stats);
     c->timed.clear();
     c->event_next = 0;
@@ -570,6 +578,7 @@ int finish_frame(WrtContext* c) {
             else {
                 if (total <= 64) return fail("ray queue overflow on a 64-slot batch: raise queue_factor");
                 long long half = ((total / 2 + 31) / 32) * 32;
+                if (c->queue_factor <= 0.f) c->learned_batch = std::min(c->learned_batch, half);
                 todo.push_back({half, total - half});
                 todo.push_back({0, half});
             }
@@ -624,7 +633,7 @@ int wrt_create(int device, WrtContext** out) {
         ev_ok = ev_ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
     if (!ev_ok ||
         cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess ||
-        cudaMallocHost((void**)&c->h_counters, wrt::C_TOTAL * sizeof(unsigned)) != cudaSuccess) {
+        cudaMallocHost((void**)&c->h_counters, (wrt::C_TOTAL + 64) * sizeof(unsigned)) != cudaSuccess) {
         delete c;
         return fail("wrt_create: stream/event/pinned allocation failed");
     }
@@ -636,6 +645,12 @@ int wrt_create(int device, WrtContext** out) {
             return fail("wrt_create: cooperative launch of k_combine_resolve is not possible on this device");
         }
         c->coop_grid = c->num_sms * std::min(per_sm, 4);
+        per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrt::k_bvh_ploc, WRT_PLOC_THREADS, 0) != cudaSuccess || per_sm < 1) {
+            wrt_destroy(c);
+            return fail("wrt_create: cooperative launch of k_bvh_ploc is not possible on this device");
+        }
+        c->ploc_coop_grid = c->num_sms * std::min(per_sm, 2);
     }
     // tuning overrides (development only; defaults are what bench.py measures)
     if (const char* e = getenv("WRT_REFILL")) c->refill = std::max(1, std::min(32, atoi(e)));
@@ -650,8 +665,7 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_SHAFT_LEVELS")) c->shaft_cull_max_level = atoi(e);
     if (const char* e = getenv("WRT_CHUNK_DIV")) c->chunk_div = std::max(0, std::min(255, atoi(e)));
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
-    if (const char* e = getenv("WRT_FUSED_BLOCKS")) c->fused_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
-    if (const char* e = getenv("WRT_FUSE_FROM")) c->fuse_from = atoi(e);
+    if (const char* e = getenv("WRT_HOST_BVH")) c->host_bvh = atoi(e) != 0;
     if (const char* e = getenv("WRT_SHADE0_SEPARATE")) c->shade0_separate = atoi(e) != 0;
     if (const char* e = getenv("WRT_DEEP_FACTOR")) { c->deep_factor = std::max(0.001f, std::min(2.f, (float)atof(e))); c->small_batch_full_levels = false; }
     if (const char* e = getenv("WRT_MAX_BATCH")) c->max_batch = std::max(64ll, (atoll(e) + 31) / 32 * 32);   // tests: force multi-batch frames
@@ -669,6 +683,7 @@ void wrt_destroy(WrtContext* c) {
     if (c->d_image) cudaFree(c->d_image);
     if (c->h_image) cudaFreeHost(c->h_image);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -678,110 +693,214 @@ void wrt_destroy(WrtContext* c) {
     delete c;
 }
 
+// Scene upload.  The host only STAGES bytes: every array of the description is copied into one pinned staging
+// buffer and crosses PCIe in a single cudaMemcpyAsync; everything derived — per-primitive boxes, the SAH-quality tree
+// the kernels walk (PLOC build, bvh_build.cuh), its dilated copy, the 8 octant copies of both trees, the float4
+// geometry / attribute / id / material layouts — is produced by kernels on the device.  One small read-back (tree
+// depth, flags) ends the call.
 int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     if (!c || !s) return fail("wrt_upload_scene: null argument");
     CK(cudaSetDevice(c->device));
-    CK(cudaDeviceSynchronize());                       // no frame may still read the old scene
+    if (s->n_nodes < 0 || s->n_prims < 0 || s->n_materials < 0 || s->n_lights < 0 || s->n_textures < 0 || s->n_normalmaps < 0 || s->n_texels < 0)
+        return fail("wrt_upload_scene: negative count in the scene description");
+    if (s->n_prims > 0 && s->n_nodes != 2 * s->n_prims)
+        return fail("wrt_upload_scene: a tree over n one-primitive leaves has 2n records (root, padding, n-1 sibling pairs)");
+    if (s->n_prims > 0 && s->n_materials == 0) return fail("wrt_upload_scene: primitives without materials");
+    // indices a kernel follows without a device-side check are validated here (the rest — material, texture, leaf
+    // links — by the kernels that unpack them)
+    for (int i = 0; i < s->n_textures + s->n_normalmaps; i++) {
+        const WrtTexture& t = i < s->n_textures ? s->textures[i] : s->normalmaps[i - s->n_textures];
+        if (t.offset < 0 || t.count < 0 || t.offset + t.count > s->n_texels) return fail("wrt_upload_scene: texture texel range outside texels[]");
+    }
+    for (int i = 0; i < s->n_nodes; i++) {             // child links of the caller's tree stay inside it
+        const int link = s->nodes[i].link;
+        if (i != 1 && link >= 0 && (link < 2 || link + 1 >= s->n_nodes)) return fail("wrt_upload_scene: tree child link out of range");
+    }
+    cudaStream_t st = c->chain;                         // ordered behind any frame still in flight: it may read the old scene
     c->has_scene = false;
     c->scene_slot = 0;
     wrt::DevScene& ds = c->ds;
     memset(&ds, 0, sizeof ds);
     c->textures_complete = true;
-    const int np = s->n_prims;
-    // nodes: identical 32-byte records, viewed as float4 pairs on the device
+    const int np = s->n_prims, nn = s->n_nodes;
     static_assert(sizeof(WrtNode) == 32, "WrtNode must be 32 bytes");
-    if (dev_upload(c, (const float4*)s->nodes, 2 * (size_t)s->n_nodes, &ds.nodes)) return 1;
-    // SAH tree over the same leaf boxes (fast_bvh.hpp explains why results are identical)
-    wrt::FastBvhBuilder& fbvh = c->fbvh;               // host-side scratch lives in the context: uploads of same-sized
-    auto t_sah0 = std::chrono::steady_clock::now();    // scenes (every frame of the end-to-end path) reuse its pages
-    fbvh.build(s);
-    auto t_sah1 = std::chrono::steady_clock::now();
-    if (fbvh.nodes.size() != (size_t)s->n_nodes) return fail("wrt_upload_scene: fast BVH build failed");
-    if (dev_upload(c, (const float4*)fbvh.nodes.data(), 2 * fbvh.nodes.size(), &ds.fnodes)) return 1;
-    {
-        std::vector<WrtNode>& oct = c->h_oct;
-        wrt::FastBvhBuilder::octant_copies_into(fbvh.nodes.data(), fbvh.nodes.size(), oct);
-        if (dev_upload(c, (const float4*)oct.data(), 2 * oct.size(), &ds.onodes)) return 1;
-        wrt::FastBvhBuilder::octant_copies_into(s->nodes, (size_t)s->n_nodes, oct);      // (the previous copy was staged)
-        if (dev_upload(c, (const float4*)oct.data(), 2 * oct.size(), &ds.ronodes)) return 1;
+    static_assert(sizeof(WrtMaterial) == 48, "WrtMaterial must be 12 floats");
+
+    // ---- 1. stage + one H2D ----
+    struct Part { const void* src; size_t bytes; size_t off; };
+    Part parts[] = {
+        {s->nodes, (size_t)nn * sizeof(WrtNode), 0},                 // 0
+        {s->prim_geom, (size_t)np * 48, 0},                          // 1
+        {s->prim_flags, (size_t)np * 4, 0},                          // 2
+        {s->prim_material, (size_t)np * 4, 0},                       // 3
+        {s->prim_texture, (size_t)np * 4, 0},                        // 4
+        {s->prim_normalmap, (size_t)np * 4, 0},                      // 5
+        {s->prim_object, (size_t)np * 4, 0},                         // 6
+        {s->object_prim, (size_t)np * 4, 0},                         // 7
+        {s->prim_normals, (size_t)np * 36, 0},                       // 8
+        {s->prim_uv, (size_t)np * 24, 0},                            // 9
+        {s->materials, (size_t)s->n_materials * sizeof(WrtMaterial), 0},   // 10
+        {s->lights, (size_t)s->n_lights * sizeof(WrtLight), 0},      // 11
+        {s->textures, (size_t)s->n_textures * sizeof(WrtTexture), 0},      // 12
+        {s->normalmaps, (size_t)s->n_normalmaps * sizeof(WrtTexture), 0},  // 13
+        {s->texels, (size_t)s->n_texels * 12, 0},                    // 14
+    };
+    size_t total = 0;
+    for (Part& p : parts) {
+        if (p.bytes && !p.src) return fail("wrt_upload_scene: null array with a non-zero count");
+        p.off = total;
+        total += (p.bytes + 255) & ~(size_t)255;
     }
-    // dilated copy for the directional-shadow loop, which the reference runs without any box test
-    std::vector<WrtNode> dil = fbvh.dilated(1e-3f, 1e-4f);
-    if (dev_upload(c, (const float4*)dil.data(), 2 * dil.size(), &ds.dnodes)) return 1;
-    std::vector<float4> geom(3 * (size_t)np), attr(4 * (size_t)np);
-    std::vector<int4> ids(np);
-    int has_light = 0;
-    for (int p = 0; p < np; p++) {
-        const float* g = s->prim_geom + 12 * (size_t)p;
-        const WrtMaterial& m = s->materials[s->prim_material[p]];
-        unsigned flags = s->prim_flags[p];
-        if (flags & WRT_PRIM_LIGHT) has_light = 1;
-        float oma = 1 - m.alpha;                       // (1 - inter.mtlcolor.alpha), BVHStrategy.hpp:38
-        float fl;
-        memcpy(&fl, &flags, 4);
-        geom[3 * (size_t)p + 0] = make_float4(g[0], g[1], g[2], g[3]);
-        geom[3 * (size_t)p + 1] = make_float4(g[4], g[5], g[6], oma);
-        geom[3 * (size_t)p + 2] = make_float4(g[8], g[9], g[10], fl);
-        const float* nn = s->prim_normals + 9 * (size_t)p;
-        const float* uv = s->prim_uv + 6 * (size_t)p;
-        attr[4 * (size_t)p + 0] = make_float4(nn[0], nn[1], nn[2], uv[0]);
-        attr[4 * (size_t)p + 1] = make_float4(nn[3], nn[4], nn[5], uv[1]);
-        attr[4 * (size_t)p + 2] = make_float4(nn[6], nn[7], nn[8], uv[2]);
-        attr[4 * (size_t)p + 3] = make_float4(uv[3], uv[4], uv[5], 0.f);
-        ids[p] = make_int4(s->prim_material[p], s->prim_texture[p], s->prim_normalmap[p], s->prim_object[p]);
-        // the strategy queries never read texels; a frame render needs every referenced map present
-        if (s->prim_texture[p] >= s->n_textures || s->prim_normalmap[p] >= s->n_normalmaps) c->textures_complete = false;
+    total = std::max<size_t>(total, 256);
+    if (c->h_stage_bytes < total) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_bytes = 0;
+        CK(cudaMallocHost((void**)&c->h_stage, total + total / 4));
+        c->h_stage_bytes = total + total / 4;
     }
-    std::vector<float4> mats(3 * (size_t)s->n_materials);
-    for (int i = 0; i < s->n_materials; i++) {
-        const WrtMaterial& m = s->materials[i];
-        mats[3 * (size_t)i + 0] = make_float4(m.diffuse[0], m.diffuse[1], m.diffuse[2], m.ka);
-        mats[3 * (size_t)i + 1] = make_float4(m.specular[0], m.specular[1], m.specular[2], m.kd);
-        mats[3 * (size_t)i + 2] = make_float4(m.ks, m.n, m.alpha, m.eta);
+    for (const Part& p : parts) if (p.bytes) memcpy(c->h_stage + p.off, p.src, p.bytes);
+    uint8_t* d_stage = nullptr;
+    if (dev_alloc(c, total, (void**)&d_stage)) return 1;
+    CK(cudaMemcpyAsync(d_stage, c->h_stage, total, cudaMemcpyHostToDevice, st));
+    auto dptr = [&](int k) { return d_stage + parts[k].off; };
+    ds.nodes = (const float4*)dptr(0);
+    ds.object_prim = (const int*)dptr(7);
+    ds.lights = (const WrtLight*)dptr(11);
+    ds.textures = (const WrtTexture*)dptr(12);
+    ds.normalmaps = (const WrtTexture*)dptr(13);
+    ds.texels = (const float*)dptr(14);
+
+    // ---- 2. device-side layouts ----
+    float4 *geom = nullptr, *attr = nullptr, *mats = nullptr, *pbox = nullptr, *fnodes = nullptr, *dnodes = nullptr, *onodes = nullptr, *ronodes = nullptr;
+    int4* ids = nullptr;
+    int* d_flags = nullptr;
+    if (dev_alloc(c, (size_t)np * 48, (void**)&geom) || dev_alloc(c, (size_t)np * 64, (void**)&attr) || dev_alloc(c, (size_t)np * 16, (void**)&ids) ||
+        dev_alloc(c, (size_t)s->n_materials * 48, (void**)&mats) || dev_alloc(c, (size_t)np * 32, (void**)&pbox) ||
+        dev_alloc(c, (size_t)nn * 32, (void**)&fnodes) || dev_alloc(c, (size_t)nn * 32, (void**)&dnodes) ||
+        dev_alloc(c, (size_t)nn * 32 * 8, (void**)&onodes) || dev_alloc(c, (size_t)nn * 32 * 8, (void**)&ronodes) ||
+        dev_alloc(c, (wrt::BS_TOTAL + 8) * sizeof(int), (void**)&d_flags))
+        return 1;
+    int* d_state = d_flags + 8;
+    CK(cudaMemsetAsync(d_flags, 0, (wrt::BS_TOTAL + 8) * sizeof(int), st));
+    const int wide = c->num_sms * 4;
+    if (np > 0) {
+        ++c->launches;
+        wrt::k_pack_prims<<<std::min(wide, (np + 255) / 256), 256, 0, st>>>(
+            np, (const float*)dptr(1), (const unsigned*)dptr(2), (const int*)dptr(3), (const int*)dptr(4), (const int*)dptr(5),
+            (const int*)dptr(6), (const float*)dptr(8), (const float*)dptr(9), (const float*)dptr(10), s->n_materials, s->n_textures,
+            s->n_normalmaps, geom, attr, ids, d_flags);
     }
-    std::vector<float4> pbox(2 * (size_t)np, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int i = 0; i < s->n_nodes; i++) {
-        const WrtNode& nd = s->nodes[i];
-        if (nd.link >= 0 || i == 1) continue;
-        int p = ~nd.link;
-        if (p < 0 || p >= np) continue;
-        pbox[2 * (size_t)p] = make_float4(nd.pmin[0], nd.pmin[1], nd.pmin[2], 0.f);
-        pbox[2 * (size_t)p + 1] = make_float4(nd.pmax[0], nd.pmax[1], nd.pmax[2], 0.f);
+    if (s->n_materials > 0) {
+        ++c->launches;
+        wrt::k_pack_materials<<<std::min(wide, (s->n_materials + 255) / 256), 256, 0, st>>>((const float*)dptr(10), s->n_materials, mats);
     }
-    if (dev_upload(c, pbox.data(), pbox.size(), &ds.prim_box)) return 1;
-    if (dev_upload(c, geom.data(), geom.size(), &ds.geom)) return 1;
-    if (dev_upload(c, attr.data(), attr.size(), &ds.attr)) return 1;
-    if (dev_upload(c, ids.data(), ids.size(), &ds.ids)) return 1;
-    if (dev_upload(c, s->object_prim, (size_t)np, &ds.object_prim)) return 1;
-    if (dev_upload(c, mats.data(), mats.size(), &ds.materials)) return 1;
-    if (dev_upload(c, s->lights, (size_t)s->n_lights, &ds.lights)) return 1;
-    if (dev_upload(c, s->textures, (size_t)s->n_textures, &ds.textures)) return 1;
-    if (dev_upload(c, s->normalmaps, (size_t)s->n_normalmaps, &ds.normalmaps)) return 1;
-    if (dev_upload(c, s->texels, 3 * (size_t)s->n_texels, &ds.texels)) return 1;
+    ds.geom = geom; ds.attr = attr; ds.ids = ids; ds.materials = mats; ds.prim_box = pbox;
+    ds.fnodes = fnodes; ds.dnodes = dnodes; ds.onodes = onodes; ds.ronodes = ronodes;
+
+    // ---- 3. trees ----
+    int fast_depth = 0;
+    const bool host_build = c->host_bvh;
+    auto t_b0 = std::chrono::steady_clock::now();
+    if (np > 0 && !host_build) {
+        wrt::BuildBuffers bb{};
+        const size_t n2 = 2 * (size_t)np;
+        size_t cub_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                        (const int*)nullptr, (int*)nullptr, np, 0, 63, st);
+        const int ploc_grid = std::max(1, std::min(c->ploc_coop_grid, (np + 2 * WRT_PLOC_THREADS - 1) / (2 * WRT_PLOC_THREADS)));
+        if (dev_alloc(c, n2 * 16, (void**)&bb.tree.lo) || dev_alloc(c, n2 * 16, (void**)&bb.tree.hi) || dev_alloc(c, n2 * 16, (void**)&bb.tree.dlo) ||
+            dev_alloc(c, n2 * 16, (void**)&bb.tree.dhi) || dev_alloc(c, n2 * 4, (void**)&bb.tree.parent) || dev_alloc(c, n2 * 4, (void**)&bb.tree.cnt) ||
+            dev_alloc(c, (size_t)np * 8, (void**)&bb.keys[0]) || dev_alloc(c, (size_t)np * 8, (void**)&bb.keys[1]) ||
+            dev_alloc(c, (size_t)np * 4, (void**)&bb.vals[0]) || dev_alloc(c, (size_t)np * 4, (void**)&bb.vals[1]) ||
+            dev_alloc(c, (size_t)np * 4, (void**)&bb.cl[0]) || dev_alloc(c, (size_t)np * 4, (void**)&bb.cl[1]) ||
+            dev_alloc(c, (size_t)np * 4, (void**)&bb.nn) || dev_alloc(c, (size_t)ploc_grid * 4, (void**)&bb.blk) ||
+            dev_alloc(c, cub_bytes, &bb.cub_temp))
+            return 1;
+        bb.state = d_state;
+        bb.cub_temp_bytes = cub_bytes;
+        c->launches += 4;
+        CK(cudaMemsetAsync(bb.tree.cnt, 0, (size_t)np * 4, st));
+        wrt::k_bvh_leaves<<<std::min(wide, (nn + 255) / 256), 256, 0, st>>>(ds.nodes, nn, np, bb, pbox, 1e-3f, 1e-4f);
+        CK(cub::DeviceRadixSort::SortPairs(bb.cub_temp, cub_bytes, bb.keys[0], bb.keys[1], bb.vals[0], bb.vals[1], np, 0, 63, st));
+        {
+            const int* sorted = bb.vals[1];
+            int n_arg = np, radius = WRT_PLOC_RADIUS;
+            void* args[] = {(void*)&bb, (void*)&sorted, (void*)&n_arg, (void*)&radius};
+            CK(cudaLaunchCooperativeKernel((const void*)wrt::k_bvh_ploc, dim3(ploc_grid), dim3(WRT_PLOC_THREADS), args, 0, st));
+        }
+        wrt::k_bvh_layout<<<std::min(wide, (int)((n2 + 255) / 256)), 256, 0, st>>>(bb, np, fnodes, dnodes);
+    } else if (np > 0) {
+        // WRT_HOST_BVH=1 (development A/B): the host's binned-SAH build of fast_bvh.hpp
+        wrt::FastBvhBuilder& fbvh = c->fbvh;
+        fbvh.build(s);
+        if (fbvh.nodes.size() != (size_t)nn) return fail("wrt_upload_scene: fast BVH build failed");
+        std::vector<WrtNode> dil = fbvh.dilated(1e-3f, 1e-4f);
+        std::vector<float4> hb(2 * (size_t)np, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int i = 0; i < nn; i++) {
+            const WrtNode& nd = s->nodes[i];
+            if (nd.link >= 0 || i == 1) continue;
+            int p = ~nd.link;
+            if (p < 0 || p >= np) return fail("wrt_upload_scene: leaf link out of range");
+            hb[2 * (size_t)p] = make_float4(nd.pmin[0], nd.pmin[1], nd.pmin[2], 0.f);
+            hb[2 * (size_t)p + 1] = make_float4(nd.pmax[0], nd.pmax[1], nd.pmax[2], 0.f);
+        }
+        CK(cudaMemcpyAsync(fnodes, fbvh.nodes.data(), (size_t)nn * 32, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dnodes, dil.data(), (size_t)nn * 32, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pbox, hb.data(), hb.size() * 16, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                  // the host vectors above go out of scope
+        fast_depth = fbvh.max_depth;
+    }
+    if (nn > 0) {
+        c->launches += 2;
+        const int g = (int)std::min<long long>(wide, (8ll * nn + 255) / 256);
+        wrt::k_octant_copies<<<g, 256, 0, st>>>(fnodes, nn, onodes);
+        wrt::k_octant_copies<<<g, 256, 0, st>>>(ds.nodes, nn, ronodes);
+    }
+    CK(cudaGetLastError());
+    unsigned* h_rb = c->h_counters + wrt::C_TOTAL;     // (the first C_TOTAL words belong to a frame that may still be in flight)
+    CK(cudaMemcpyAsync(h_rb, d_flags, (wrt::BS_TOTAL + 8) * sizeof(int), cudaMemcpyDeviceToHost, st));
+
+    // ---- 4. host-side scalars (while the device builds) ----
     for (int i = 0; i < s->n_lights && i < WRT_INLINE_LIGHTS; i++) ds.lights_c[i] = s->lights[i];
-    ds.n_nodes = s->n_nodes; ds.n_prims = np; ds.n_lights = s->n_lights;
+    ds.n_nodes = nn; ds.n_prims = np; ds.n_lights = s->n_lights;
     ds.n_point_lights = ds.n_dir_lights = 0;
     for (int i = 0; i < s->n_lights; i++) {
         if (fabsf(s->lights[i].pos[3] - 1.f) < 0.00001f) ++ds.n_point_lights;      // FLOAT_EQUAL(w, 1), Renderer.hpp:275
         else ++ds.n_dir_lights;
     }
-    ds.has_light_prims = has_light;
     ds.shadow_type = s->shadow_type; ds.depth_cueing = s->depth_cueing;
     for (int k = 0; k < 3; k++) { ds.bkg[k] = s->bkgcolor[k]; ds.dc[k] = s->dc[k]; ds.eye[k] = s->eye[k]; }
     ds.eta = s->eta;
     ds.amin = s->amin; ds.amax = s->amax; ds.distmin = s->distmin; ds.distmax = s->distmax;
     c->bvh_depth = tree_depth(s);
-    c->stack_rows = std::max(c->bvh_depth, fbvh.max_depth) + 2;
+    CK(cudaStreamSynchronize(st));
+    auto t_b1 = std::chrono::steady_clock::now();
+    const int* rb = (const int*)h_rb;
+    const int flags = rb[0];
+    const int* state = rb + 8;
+    if (state[wrt::BS_ERROR] == 1) return fail("wrt_upload_scene: leaf link out of range in the scene's tree (every primitive needs exactly one leaf record)");
+    if (state[wrt::BS_ERROR]) return fail("wrt_upload_scene: device BVH build made no progress (non-finite boxes?)");
+    if (flags & 4) return fail("wrt_upload_scene: primitive material index out of range");
+    if (np > 0 && !host_build) {
+        fast_depth = state[wrt::BS_DEPTH];
+        if (state[wrt::BS_ALLOC] != 2 * np - 1) return fail("wrt_upload_scene: device BVH build is incomplete (a primitive without a leaf record?)");
+    }
+    ds.has_light_prims = (flags & 1) ? 1 : 0;
+    // the strategy queries never read texels; a frame render needs every referenced map present
+    c->textures_complete = !(flags & 2);
+    c->stack_rows = std::max(c->bvh_depth, fast_depth) + 2;
 #ifdef WRT_DEBUG_BOUNDS
     if (const char* e = getenv("WRT_DEBUG_STACK_ROWS")) c->stack_rows = std::max(1, atoi(e));   // provoke the stack check (tests)
 #endif
     if (c->stack_rows > 90)     // 90 rows x 128 threads x 4 B = 45 KB of dynamic shared memory per CTA
         return fail("wrt_upload_scene: acceleration tree deeper than 88 levels (degenerate geometry?)");
-    CK(cudaStreamSynchronize(c->chain));          // host staging vectors go out of scope here
+    c->fast_depth = fast_depth;
+    c->build_passes = state[wrt::BS_PASSES];
     c->has_scene = true;
     if (getenv("WRT_VERBOSE"))
-        fprintf(stderr, "[wrt] upload: %d prims, reference tree depth %d, SAH tree depth %d (built in %.2f ms)\n", np,
-                c->bvh_depth, fbvh.max_depth, std::chrono::duration<double, std::milli>(t_sah1 - t_sah0).count());
+        fprintf(stderr, "[wrt] upload: %d prims, %zu bytes staged, reference tree depth %d, walked tree depth %d (%s, %d PLOC passes), %.3f ms\n",
+                np, total, c->bvh_depth, fast_depth, host_build ? "host SAH" : "device PLOC", c->build_passes,
+                std::chrono::duration<double, std::milli>(t_b1 - t_b0).count());
     return 0;
 }
 
@@ -1047,6 +1166,203 @@ int wrt_get_kernel_launches(WrtContext* c, int32_t* launches, int capacity) {
     int n = std::min(capacity, (int)WRT_KERNEL_FAMILIES);
     for (int i = 0; i < n; i++) launches[i] = c->family_launches[i];
     return n;
+}
+
+
+// ======================= multi-GPU in one process =======================
+// wrt_multi_*: the scene replicated on n GPUs, the image sharded as interleaved tiles (include/wrt_tiles.h), one host
+// thread per GPU driving an ordinary WrtContext.  There is no gather step: with peer access every GPU's resolve kernel
+// stores its 8-bit pixels straight into device 0's row-major frame over NVLink (k_combine_resolve's `image` pointer is a
+// peer pointer), so the exchange overlaps the last kernel of each GPU and rank 0 only copies the finished frame to the
+// host.  Without peer access (never the case on an NVSwitch box) the ranks' tile buffers are copied to device 0 and
+// de-interleaved there by k_scatter_tiles.
+
+} // extern "C"
+
+struct WrtMulti {
+    std::vector<WrtContext*> ctx;
+    std::vector<int> devices;
+    bool peer_stores = true;
+    uint8_t* d_gathered = nullptr;       // fallback path only (on device 0)
+    size_t gathered_bytes = 0;
+    std::vector<uint8_t*> d_packed;      // fallback path only (per device)
+    std::vector<size_t> packed_bytes;
+    std::vector<std::string> errors;
+};
+
+namespace {
+
+// Runs fn(rank) on one host thread per GPU (rank 0 on the caller's thread) and collects the error strings.
+template <class F>
+int multi_run(WrtMulti* m, F fn) {
+    const int n = (int)m->ctx.size();
+    std::vector<int> rc(n, 0);
+    m->errors.assign(n, std::string());
+    std::vector<std::thread> th;
+    for (int r = 1; r < n; r++)
+        th.emplace_back([&, r] {
+            rc[r] = fn(r);
+            if (rc[r]) m->errors[r] = g_err;           // g_err is thread_local
+        });
+    rc[0] = fn(0);
+    if (rc[0]) m->errors[0] = g_err;
+    for (std::thread& t : th) t.join();
+    for (int r = 0; r < n; r++)
+        if (rc[r]) return fail("GPU " + std::to_string(m->devices[r]) + ": " + m->errors[r]);
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int wrt_multi_create(const int* devices, int n, WrtMulti** out) {
+    if (!out) return fail("wrt_multi_create: null out pointer");
+    *out = nullptr;
+    if (!devices || n < 1) return fail("wrt_multi_create: need at least one device");
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) return fail("wrt_multi_create: device listed twice");
+    WrtMulti* m = new WrtMulti();
+    m->devices.assign(devices, devices + n);
+    m->ctx.assign(n, nullptr);
+    m->d_packed.assign(n, nullptr);
+    m->packed_bytes.assign(n, 0);
+    for (int r = 0; r < n; r++) {
+        if (wrt_create(devices[r], &m->ctx[r]) != 0) { wrt_multi_destroy(m); return 1; }
+    }
+    // every GPU must be able to store into device 0's frame
+    for (int r = 1; r < n && m->peer_stores; r++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[r], devices[0]) != cudaSuccess || !can) { m->peer_stores = false; break; }
+        cudaSetDevice(devices[r]);
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) m->peer_stores = false;
+        cudaGetLastError();
+    }
+    if (getenv("WRT_MULTI_NO_PEER")) m->peer_stores = false;          // tests: force the copy + scatter path
+    *out = m;
+    return 0;
+}
+
+void wrt_multi_destroy(WrtMulti* m) {
+    if (!m) return;
+    for (size_t r = 0; r < m->ctx.size(); r++) {
+        if (m->d_packed[r]) { cudaSetDevice(m->devices[r]); cudaFree(m->d_packed[r]); }
+        if (m->ctx[r]) wrt_destroy(m->ctx[r]);
+    }
+    if (m->d_gathered) { cudaSetDevice(m->devices[0]); cudaFree(m->d_gathered); }
+    delete m;
+}
+
+int wrt_multi_device_count(WrtMulti* m) { return m ? (int)m->ctx.size() : 0; }
+WrtContext* wrt_multi_context(WrtMulti* m, int rank) { return (m && rank >= 0 && rank < (int)m->ctx.size()) ? m->ctx[rank] : nullptr; }
+int wrt_multi_uses_peer_stores(WrtMulti* m) { return m && m->peer_stores ? 1 : 0; }
+
+int wrt_multi_upload_scene(WrtMulti* m, const WrtSceneDesc* s) {
+    if (!m || !s) return fail("wrt_multi_upload_scene: null argument");
+    return multi_run(m, [&](int r) { return wrt_upload_scene(m->ctx[r], s); });
+}
+
+int wrt_multi_set_camera(WrtMulti* m, const WrtCamera* cam) {
+    if (!m || !cam) return fail("wrt_multi_set_camera: null argument");
+    for (WrtContext* c : m->ctx) if (wrt_set_camera(c, cam)) return 1;
+    return 0;
+}
+
+int wrt_multi_set_options(WrtMulti* m, int traversal, uint32_t seed, float queue_factor) {
+    if (!m) return fail("wrt_multi_set_options: null argument");
+    for (WrtContext* c : m->ctx) if (wrt_set_options(c, traversal, seed, queue_factor)) return 1;
+    return 0;
+}
+
+int wrt_multi_render(WrtMulti* m, uint8_t* rgb_host, WrtStats* stats) {
+    if (!m || !rgb_host) return fail("wrt_multi_render: null argument");
+    const int n = (int)m->ctx.size();
+    WrtContext* c0 = m->ctx[0];
+    if (!c0->has_cam) return fail("wrt_multi_render: no camera set");
+    const size_t bytes = (size_t)c0->cam.width * c0->cam.height * 3;
+    if (bytes == 0) return fail("wrt_multi_render: empty image");
+    CK(cudaSetDevice(c0->device));
+    if (c0->d_image_bytes < bytes) {
+        CK(cudaDeviceSynchronize());
+        if (c0->d_image) cudaFree(c0->d_image);
+        c0->d_image = nullptr; c0->d_image_bytes = 0;
+        CK(cudaMalloc((void**)&c0->d_image, bytes));
+        c0->d_image_bytes = bytes;
+    }
+    const int tw = c0->tile_w, thh = c0->tile_h;
+    for (int r = 0; r < n; r++) if (wrt_set_tiles(m->ctx[r], tw, thh, r, n)) return 1;
+    const long long stride = c0->local_slots(0, n) * 3;               // rank 0 owns the most tiles
+    if (!m->peer_stores) {
+        if (m->gathered_bytes < (size_t)stride * n) {
+            if (m->d_gathered) cudaFree(m->d_gathered);
+            m->d_gathered = nullptr; m->gathered_bytes = 0;
+            CK(cudaMalloc((void**)&m->d_gathered, (size_t)stride * n));
+            m->gathered_bytes = (size_t)stride * n;
+        }
+    }
+    uint8_t* d_image0 = c0->d_image;
+    int rc = multi_run(m, [&](int r) -> int {
+        WrtContext* c = m->ctx[r];
+        CK(cudaSetDevice(c->device));
+        if (m->peer_stores) {
+            if (render_all(c, nullptr, false, d_image0, nullptr)) return 1;      // stores cross NVLink from the resolve kernel
+            return finish_frame(c);
+        }
+        if (m->packed_bytes[r] < (size_t)stride) {
+            if (m->d_packed[r]) cudaFree(m->d_packed[r]);
+            m->d_packed[r] = nullptr; m->packed_bytes[r] = 0;
+            CK(cudaMalloc((void**)&m->d_packed[r], (size_t)stride));
+            m->packed_bytes[r] = (size_t)stride;
+        }
+        if (render_all(c, nullptr, false, nullptr, m->d_packed[r])) return 1;
+        if (finish_frame(c)) return 1;
+        CK(cudaMemcpyPeerAsync(m->d_gathered + (size_t)r * stride, m->devices[0], m->d_packed[r], c->device, (size_t)stride, c->chain));
+        CK(cudaStreamSynchronize(c->chain));
+        return 0;
+    });
+    for (int r = 0; r < n; r++) wrt_set_tiles(m->ctx[r], tw, thh, 0, 1);         // the contexts stay usable on their own
+    if (rc) return 1;
+    CK(cudaSetDevice(c0->device));
+    cudaStream_t st = c0->chain;
+    if (!m->peer_stores) {
+        wrt_set_tiles(c0, tw, thh, 0, n);
+        int src = wrt_scatter_tiles(c0, m->d_gathered, n, stride, c0->d_image, (void*)st);
+        wrt_set_tiles(c0, tw, thh, 0, 1);
+        if (src) return 1;
+    }
+    cudaPointerAttributes attr;
+    const bool user_pinned = cudaPointerGetAttributes(&attr, rgb_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (user_pinned) {
+        CK(cudaMemcpyAsync(rgb_host, c0->d_image, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        if (c0->h_image_bytes < bytes) {
+            if (c0->h_image) cudaFreeHost(c0->h_image);
+            c0->h_image = nullptr; c0->h_image_bytes = 0;
+            CK(cudaMallocHost((void**)&c0->h_image, bytes));
+            c0->h_image_bytes = bytes;
+        }
+        CK(cudaMemcpyAsync(c0->h_image, c0->d_image, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(rgb_host, c0->h_image, bytes);
+    }
+    if (stats) {
+        WrtStats t{};
+        for (int r = 0; r < n; r++) {
+            const WrtStats& a = m->ctx[r]->stats;
+            t.closest_rays += a.closest_rays; t.shadow_rays += a.shadow_rays; t.shadow_requests += a.shadow_requests;
+            for (int d = 0; d < WRT_MAX_DEPTH; d++) t.rays_per_depth[d] += a.rays_per_depth[d];
+            t.overflow_retries += a.overflow_retries;
+            t.gpu_ms = std::max(t.gpu_ms, a.gpu_ms);                   // the frame takes as long as its slowest GPU
+            t.shaft_culled_requests += a.shaft_culled_requests; t.unlit_skipped_requests += a.unlit_skipped_requests;
+            t.shadow_rays_traced += a.shadow_rays_traced;
+        }
+        *stats = t;
+    }
+    return 0;
 }
 
 } // extern "C"

@@ -1,9 +1,11 @@
 // main.cpp — drop-in for the reference's executable (src/main.cpp:12-68):
-//   wrt <config.txt>      ->  <config>.ppm  (ASCII P3, same bytes for the same pixels)
+//   wrt <config.txt> [--gpus N]   ->  <config>.ppm  (ASCII P3, same bytes for the same pixels)
 // Same behaviour around the hot path: the config grammar, the always-attempted
 // load of ./bunny.obj with the hard-coded material and transform, textures
 // resolved against the cwd, "ERROR: ..." + exit(-1) on bad input.  The render
-// itself runs on the GPU through CudaStrategy's context (no CPU fallback).
+// itself runs on the GPU through CudaStrategy's context (no CPU fallback); with
+// --gpus N (or WRT_GPUS=N) on GPUs 0..N-1 through wrt_multi_* (scene replicated, tiles
+// interleaved, pixels stored into GPU 0's frame over NVLink) — same image, byte for byte.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -20,10 +22,13 @@ int main(int argc, char* argv[]) {
         return 0;
     }
     bool glass = false, exhaustive = false;
+    int gpus = getenv("WRT_GPUS") ? atoi(getenv("WRT_GPUS")) : 1;
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "--glass")) glass = true;            // main.cpp:35-43 variant
         else if (!strcmp(argv[i], "--exhaustive")) exhaustive = true;
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
     }
+    if (gpus < 1) gpus = 1;
     wrt::HostScene scene;
     try {
         scene.parseConfigFile(argv[1]);
@@ -40,12 +45,28 @@ int main(int argc, char* argv[]) {
         exit(-1);
     }
     try {
-        wrt::CudaStrategy strategy(scene);
-        if (exhaustive) wrt_set_options(strategy.context(), WRT_TRAVERSAL_EXHAUSTIVE, WRT_DEFAULT_SEED, 0.f);
         std::vector<uint8_t> rgb((size_t)scene.width * scene.height * 3);
-        auto start = std::chrono::system_clock::now();
         WrtStats st;
-        if (wrt_render(strategy.context(), rgb.data(), &st) != 0) throw std::runtime_error(wrt_last_error());
+        std::chrono::system_clock::time_point start;
+        const int traversal = exhaustive ? WRT_TRAVERSAL_EXHAUSTIVE : WRT_TRAVERSAL_PRUNED;
+        if (gpus == 1) {
+            wrt::CudaStrategy strategy(scene);
+            if (exhaustive) wrt_set_options(strategy.context(), traversal, WRT_DEFAULT_SEED, 0.f);
+            start = std::chrono::system_clock::now();
+            if (wrt_render(strategy.context(), rgb.data(), &st) != 0) throw std::runtime_error(wrt_last_error());
+        } else {
+            std::vector<int> devices(gpus);
+            for (int i = 0; i < gpus; i++) devices[i] = i;
+            WrtMulti* m = nullptr;
+            if (wrt_multi_create(devices.data(), gpus, &m) != 0) throw std::runtime_error(wrt_last_error());
+            bool ok = wrt_multi_upload_scene(m, &scene.desc) == 0 && wrt_multi_set_camera(m, &scene.cam) == 0 &&
+                      wrt_multi_set_options(m, traversal, WRT_DEFAULT_SEED, 0.f) == 0;
+            start = std::chrono::system_clock::now();
+            ok = ok && wrt_multi_render(m, rgb.data(), &st) == 0;
+            std::string err = ok ? "" : wrt_last_error();
+            wrt_multi_destroy(m);
+            if (!ok) throw std::runtime_error(err);
+        }
         if (wrt_write_ppm_p3(scene.outputName().c_str(), scene.width, scene.height, rgb.data()) != 0)
             throw std::runtime_error(wrt_host_last_error());
         std::cout << "Generating is done successfully!\n";

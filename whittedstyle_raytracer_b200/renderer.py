@@ -179,3 +179,55 @@ class Renderer:
 
     def scatter_tiles(self, d_gathered: int, world: int, stride_bytes: int, d_image: int, stream: int | None = None):
         self.ctx._check(self.ctx.lib.wrt_scatter_tiles(self.ctx.h, d_gathered, world, stride_bytes, d_image, stream))
+
+
+class MultiRenderer:
+    """Renderer over several GPUs of one process (wrt_multi_*): scene replicated, interleaved tiles, every GPU's
+    resolve kernel stores its pixels into GPU devices[0]'s frame over NVLink.  render() -> (H, W, 3) uint8, identical to
+    the single-GPU image."""
+
+    def __init__(self, scene: Scene, devices):
+        self.lib = cabi.load_cuda()
+        self.h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        self._check(self.lib.wrt_multi_create(devs, len(devices), C.byref(self.h)))
+        self.scene = scene
+        self._check(self.lib.wrt_multi_upload_scene(self.h, scene.desc_ptr))
+        self._check(self.lib.wrt_multi_set_camera(self.h, scene.camera_ptr))
+        self.last_stats: dict = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CudaError(self.lib.wrt_last_error().decode(errors="replace"))
+
+    @property
+    def uses_peer_stores(self) -> bool:
+        return bool(self.lib.wrt_multi_uses_peer_stores(self.h))
+
+    def set_options(self, traversal=TRAVERSAL_PRUNED, seed=cabi.WRT_DEFAULT_SEED, queue_factor=0.0):
+        self._check(self.lib.wrt_multi_set_options(self.h, traversal, seed, queue_factor))
+
+    def upload(self):
+        self._check(self.lib.wrt_multi_upload_scene(self.h, self.scene.desc_ptr))
+        self._check(self.lib.wrt_multi_set_camera(self.h, self.scene.camera_ptr))
+
+    def render(self, out: np.ndarray | None = None) -> np.ndarray:
+        cam = self.scene.camera
+        if out is None:
+            out = np.zeros((cam.height, cam.width, 3), np.uint8)
+        st = cabi.WrtStats()
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else int(out)
+        self._check(self.lib.wrt_multi_render(self.h, ptr, C.byref(st)))
+        self.last_stats = stats_dict(st)
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.wrt_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

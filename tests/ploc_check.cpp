@@ -26,8 +26,12 @@ int main(int argc, char** argv) {
     PlocTree t{lo.data(), hi.data(), dlo.data(), dhi.data(), parent.data(), cnt.data()};
     // pass 0: leaves + Morton keys (k_bvh_leaves)
     std::vector<std::pair<uint64_t, int>> keys(n);
-    const float* bmin = s->nodes[0].pmin;
-    const float* bmax = s->nodes[0].pmax;
+    float bmin[3] = {3.4e38f, 3.4e38f, 3.4e38f}, bmax[3] = {-3.4e38f, -3.4e38f, -3.4e38f};      // centroid bounds (k_bvh_leaves)
+    for (int i = 0; i < s->n_nodes; i++) {
+        const WrtNode& nd = s->nodes[i];
+        if (nd.link >= 0 || i == 1) continue;
+        for (int k = 0; k < 3; k++) { float c = 0.5f * nd.pmin[k] + 0.5f * nd.pmax[k]; bmin[k] = std::min(bmin[k], c); bmax[k] = std::max(bmax[k], c); }
+    }
     std::vector<int> seen(n, 0);
     for (int i = 0; i < s->n_nodes; i++) {
         const WrtNode& nd = s->nodes[i];

@@ -14,6 +14,8 @@
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cfloat>
+
 #include "ploc_bvh.h"
 #include "../../../include/wrt_scene.h"
 
@@ -35,10 +37,22 @@ struct BuildBuffers {
     size_t cub_temp_bytes;
 };
 
+// float atomic min / max through the integer units (works for any mix of signs; the cell starts at +-FLT_MAX)
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.f) atomicMin((int*)addr, __float_as_int(v));
+    else atomicMax((unsigned*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v));
+    else atomicMin((unsigned*)addr, __float_as_uint(v));
+}
+
+// bounds[0..2] = min, bounds[3..5] = max of the leaf-box centroids (the Morton grid spans the centroids, not the
+// scene: measured on real rays, trees sorted on the centroid grid cost 4-5 % more node steps than the host's
+// binned-SAH tree, on the scene-box grid 9 %)
 __global__ void __launch_bounds__(256) k_bvh_leaves(const float4* __restrict__ ref_nodes, int n_nodes, int n_prims, BuildBuffers bb,
-                                                    float4* prim_box, float dil_rel, float dil_abs) {
-    const float4 rlo = ref_nodes[0], rhi = ref_nodes[1];
-    const float bmin[3] = {rlo.x, rlo.y, rlo.z}, bmax[3] = {rhi.x, rhi.y, rhi.z};
+                                                    float4* prim_box, float* bounds, float dil_rel, float dil_abs) {
+    float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
         if (i == 1) continue;                                  // padding record
         const float4 lo = ref_nodes[2 * (size_t)i], hi = ref_nodes[2 * (size_t)i + 1];
@@ -52,9 +66,33 @@ __global__ void __launch_bounds__(256) k_bvh_leaves(const float4* __restrict__ r
         prim_box[2 * (size_t)p] = make_float4(mn[0], mn[1], mn[2], 0.f);
         prim_box[2 * (size_t)p + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
         ploc_init_leaf(bb.tree, p, mn, mx, dil_rel, dil_abs);
-        const float c[3] = {0.5f * mn[0] + 0.5f * mx[0], 0.5f * mn[1] + 0.5f * mx[1], 0.5f * mn[2] + 0.5f * mx[2]};
-        bb.keys[0][p] = ploc_morton(c, bmin, bmax);
+        for (int k = 0; k < 3; k++) {
+            const float c = 0.5f * mn[k] + 0.5f * mx[k];
+            if (c < cmn[k]) cmn[k] = c;                        // (NaN centroids never enter the bounds)
+            if (c > cmx[k]) cmx[k] = c;
+        }
         bb.vals[0][p] = p;
+    }
+    for (int k = 0; k < 3; k++) {
+        float a = cmn[k], b = cmx[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a = fminf(a, __shfl_xor_sync(0xffffffffu, a, off));
+            b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, off));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (a < FLT_MAX) atomic_min_float(bounds + k, a);
+            if (b > -FLT_MAX) atomic_max_float(bounds + 3 + k, b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bvh_keys(int n_prims, BuildBuffers bb, const float* __restrict__ bounds) {
+    const float bmin[3] = {bounds[0], bounds[1], bounds[2]}, bmax[3] = {bounds[3], bounds[4], bounds[5]};
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_prims; p += gridDim.x * blockDim.x) {
+        const float4 lo = bb.tree.lo[p], hi = bb.tree.hi[p];
+        const float c[3] = {0.5f * lo.x + 0.5f * hi.x, 0.5f * lo.y + 0.5f * hi.y, 0.5f * lo.z + 0.5f * hi.z};
+        bb.keys[0][p] = ploc_morton(c, bmin, bmax);
     }
 }
 

@@ -54,15 +54,15 @@ __device__ __forceinline__ bool wrt_bounds_ok(bool ok, unsigned line) {
 enum CounterSlot {
     C_NRAYS = 0,                 // [WRT_MAX_DEPTH + 1] level d >= 1: reflection rays (first half of the level's arrays)
     C_NTRAYS = 112,              // [WRT_MAX_DEPTH + 1] level d >= 1: transmission rays (second half)
-    C_NPREQ = 16,                // [2] point-light shadow requests: queue 0 = level 0, queue 1 = levels 1..8
-    C_NDREQ = 32,                // [2] directional-light shadow requests, same two queues
+    C_NPREQ = 16,                // [WRT_QUEUES] point-light shadow requests per request queue (FrameBuffers::queue_of_level)
+    C_NDREQ = 32,                // [WRT_QUEUES] directional-light shadow requests, same queues
     C_VALID0 = 48,               // valid (non-padding) primary rays
     C_OVERFLOW = 49,             // set when a queue append was dropped
     C_NEMPTY = 50,               // queued soft-shadow requests whose candidate list came out empty (= 50 lit samples)
     C_NCULL = 128,               // [9] soft-shadow requests answered by the shaft test (shaft_cull.h), never queued
     C_NSKIP = 144,               // [9] point-light requests whose light terms vanish (dev_shade.cuh), never queued
     C_NDSKIP = 160,              // [9] the same for directional lights
-    C_POOL = 176,                // [2] fill level of the candidate-list pools (k_soft_lists)
+    C_POOL = 176,                // [WRT_QUEUES] fill level of the candidate-list pools (k_soft_lists)
     C_WORK = 192,                // [<= 32 x 2] work-distribution counters (64-bit), one per persistent launch
     C_TOTAL = 256
 };
@@ -72,6 +72,8 @@ struct TileMap : WrtTileMap {     // include/wrt_tiles.h
         return wrt_tilemap_slot_to_pixel(this, slot, rank_, &px, &py) != 0;
     }
 };
+
+#define WRT_QUEUES 3
 
 // Everything a kernel needs to (re)generate the primary ray of a slot: level-0 rays never exist in memory.
 struct PrimaryGen {
@@ -90,14 +92,17 @@ struct FrameBuffers {
     float4* surf;                // 4 per node: {pos, prim} {nDir, material} {Od, -} {ray origin, -}
     float4* node_a;              // per node {local.rgb -> colour.rgb, fr}
     float4* node_b;              // per node {kT, childR, childT, composite flag}  (children as node ids)
-    float4* preq_o[2];           // point-light request: {shadow ray origin, node}
-    uint4*  preq_k[2];           //                      {light, pixel, path, -}
-    float4* dreq_o[2];           // directional request: {pos, node}
-    uint4*  dreq_k[2];           //                      {light, self prim, -, -}
+    // Shadow requests go to WRT_QUEUES queues by ray-tree level: queue 0 = level 0, queue 1 = levels 1..k, queue 2 = levels
+    // k+1..8.  Each queue gets ONE set of shadow launches, started as soon as its last level's surface stage is done.
+    float4* preq_o[WRT_QUEUES];  // point-light request: {shadow ray origin, node}
+    uint4*  preq_k[WRT_QUEUES];  //                      {light, pixel, path, -}
+    float4* dreq_o[WRT_QUEUES];  // directional request: {pos, node}
+    uint4*  dreq_k[WRT_QUEUES];  //                      {light, self prim, -, -}
+    unsigned char queue_of_level[WRT_MAX_DEPTH + 3];
     float*  coeff;               // [node * n_lights + light]
     unsigned* counters;
     unsigned cap0, capd;         // slots of level 0 (batch capacity) and of every deeper level
-    unsigned preq_cap[2], dreq_cap[2];
+    unsigned preq_cap[WRT_QUEUES], dreq_cap[WRT_QUEUES];
     unsigned n_node_cap;         // cap0 + (WRT_MAX_DEPTH-1) * capd
 };
 
@@ -186,7 +191,7 @@ __device__ __forceinline__ void surface_warp(const DevScene& s, const FrameBuffe
                                              f3 org, f3 dir, unsigned pixel, unsigned path, float hit_t, int prim,
                                              float b1, float b2, unsigned slot) {
     const unsigned child_half = fb.capd / 2;
-    const int q = level == 0 ? 0 : 1;
+    const int q = fb.queue_of_level[level];
     float4* nray_o = fb.ray_o[(level + 1) & 1];
     float4* nray_d = fb.ray_d[(level + 1) & 1];
     unsigned* overflow = fb.counters + C_OVERFLOW;
@@ -573,70 +578,146 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 #define WRT_LIST_CAP 192
 #endif
 struct SoftListBuffers {
-    int*  scratch;        // WRT_LIST_CAP ints per thread of the grid: the walk writes here, then compacts into the pool
-    int*  pool;           // compacted lists
+    int*  scratch;        // WRT_LIST_CAP ints per thread of the grid: a walk writes here, then copies into the pool
+    float* shafts;        // WRT_LISTS_CHUNK x 10 floats per warp of the grid: the shafts of the warp's current chunk
+    int*  pool;           // the lists
     int2* ref;            // per request: {pool offset, count}
     unsigned pool_cap;
+    unsigned region_per_request;   // pool entries a warp reserves per request of its chunk (one atomic per chunk)
 };
 #ifndef WRT_LIST_CHUNK_PASSES
 #define WRT_LIST_CHUNK_PASSES 8
 #endif
+#ifndef WRT_LISTS_CHUNK
+#define WRT_LISTS_CHUNK 128
+#endif
+#ifndef WRT_LISTS_REFILL
+#define WRT_LISTS_REFILL 8
+#endif
 
-// (Phase 1 as a run_queue query with per-lane refill was tried — walk lengths differ a lot, 7-13 of 32 lanes are
-// active — and was slower, 19.5 vs 18.3 ms per frame: the refilled lanes run the ~200-instruction shaft set-up a few
-// lanes at a time, and lists allocated out of request order scatter phase 2's reads.)
+// One lane walks one request's shaft, but walk lengths differ a lot (3 ... 400 node pairs; ncu: 8.6 of 32 lanes
+// active when every lane takes one request and the warp waits for the longest).  So a warp owns WRT_LISTS_CHUNK
+// consecutive requests at a time:
+//   A. all lanes build the chunk's shafts (wrt_shaft_make, ~200 instructions, fully converged) into a per-warp slot
+//      array (global scratch, L1-resident);
+//   B. lanes walk; a lane that finishes copies its list into the pool and takes the chunk's next request
+//      (WRT_LISTS_REFILL idle lanes trigger a hand-out: a slot load, no set-up code on a few lanes).
+// Pool space: the warp reserves region_per_request entries per request of the chunk with ONE global atomic and lanes
+// sub-allocate from the region through a shared-memory cursor; a list that does not fit takes its own global
+// allocation; an exhausted pool means count = -1 (per-ray walk).  Lists of a chunk stay close together in the pool.
+// (An earlier refill attempt through run_queue — set-up code on the refilled lanes only — was slower than no refill.)
 __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                               int work_slot, int stack_rows, SoftListBuffers lb) {
     extern __shared__ int smem[];
+    __shared__ unsigned s_used[4];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
-    int* mine = lb.scratch + (((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane) * WRT_LIST_CAP;
+    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    int* mine = lb.scratch + (gwarp * 32 + lane) * WRT_LIST_CAP;
+    float* slots = lb.shafts + gwarp * (size_t)WRT_LISTS_CHUNK * 10;
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
     unsigned* pool_head = fb.counters + C_POOL + q;
+    unsigned n_empty = 0;
     while (true) {
         unsigned long long claimed = 0;
-        if (lane == 0) claimed = atomicAdd(work, 32ull);
+        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)WRT_LISTS_CHUNK);
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
         if (claimed >= nreq) break;
-        const unsigned req = (unsigned)claimed + lane;
-        int cnt = 0;
-        if (req < nreq) {
-            cnt = -1;
-            float4 o4 = fb.preq_o[q][req];
-            uint4 k = fb.preq_k[q][req];
+        const unsigned base = (unsigned)claimed;
+        const unsigned chunk = nreq - base < (unsigned)WRT_LISTS_CHUNK ? nreq - base : (unsigned)WRT_LISTS_CHUNK;
+        // ---- A: shafts of the chunk ----
+        for (unsigned r = lane; r < chunk; r += 32) {
+            float4 o4 = fb.preq_o[q][base + r];
+            uint4 k = fb.preq_k[q][base + r];
             const WrtLight* L = s.lights + k.x;
             float tri[9];
             for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
             const float o[3] = {o4.x, o4.y, o4.z};
             WrtShaft sh;
-            if (wrt_shaft_make(o, tri, &sh))
-                cnt = wrt_shaft_candidates(s.onodes, s.n_nodes, &sh, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+            const bool ok = wrt_shaft_make(o, tri, &sh);
+            float* d = slots + (size_t)r * 10;
+            d[0] = sh.o[0]; d[1] = sh.o[1]; d[2] = sh.o[2];
+            d[3] = sh.ilo[0]; d[4] = sh.ilo[1]; d[5] = sh.ilo[2];
+            d[6] = sh.ihi[0]; d[7] = sh.ihi[1]; d[8] = sh.ihi[2];
+            d[9] = __int_as_float(ok ? (sh.octant | (sh.use << 3)) : -1);
         }
-        // pool space for the warp's lists: one atomic
-        const int n = cnt > 0 ? cnt : 0;
-        int incl = n;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= (unsigned)off) incl += v;
+        // ---- pool region of the chunk: one atomic ----
+        unsigned region = 0;
+        if (lane == 0) {
+            region = atomicAdd(pool_head, chunk * lb.region_per_request);
+            s_used[warp] = 0u;
         }
-        const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
-        unsigned base = 0;
-        if (lane == 31 && total > 0) base = atomicAdd(pool_head, total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        const unsigned off = base + (unsigned)(incl - n);
-        if (total > 0 && (base > lb.pool_cap || total > lb.pool_cap - base) && cnt > 0) cnt = -1;     // pool full: per-ray walk
-        if (req < nreq) {
-            for (int i = 0; i < cnt; i++)
-                if (WRT_IN_BOUNDS(off + i, lb.pool_cap)) lb.pool[off + i] = mine[i];
-            if (WRT_IN_BOUNDS(req, fb.preq_cap[q])) lb.ref[req] = make_int2((int)off, cnt);
+        region = __shfl_sync(0xffffffffu, region, 0);
+        unsigned region_size = chunk * lb.region_per_request;
+        if (region >= lb.pool_cap) region_size = 0;
+        else if (region_size > lb.pool_cap - region) region_size = lb.pool_cap - region;
+        __syncwarp();
+        // ---- B: walks with refill ----
+        unsigned next = 0;                                   // warp-uniform: requests of the chunk handed out so far
+        bool active = false;
+        unsigned my = 0;
+        WrtShaft sh;
+        WrtShaftWalk w;
+        w.nodes = s.onodes; w.cur = 0; w.sp = 0; w.n = 0;
+        while (true) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (next < chunk && (idle == 0xffffffffu || __popc(idle) >= WRT_LISTS_REFILL)) {
+                const unsigned cand = next + __popc(idle & lt_mask);
+                next += __popc(idle);
+                if (!active && cand < chunk) {
+                    my = cand;
+                    const float* d = slots + (size_t)my * 10;
+                    const int ou = __float_as_int(d[9]);
+                    int rc = -1;
+                    if (ou >= 0) {
+                        sh.o[0] = d[0]; sh.o[1] = d[1]; sh.o[2] = d[2];
+                        sh.ilo[0] = d[3]; sh.ilo[1] = d[4]; sh.ilo[2] = d[5];
+                        sh.ihi[0] = d[6]; sh.ihi[1] = d[7]; sh.ihi[2] = d[8];
+                        sh.octant = ou & 7; sh.use = ou >> 3;
+                        rc = wrt_shaft_walk_begin(s.onodes, s.n_nodes, &sh, &w);
+                    }
+                    if (rc == 1) active = true;
+                    else {                                   // answered without a walk: -1 = ray by ray, 0 = empty list
+                        if (WRT_IN_BOUNDS(base + my, fb.preq_cap[q])) lb.ref[base + my] = make_int2(0, rc);
+                        if (rc == 0) ++n_empty;
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) {
+                if (next >= chunk) break;
+                continue;
+            }
+#pragma unroll 1
+            for (int it = 0; it < 4; it++) {
+                if (!active) continue;
+                const int rc = wrt_shaft_walk_step(&sh, &w, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+                if (rc == 1) continue;
+                // finished: copy the list into the pool
+                active = false;
+                int cnt = rc < 0 ? -1 : w.n;
+                unsigned dst = 0;
+                if (cnt > 0) {
+                    const unsigned off = atomicAdd(&s_used[warp], (unsigned)cnt);
+                    if (off <= region_size && (unsigned)cnt <= region_size - off) dst = region + off;
+                    else if (*(volatile unsigned*)pool_head < lb.pool_cap) {            // region used up: own allocation
+                        dst = atomicAdd(pool_head, (unsigned)cnt);
+                        if (dst >= lb.pool_cap || (unsigned)cnt > lb.pool_cap - dst) cnt = -1;
+                    } else cnt = -1;                                                        // pool full: per-ray walk
+                    for (int i = 0; i < cnt; i++)
+                        if (WRT_IN_BOUNDS(dst + i, lb.pool_cap)) lb.pool[dst + i] = mine[i];
+                }
+                if (WRT_IN_BOUNDS(base + my, fb.preq_cap[q])) lb.ref[base + my] = make_int2((int)dst, cnt);
+                // an empty list is an empty shaft: the ray kernel answers "lit" without building the rays (statistics only here)
+                if (cnt == 0) ++n_empty;
+            }
         }
-        // an empty list is an empty shaft: the ray kernel answers "lit" without building the rays (statistics only here)
-        const unsigned n_empty = __popc(__ballot_sync(0xffffffffu, req < nreq && cnt == 0));
-        if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);
+        __syncwarp();
     }
+    n_empty = __reduce_add_sync(0xffffffffu, n_empty);
+    if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);
 }
 
 __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,

@@ -147,48 +147,72 @@ WRT_SHAFT_HD bool wrt_shaft_may_hit_lb(const WrtShaft* sh, const float4 nearp, c
 // to out[0 .. n) nearest-first (by the entry lower bound).  A sample ray of the request that is not
 // axis-degenerate tests exactly the primitives whose own box it hits and all of those are
 // in the list, so "any list member blocks the ray" equals the any-hit traversal's answer.
-// Returns n, or -1 when the list would exceed out_cap or the walk's stack would overflow (the request is then
-// traced ray by ray).  stack[k * stack_stride], k < stack_cap, is the caller's traversal stack.
+// The walk is a resumable state machine (the list kernel interleaves the walks of a warp's lanes and refills lanes
+// as they finish): wrt_shaft_walk_begin, then wrt_shaft_walk_step until it stops returning 1.
+// stack[k * stack_stride], k < stack_cap, is the caller's traversal stack.
+typedef struct WrtShaftWalk {
+    const float4* nodes;   // the shaft's octant copy of the tree
+    int cur, sp, n;        // node pair to visit next, stack fill, list length so far
+} WrtShaftWalk;
+
+// 1 = walk started; 0 = finished at once with an empty list (no tree); -1 = give up (trace the request ray by ray).
+WRT_SHAFT_HD int wrt_shaft_walk_begin(const float4* onodes, int n_nodes, const WrtShaft* sh, WrtShaftWalk* w) {
+    w->sp = 0; w->n = 0; w->cur = 0; w->nodes = onodes;
+    if (n_nodes <= 0) return 0;
+    w->nodes = onodes + (size_t)sh->octant * 2 * (size_t)n_nodes;
+    union { float f; int i; } u;
+    u.f = WRT_SHAFT_LD4(w->nodes).w;
+    w->cur = u.i;
+    return w->cur < 0 ? -1 : 1;                                           // lone primitive: tested without its box
+}
+
+// One node pair.  1 = call again; 0 = done, out[0 .. w->n) is the list; -1 = the list would exceed out_cap or the
+// stack would overflow.
+WRT_SHAFT_HD int wrt_shaft_walk_step(const WrtShaft* sh, WrtShaftWalk* w, int* stack, int stack_stride, int stack_cap,
+                                     int* out, int out_cap) {
+    const float4* nd = w->nodes + 2 * (size_t)w->cur;
+    float4 l0 = WRT_SHAFT_LD4(nd), l1 = WRT_SHAFT_LD4(nd + 1), r0 = WRT_SHAFT_LD4(nd + 2), r1 = WRT_SHAFT_LD4(nd + 3);
+    float tl, tr;
+    bool hl = wrt_shaft_may_hit_lb(sh, l0, l1, &tl), hr = wrt_shaft_may_hit_lb(sh, r0, r1, &tr);
+    union { float f; int i; } u;
+    u.f = l0.w; const int linkL = u.i;
+    u.f = r0.w; const int linkR = u.i;
+    const bool right_first = hl && hr && tr < tl;
+    int n = w->n;
+    // leaves: into the list, nearer one first
+    if (hl && linkL < 0 && hr && linkR < 0) {
+        if (n + 2 > out_cap) return -1;
+        out[n++] = right_first ? ~linkR : ~linkL;
+        out[n++] = right_first ? ~linkL : ~linkR;
+        hl = false; hr = false;
+    } else {
+        if (hl && linkL < 0) { if (n == out_cap) return -1; out[n++] = ~linkL; hl = false; }
+        if (hr && linkR < 0) { if (n == out_cap) return -1; out[n++] = ~linkR; hr = false; }
+    }
+    w->n = n;
+    if (hl && hr) {
+        if (w->sp == stack_cap) return -1;
+        stack[w->sp * stack_stride] = right_first ? linkL : linkR;
+        ++w->sp;
+        w->cur = right_first ? linkR : linkL;
+    } else if (hl) w->cur = linkL;
+    else if (hr) w->cur = linkR;
+    else {
+        if (w->sp == 0) return 0;
+        --w->sp;
+        w->cur = stack[w->sp * stack_stride];
+    }
+    return 1;
+}
+
+// The whole walk in one call.  Returns the list length, or -1 (see wrt_shaft_walk_step).
 WRT_SHAFT_HD int wrt_shaft_candidates(const float4* onodes, int n_nodes, const WrtShaft* sh, int* stack, int stack_stride,
                                       int stack_cap, int* out, int out_cap) {
-    if (n_nodes <= 0) return 0;
-    const float4* nodes = onodes + (size_t)sh->octant * 2 * (size_t)n_nodes;
-    union { float f; int i; } w;
-    w.f = WRT_SHAFT_LD4(nodes).w;
-    int cur = w.i;
-    if (cur < 0) return -1;                                               // lone primitive: tested without its box
-    int sp = 0, n = 0;
-    while (true) {
-        const float4* nd = nodes + 2 * (size_t)cur;
-        float4 l0 = WRT_SHAFT_LD4(nd), l1 = WRT_SHAFT_LD4(nd + 1), r0 = WRT_SHAFT_LD4(nd + 2), r1 = WRT_SHAFT_LD4(nd + 3);
-        float tl, tr;
-        bool hl = wrt_shaft_may_hit_lb(sh, l0, l1, &tl), hr = wrt_shaft_may_hit_lb(sh, r0, r1, &tr);
-        w.f = l0.w; const int linkL = w.i;
-        w.f = r0.w; const int linkR = w.i;
-        const bool right_first = hl && hr && tr < tl;
-        // leaves: into the list, nearer one first
-        if (hl && linkL < 0 && hr && linkR < 0) {
-            if (n + 2 > out_cap) return -1;
-            out[n++] = right_first ? ~linkR : ~linkL;
-            out[n++] = right_first ? ~linkL : ~linkR;
-            hl = false; hr = false;
-        } else {
-            if (hl && linkL < 0) { if (n == out_cap) return -1; out[n++] = ~linkL; hl = false; }
-            if (hr && linkR < 0) { if (n == out_cap) return -1; out[n++] = ~linkR; hr = false; }
-        }
-        if (hl && hr) {
-            if (sp == stack_cap) return -1;
-            stack[sp * stack_stride] = right_first ? linkL : linkR;
-            ++sp;
-            cur = right_first ? linkR : linkL;
-        } else if (hl) cur = linkL;
-        else if (hr) cur = linkR;
-        else {
-            if (sp == 0) return n;
-            --sp;
-            cur = stack[sp * stack_stride];
-        }
-    }
+    WrtShaftWalk w;
+    int rc = wrt_shaft_walk_begin(onodes, n_nodes, sh, &w);
+    if (rc <= 0) return rc;
+    while ((rc = wrt_shaft_walk_step(sh, &w, stack, stack_stride, stack_cap, out, out_cap)) == 1) {}
+    return rc < 0 ? -1 : w.n;
 }
 
 // True when no leaf box of the tree can be hit by any ray of the shaft.

@@ -6,6 +6,9 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,7 +54,7 @@ struct WrtContext {
     // levels' shadow kernels, combine + resolve) and `side` (level 0's shadow + shade kernels).  A caller-provided stream
     // (wrt_render_device) is joined to them by two events, nothing else runs on it.
     cudaStream_t chain = nullptr, side = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_lvl0 = nullptr, ev_side = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_lvl0 = nullptr, ev_mid = nullptr, ev_side = nullptr, ev_out = nullptr;
     bool overlap = true;
 
     // scene
@@ -80,7 +83,7 @@ struct WrtContext {
     bool soft_lists = true;            // soft shadows: per-request candidate lists (k_soft_lists + k_soft_list_rays) instead of per-ray walks
     long long list_pool_cap_override = 0;
     int shaft_cull_max_level = 0;      // deepest ray-tree level whose surface stage runs the shaft test (when lists are on)
-    wrt::SoftListBuffers list_bufs[2] = {};
+    wrt::SoftListBuffers list_bufs[WRT_QUEUES] = {};
     wrt::FastBvhBuilder fbvh;          // WRT_HOST_BVH=1 only: the host's binned-SAH build (development A/B)
     bool host_bvh = false;
     uint8_t* h_stage = nullptr;        // pinned staging of the scene description: one H2D per upload
@@ -93,6 +96,8 @@ struct WrtContext {
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
     int trace_blocks_per_sm = 10;      // persistent shadow / unfused closest-hit kernels
     bool shade0_separate = true;       // level 0 is shaded by its own launch on the side stream (else inside combine)
+    int deep_split = 3;                // request queues: level 0 | levels 1..deep_split | deeper (8: one deep queue)
+    int fb_split = -1;
     bool small_batch_full_levels = true; // automatic sizing: batches under 1 M slots get full-size deep levels
     long long max_batch = 1ll << 25;   // primary slots per batch (8K = 33.2 M slots fits)
     long long learned_batch = 1ll << 40; // a batch size that overflowed with the deep levels at their largest: later frames of
@@ -222,7 +227,7 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
     const wrt::DevScene& ds = c->ds;
     const unsigned capd = deep_slots_for(c, slots);
     if (c->batch_slots >= slots && c->deep_slots >= capd && c->fb_lights == ds.n_lights && c->fb_point == ds.n_point_lights &&
-        c->fb_dir == ds.n_dir_lights)
+        c->fb_dir == ds.n_dir_lights && c->fb_split == c->deep_split)
         return 0;
     CK(cudaDeviceSynchronize());
     free_frame(c);
@@ -236,8 +241,14 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
     auto req_cap = [](unsigned long long nodes, int lights) {
         return (unsigned)std::min<unsigned long long>(nodes * (unsigned long long)std::max(1, lights), 0xffffff00ull);
     };
-    fb.preq_cap[0] = req_cap(cap0, ds.n_point_lights); fb.preq_cap[1] = req_cap(deep_nodes, ds.n_point_lights);
-    fb.dreq_cap[0] = req_cap(cap0, ds.n_dir_lights);   fb.dreq_cap[1] = req_cap(deep_nodes, ds.n_dir_lights);
+    (void)deep_nodes;
+    const int split = std::max(1, std::min(WRT_MAX_DEPTH - 1, c->deep_split));
+    const unsigned long long q_nodes[WRT_QUEUES] = {cap0, (unsigned long long)split * capd, (unsigned long long)(WRT_MAX_DEPTH - 1 - split) * capd};
+    for (int q = 0; q < WRT_QUEUES; q++) {
+        fb.preq_cap[q] = req_cap(std::max(q_nodes[q], 1ull), ds.n_point_lights);
+        fb.dreq_cap[q] = req_cap(std::max(q_nodes[q], 1ull), ds.n_dir_lights);
+    }
+    for (int d = 0; d < WRT_MAX_DEPTH; d++) fb.queue_of_level[d] = (unsigned char)(d == 0 ? 0 : (d <= split ? 1 : 2));
     for (int k = 0; k < 2; k++) {
         if (frame_alloc(c, &fb.ray_o[k], capd)) return 1;
         if (frame_alloc(c, &fb.ray_d[k], capd)) return 1;
@@ -247,7 +258,7 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
     if (frame_alloc(c, &fb.node_a, (size_t)nodes64)) return 1;
     if (frame_alloc(c, &fb.node_b, (size_t)nodes64)) return 1;
     if (frame_alloc(c, &fb.coeff, (size_t)nodes64 * std::max(1, ds.n_lights))) return 1;
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < WRT_QUEUES; q++) {
         if (frame_alloc(c, &fb.preq_o[q], ds.n_point_lights ? fb.preq_cap[q] : 1)) return 1;
         if (frame_alloc(c, &fb.preq_k[q], ds.n_point_lights ? fb.preq_cap[q] : 1)) return 1;
         if (frame_alloc(c, &fb.dreq_o[q], ds.n_dir_lights ? fb.dreq_cap[q] : 1)) return 1;
@@ -258,20 +269,26 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
     // walk scratch per thread, list pool, per-request {offset, count}.  A full pool only means per-ray walks for the
     // remaining requests.  Level-0 requests that survive the shaft test at spawn time have 1-2 candidates; deep-level
     // ones (origins on the bunny) ~30.
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < WRT_QUEUES; q++) {
         wrt::SoftListBuffers& lb = c->list_bufs[q];
-        const unsigned long long per_req = q == 0 ? 2ull : 12ull;
+        // Level-0 requests that survive the shaft test at spawn time have 1-2 candidates, deep-level ones (origins on
+        // the bunny) ~30.  A warp reserves region_per_request entries per request of its chunk; the pool holds that for
+        // half of the queue's capacity (queues run far below capacity; a full pool only means per-ray walks).
+        lb.region_per_request = q == 0 ? 4u : 32u;
+        const unsigned long long per_req = q == 0 ? 4ull : 16ull;
         lb.pool_cap = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(8ull << 20, per_req * fb.preq_cap[q]), 1ull << 30);
         if (!ds.n_point_lights || ds.shadow_type == 0) lb.pool_cap = 64;
         if (c->list_pool_cap_override > 0) lb.pool_cap = (unsigned)c->list_pool_cap_override;     // tests: force the pool-full path
         const bool lists_possible = ds.n_point_lights && ds.shadow_type != 0;
         if (frame_alloc(c, &lb.scratch, lists_possible ? (size_t)c->num_sms * c->trace_blocks_per_sm * 128 * WRT_LIST_CAP : 1)) return 1;
+        if (frame_alloc(c, &lb.shafts, lists_possible ? (size_t)c->num_sms * c->trace_blocks_per_sm * 4 * WRT_LISTS_CHUNK * 10 : 1)) return 1;
         if (frame_alloc(c, &lb.pool, lb.pool_cap)) return 1;
         if (frame_alloc(c, &lb.ref, lists_possible ? fb.preq_cap[q] : 1)) return 1;
     }
     c->batch_slots = slots;
     c->deep_slots = capd;
     c->fb_lights = ds.n_lights; c->fb_point = ds.n_point_lights; c->fb_dir = ds.n_dir_lights;
+    c->fb_split = c->deep_split;
     return 0;
 }
 
@@ -409,16 +426,25 @@ int enqueue_batch(WrtContext* c, long long slot0, unsigned n, uint8_t* d_image, 
         CK(cudaEventRecord(c->ev_lvl0, st));
         CK(cudaStreamWaitEvent(ss, c->ev_lvl0, 0));
     }
-    // level 0's shadow + shade kernels run beside the deep chain: a deep level holds few, long, incoherent rays and
-    // leaves most of the SMs idle; a persistent traversal kernel ends with its longest ray
+    // Level 0's shadow + shade kernels run beside the deep chain on the side stream, then the shadow kernels of levels
+    // 1..split (queue 1) as soon as those levels' surface stages are done; the chain goes on with the deeper levels and
+    // ends with their shadow kernels (queue 2).  A deep level holds few, long, incoherent rays and leaves most of the SMs
+    // idle, and a persistent traversal kernel ends with its longest ray: the shadow work fills those gaps.
     if (enqueue_shadows(c, ss, 0, work_seq)) return 1;
     if (c->shade0_separate) {
         LaunchScope ls(c, ss, F_SHADE);
         k_shade<<<wide_grid, 256, 0, ss>>>(ds, fb, n, 0, 0);
     }
+    const int split = std::max(1, std::min(WRT_MAX_DEPTH - 1, c->deep_split));
+    for (int d = 1; d <= split; d++) level_kernels(d);
+    if (overlap) {
+        CK(cudaEventRecord(c->ev_mid, st));
+        CK(cudaStreamWaitEvent(ss, c->ev_mid, 0));
+    }
+    if (enqueue_shadows(c, ss, 1, work_seq)) return 1;
     if (overlap) CK(cudaEventRecord(c->ev_side, ss));
-    for (int d = 1; d < WRT_MAX_DEPTH; d++) level_kernels(d);
-    if (enqueue_shadows(c, st, 1, work_seq)) return 1;
+    for (int d = split + 1; d < WRT_MAX_DEPTH; d++) level_kernels(d);
+    if (split < WRT_MAX_DEPTH - 1 && enqueue_shadows(c, st, 2, work_seq)) return 1;
     if (overlap) CK(cudaStreamWaitEvent(st, c->ev_side, 0));
     {
         LaunchScope ls(c, st, F_COMBINE);
@@ -444,7 +470,8 @@ void add_batch_stats(WrtContext* c, const unsigned* cnt) {
     // requests answered without tracing count like the reference counts them (it traces them)
     int64_t culled = 0, skip_p = 0, skip_d = 0;
     for (int d = 0; d < WRT_MAX_DEPTH; d++) { culled += cnt[wrt::C_NCULL + d]; skip_p += cnt[wrt::C_NSKIP + d]; skip_d += cnt[wrt::C_NDSKIP + d]; }
-    const int64_t queued_p = (int64_t)cnt[wrt::C_NPREQ] + cnt[wrt::C_NPREQ + 1], queued_d = (int64_t)cnt[wrt::C_NDREQ] + cnt[wrt::C_NDREQ + 1];
+    int64_t queued_p = 0, queued_d = 0;
+    for (int q = 0; q < WRT_QUEUES; q++) { queued_p += cnt[wrt::C_NPREQ + q]; queued_d += cnt[wrt::C_NDREQ + q]; }
     const int64_t empty = cnt[wrt::C_NEMPTY];          // queued, but their candidate list came out empty: no rays built
     const int64_t p = queued_p + culled + skip_p, q = queued_d + skip_d;
     const int64_t per = ds.shadow_type ? WRT_SOFT_SAMPLES : 1;
@@ -629,7 +656,7 @@ int wrt_create(int device, WrtContext** out) {
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     bool ev_ok = cudaStreamCreateWithPriority(&c->chain, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
                  cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_least) == cudaSuccess;
-    for (cudaEvent_t* e : {&c->ev_in, &c->ev_lvl0, &c->ev_side, &c->ev_out})
+    for (cudaEvent_t* e : {&c->ev_in, &c->ev_lvl0, &c->ev_mid, &c->ev_side, &c->ev_out})
         ev_ok = ev_ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
     if (!ev_ok ||
         cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess ||
@@ -667,6 +694,7 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_HOST_BVH")) c->host_bvh = atoi(e) != 0;
     if (const char* e = getenv("WRT_SHADE0_SEPARATE")) c->shade0_separate = atoi(e) != 0;
+    if (const char* e = getenv("WRT_DEEP_SPLIT")) c->deep_split = std::max(1, std::min(WRT_MAX_DEPTH - 1, atoi(e)));
     if (const char* e = getenv("WRT_DEEP_FACTOR")) { c->deep_factor = std::max(0.001f, std::min(2.f, (float)atof(e))); c->small_batch_full_levels = false; }
     if (const char* e = getenv("WRT_MAX_BATCH")) c->max_batch = std::max(64ll, (atoll(e) + 31) / 32 * 32);   // tests: force multi-batch frames
     *out = c;
@@ -687,7 +715,7 @@ void wrt_destroy(WrtContext* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
-    for (cudaEvent_t e : {c->ev_in, c->ev_lvl0, c->ev_side, c->ev_out}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev_in, c->ev_lvl0, c->ev_mid, c->ev_side, c->ev_out}) if (e) cudaEventDestroy(e);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->chain) cudaStreamDestroy(c->chain);
     delete c;
@@ -778,10 +806,16 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         dev_alloc(c, (size_t)s->n_materials * 48, (void**)&mats) || dev_alloc(c, (size_t)np * 32, (void**)&pbox) ||
         dev_alloc(c, (size_t)nn * 32, (void**)&fnodes) || dev_alloc(c, (size_t)nn * 32, (void**)&dnodes) ||
         dev_alloc(c, (size_t)nn * 32 * 8, (void**)&onodes) || dev_alloc(c, (size_t)nn * 32 * 8, (void**)&ronodes) ||
-        dev_alloc(c, (wrt::BS_TOTAL + 8) * sizeof(int), (void**)&d_flags))
+        dev_alloc(c, (wrt::BS_TOTAL + 16) * sizeof(int), (void**)&d_flags))
         return 1;
     int* d_state = d_flags + 8;
+    float* d_bounds = (float*)(d_flags + 8 + wrt::BS_TOTAL);           // centroid bounds of the leaf boxes (min xyz, max xyz)
     CK(cudaMemsetAsync(d_flags, 0, (wrt::BS_TOTAL + 8) * sizeof(int), st));
+    {
+        const float init[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f, 0.f};
+        memcpy(c->h_counters + wrt::C_TOTAL + 32, init, sizeof init);   // (pinned; the copy below reads it asynchronously)
+        CK(cudaMemcpyAsync(d_bounds, c->h_counters + wrt::C_TOTAL + 32, sizeof init, cudaMemcpyHostToDevice, st));
+    }
     const int wide = c->num_sms * 4;
     if (np > 0) {
         ++c->launches;
@@ -818,9 +852,10 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
             return 1;
         bb.state = d_state;
         bb.cub_temp_bytes = cub_bytes;
-        c->launches += 4;
+        c->launches += 5;
         CK(cudaMemsetAsync(bb.tree.cnt, 0, (size_t)np * 4, st));
-        wrt::k_bvh_leaves<<<std::min(wide, (nn + 255) / 256), 256, 0, st>>>(ds.nodes, nn, np, bb, pbox, 1e-3f, 1e-4f);
+        wrt::k_bvh_leaves<<<std::min(wide, (nn + 255) / 256), 256, 0, st>>>(ds.nodes, nn, np, bb, pbox, d_bounds, 1e-3f, 1e-4f);
+        wrt::k_bvh_keys<<<std::min(wide, (np + 255) / 256), 256, 0, st>>>(np, bb, d_bounds);
         CK(cub::DeviceRadixSort::SortPairs(bb.cub_temp, cub_bytes, bb.keys[0], bb.keys[1], bb.vals[0], bb.vals[1], np, 0, 63, st));
         {
             const int* sorted = bb.vals[1];
@@ -1188,27 +1223,62 @@ struct WrtMulti {
     std::vector<uint8_t*> d_packed;      // fallback path only (per device)
     std::vector<size_t> packed_bytes;
     std::vector<std::string> errors;
+    // one persistent host thread per GPU 1..n-1 (GPU 0 is driven by the caller's thread): a frame is a few milliseconds,
+    // thread creation per call would show
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<int(int)> job;
+    std::vector<int> rc;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool quit = false;
 };
 
 namespace {
 
-// Runs fn(rank) on one host thread per GPU (rank 0 on the caller's thread) and collects the error strings.
-template <class F>
-int multi_run(WrtMulti* m, F fn) {
+void multi_worker(WrtMulti* m, int r) {
+    uint64_t seen = 0;
+    while (true) {
+        std::function<int(int)> job;
+        {
+            std::unique_lock<std::mutex> lk(m->mu);
+            m->cv_go.wait(lk, [&] { return m->quit || m->generation != seen; });
+            if (m->quit) return;
+            seen = m->generation;
+            job = m->job;
+        }
+        const int rc = job(r);
+        {
+            std::lock_guard<std::mutex> lk(m->mu);
+            m->rc[r] = rc;
+            if (rc) m->errors[r] = g_err;               // g_err is thread_local
+            if (--m->pending == 0) m->cv_done.notify_one();
+        }
+    }
+}
+
+// Runs fn(rank) for every GPU (rank 0 on the caller's thread) and collects the error strings.
+int multi_run(WrtMulti* m, std::function<int(int)> fn) {
     const int n = (int)m->ctx.size();
-    std::vector<int> rc(n, 0);
-    m->errors.assign(n, std::string());
-    std::vector<std::thread> th;
-    for (int r = 1; r < n; r++)
-        th.emplace_back([&, r] {
-            rc[r] = fn(r);
-            if (rc[r]) m->errors[r] = g_err;           // g_err is thread_local
-        });
-    rc[0] = fn(0);
-    if (rc[0]) m->errors[0] = g_err;
-    for (std::thread& t : th) t.join();
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->rc.assign(n, 0);
+        m->errors.assign(n, std::string());
+        m->job = fn;
+        m->pending = n - 1;
+        ++m->generation;
+    }
+    m->cv_go.notify_all();
+    const int rc0 = fn(0);
+    {
+        std::unique_lock<std::mutex> lk(m->mu);
+        m->cv_done.wait(lk, [&] { return m->pending == 0; });
+        m->rc[0] = rc0;
+        if (rc0) m->errors[0] = g_err;
+    }
     for (int r = 0; r < n; r++)
-        if (rc[r]) return fail("GPU " + std::to_string(m->devices[r]) + ": " + m->errors[r]);
+        if (m->rc[r]) return fail("GPU " + std::to_string(m->devices[r]) + ": " + m->errors[r]);
     return 0;
 }
 
@@ -1241,12 +1311,19 @@ int wrt_multi_create(const int* devices, int n, WrtMulti** out) {
         cudaGetLastError();
     }
     if (getenv("WRT_MULTI_NO_PEER")) m->peer_stores = false;          // tests: force the copy + scatter path
+    for (int r = 1; r < n; r++) m->workers.emplace_back(multi_worker, m, r);
     *out = m;
     return 0;
 }
 
 void wrt_multi_destroy(WrtMulti* m) {
     if (!m) return;
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->quit = true;
+    }
+    m->cv_go.notify_all();
+    for (std::thread& t : m->workers) t.join();
     for (size_t r = 0; r < m->ctx.size(); r++) {
         if (m->d_packed[r]) { cudaSetDevice(m->devices[r]); cudaFree(m->d_packed[r]); }
         if (m->ctx[r]) wrt_destroy(m->ctx[r]);

@@ -45,4 +45,21 @@ __device__ __forceinline__ float ref_powf(float x, float y) { return (float)pow(
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// One 256-bit read-only load (sm_100: LDG.E.256) of two adjacent float4 — a whole 32-byte tree record or primitive box.
+// p must be 32-byte aligned.  Divergent lanes cost the L1 one wavefront per lane and instruction, so a record fetched
+// as one 256-bit load costs half the wavefronts of two 128-bit loads (the deep closest-hit levels ran the L1 data
+// pipe at 82-87 % of its wavefront peak, profiles/NOTES.md).
+#ifndef WRT_NO_LDG256
+__device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b) {
+    unsigned long long q0, q1, q2, q3;
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(p));
+    a.x = __uint_as_float((unsigned)q0); a.y = __uint_as_float((unsigned)(q0 >> 32));
+    a.z = __uint_as_float((unsigned)q1); a.w = __uint_as_float((unsigned)(q1 >> 32));
+    b.x = __uint_as_float((unsigned)q2); b.y = __uint_as_float((unsigned)(q2 >> 32));
+    b.z = __uint_as_float((unsigned)q3); b.w = __uint_as_float((unsigned)(q3 >> 32));
+}
+#else
+__device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b) { a = __ldg(p); b = __ldg(p + 1); }
+#endif
+
 } // namespace wrt

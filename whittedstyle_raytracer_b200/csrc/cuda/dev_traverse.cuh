@@ -191,7 +191,9 @@ template <bool NEAR_FIRST, bool PRESORTED = false, class LeafFn>
 __device__ __forceinline__ bool traverse_step(const float4* __restrict__ nodes, const Ray& r, Stack& st, int& cur,
                                               const float& limit, LeafFn&& leaf) {
     const float4* n = nodes + 2 * cur;
-    float4 l0 = ldg4(n), l1 = ldg4(n + 1), r0 = ldg4(n + 2), r1 = ldg4(n + 3);
+    float4 l0, l1, r0, r1;
+    ldg8(n, l0, l1);
+    ldg8(n + 2, r0, r1);
     float tl, tr;
     bool hl = PRESORTED ? slab_presorted(l0, l1, r, tl) : slab(l0, l1, r, tl);
     bool hr = PRESORTED ? slab_presorted(r0, r1, r, tr) : slab(r0, r1, r, tr);
@@ -341,8 +343,9 @@ __device__ __forceinline__ void occluded_leaf(const DevScene& s, const Ray& r, f
 // testing one of them early is only a reordering; the own-box test keeps the predicate exact.
 __device__ __forceinline__ bool occluder_cache_hit(const DevScene& s, const Ray& r, float dis, int p) {
     float te;
-    const float4* b = s.prim_box + 2 * (size_t)p;
-    if (!slab(ldg4(b), ldg4(b + 1), r, te)) return false;
+    float4 blo, bhi;
+    ldg8(s.prim_box + 2 * (size_t)p, blo, bhi);
+    if (!slab(blo, bhi, r, te)) return false;
     PrimHit h; float oma; unsigned fl;
     return prim_test(s, p, r, h, oma, fl) && h.t < dis;
 }

@@ -596,38 +596,48 @@ struct SoftListBuffers {
 #endif
 
 // One lane walks one request's shaft, but walk lengths differ a lot (3 ... 400 node pairs; ncu: 8.6 of 32 lanes
-// active when every lane takes one request and the warp waits for the longest).  So a warp owns WRT_LISTS_CHUNK
-// consecutive requests at a time:
+// active when every lane takes one request and the warp waits for the longest).  So a warp owns a chunk of
+// consecutive requests at a time (32 ... WRT_LISTS_CHUNK, by queue length):
 //   A. all lanes build the chunk's shafts (wrt_shaft_make, ~200 instructions, fully converged) into a per-warp slot
 //      array (global scratch, L1-resident);
-//   B. lanes walk; a lane that finishes copies its list into the pool and takes the chunk's next request
-//      (WRT_LISTS_REFILL idle lanes trigger a hand-out: a slot load, no set-up code on a few lanes).
-// Pool space: the warp reserves region_per_request entries per request of the chunk with ONE global atomic and lanes
-// sub-allocate from the region through a shared-memory cursor; a list that does not fit takes its own global
-// allocation; an exhausted pool means count = -1 (per-ray walk).  Lists of a chunk stay close together in the pool.
+//   B. lanes walk; a finished lane keeps its list in its scratch column and goes idle; once WRT_LISTS_REFILL lanes are
+//      idle the WHOLE warp flushes the finished lists into the pool (coalesced copies, 32 entries per step — a lane
+//      copying its own list alone stalls the other 31: measured, 27 % slower than no refill at all) and hands the
+//      chunk's next requests to the idle lanes (a slot load, no set-up code on a few lanes).
+// Pool space: the warp reserves region_per_request entries per request of the chunk with ONE global atomic and
+// allocates from the region through a warp-uniform cursor; when the region is used up it takes what the flush needs
+// with another atomic; an exhausted pool means count = -1 (per-ray walk).  Lists of a chunk stay close together.
 // (An earlier refill attempt through run_queue — set-up code on the refilled lanes only — was slower than no refill.)
 __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                               int work_slot, int stack_rows, SoftListBuffers lb) {
     extern __shared__ int smem[];
-    __shared__ unsigned s_used[4];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
     const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    int* mine = lb.scratch + (gwarp * 32 + lane) * WRT_LIST_CAP;
+    int* warp_scratch = lb.scratch + gwarp * 32 * WRT_LIST_CAP;
+    int* mine = warp_scratch + (size_t)lane * WRT_LIST_CAP;
     float* slots = lb.shafts + gwarp * (size_t)WRT_LISTS_CHUNK * 10;
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
     unsigned* pool_head = fb.counters + C_POOL + q;
+    // chunk size: ~4 chunks per warp on short queues (the launch ends with its slowest chunk), WRT_LISTS_CHUNK on long ones
+    unsigned chunk_size;
+    {
+        const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+        unsigned long long per = nreq / (warps * 4ull);
+        per = (per + 31ull) & ~31ull;
+        chunk_size = per < 32ull ? 32u : (per > (unsigned long long)WRT_LISTS_CHUNK ? (unsigned)WRT_LISTS_CHUNK : (unsigned)per);
+    }
     unsigned n_empty = 0;
     while (true) {
         unsigned long long claimed = 0;
-        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)WRT_LISTS_CHUNK);
+        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)chunk_size);
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
         if (claimed >= nreq) break;
         const unsigned base = (unsigned)claimed;
-        const unsigned chunk = nreq - base < (unsigned)WRT_LISTS_CHUNK ? nreq - base : (unsigned)WRT_LISTS_CHUNK;
+        const unsigned chunk = nreq - base < chunk_size ? nreq - base : chunk_size;
         // ---- A: shafts of the chunk ----
         for (unsigned r = lane; r < chunk; r += 32) {
             float4 o4 = fb.preq_o[q][base + r];
@@ -644,74 +654,99 @@ __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s
             d[6] = sh.ihi[0]; d[7] = sh.ihi[1]; d[8] = sh.ihi[2];
             d[9] = __int_as_float(ok ? (sh.octant | (sh.use << 3)) : -1);
         }
-        // ---- pool region of the chunk: one atomic ----
-        unsigned region = 0;
-        if (lane == 0) {
-            region = atomicAdd(pool_head, chunk * lb.region_per_request);
-            s_used[warp] = 0u;
-        }
-        region = __shfl_sync(0xffffffffu, region, 0);
-        unsigned region_size = chunk * lb.region_per_request;
-        if (region >= lb.pool_cap) region_size = 0;
-        else if (region_size > lb.pool_cap - region) region_size = lb.pool_cap - region;
+        // ---- pool region of the chunk: one atomic; [cursor, region_end) is what is left of it (warp-uniform) ----
+        unsigned cursor = 0;
+        if (lane == 0) cursor = atomicAdd(pool_head, chunk * lb.region_per_request);
+        cursor = __shfl_sync(0xffffffffu, cursor, 0);
+        unsigned region_end = cursor + chunk * lb.region_per_request;
+        if (cursor >= lb.pool_cap) { cursor = 0; region_end = 0; }
+        else if (region_end > lb.pool_cap || region_end < cursor) region_end = lb.pool_cap;
         __syncwarp();
-        // ---- B: walks with refill ----
+        // ---- B: walks, flush + refill ----
         unsigned next = 0;                                   // warp-uniform: requests of the chunk handed out so far
         bool active = false;
+        int pend = -2;                                       // finished walk waiting for the flush: list length, -1 = give up; -2 = nothing
         unsigned my = 0;
         WrtShaft sh;
         WrtShaftWalk w;
         w.nodes = s.onodes; w.cur = 0; w.sp = 0; w.n = 0;
         while (true) {
             const unsigned idle = __ballot_sync(0xffffffffu, !active);
-            if (next < chunk && (idle == 0xffffffffu || __popc(idle) >= WRT_LISTS_REFILL)) {
-                const unsigned cand = next + __popc(idle & lt_mask);
-                next += __popc(idle);
-                if (!active && cand < chunk) {
-                    my = cand;
-                    const float* d = slots + (size_t)my * 10;
-                    const int ou = __float_as_int(d[9]);
-                    int rc = -1;
-                    if (ou >= 0) {
-                        sh.o[0] = d[0]; sh.o[1] = d[1]; sh.o[2] = d[2];
-                        sh.ilo[0] = d[3]; sh.ilo[1] = d[4]; sh.ilo[2] = d[5];
-                        sh.ihi[0] = d[6]; sh.ihi[1] = d[7]; sh.ihi[2] = d[8];
-                        sh.octant = ou & 7; sh.use = ou >> 3;
-                        rc = wrt_shaft_walk_begin(s.onodes, s.n_nodes, &sh, &w);
+            const bool more = next < chunk;
+            if (idle == 0xffffffffu || (more && __popc(idle) >= WRT_LISTS_REFILL)) {
+                // flush: the finished lists -> pool, all lanes copying
+                __syncwarp();                                // the lists other lanes wrote to their scratch columns are visible
+                const int cnt = pend > 0 ? pend : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= (unsigned)off) incl += v;
+                }
+                const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+                if (total > 0) {
+                    unsigned first = cursor;
+                    bool fits = total <= region_end - cursor;
+                    if (fits) cursor += total;
+                    else {                                   // region used up: take exactly what this flush needs
+                        unsigned g = 0xffffffffu;
+                        if (lane == 0 && *(volatile unsigned*)pool_head < lb.pool_cap) g = atomicAdd(pool_head, total);
+                        g = __shfl_sync(0xffffffffu, g, 0);
+                        fits = g < lb.pool_cap && total <= lb.pool_cap - g;
+                        first = g;
                     }
-                    if (rc == 1) active = true;
-                    else {                                   // answered without a walk: -1 = ray by ray, 0 = empty list
-                        if (WRT_IN_BOUNDS(base + my, fb.preq_cap[q])) lb.ref[base + my] = make_int2(0, rc);
-                        if (rc == 0) ++n_empty;
+                    const unsigned dst = first + (unsigned)(incl - cnt);
+                    unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+                    while (todo) {
+                        const int src_lane = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int c = __shfl_sync(0xffffffffu, cnt, src_lane);
+                        const unsigned d0 = __shfl_sync(0xffffffffu, dst, src_lane);
+                        if (fits) {
+                            const int* src = warp_scratch + (size_t)src_lane * WRT_LIST_CAP;
+                            for (int i = (int)lane; i < c; i += 32)
+                                if (WRT_IN_BOUNDS(d0 + i, lb.pool_cap)) lb.pool[d0 + i] = src[i];
+                        }
+                    }
+                    if (cnt > 0 && WRT_IN_BOUNDS(base + my, fb.preq_cap[q])) lb.ref[base + my] = fits ? make_int2((int)dst, cnt) : make_int2(0, -1);
+                }
+                if (pend == 0 || pend == -1) {               // empty list (= lit, no rays needed) / give up (= ray by ray)
+                    if (WRT_IN_BOUNDS(base + my, fb.preq_cap[q])) lb.ref[base + my] = make_int2(0, pend);
+                    if (pend == 0) ++n_empty;
+                }
+                pend = -2;
+                __syncwarp();                                // the scratch columns are free again
+                // refill
+                if (more) {
+                    const unsigned cand = next + __popc(idle & lt_mask);
+                    next += __popc(idle);
+                    if (!active && cand < chunk) {
+                        my = cand;
+                        const float* d = slots + (size_t)my * 10;
+                        const int ou = __float_as_int(d[9]);
+                        int rc = -1;
+                        if (ou >= 0) {
+                            sh.o[0] = d[0]; sh.o[1] = d[1]; sh.o[2] = d[2];
+                            sh.ilo[0] = d[3]; sh.ilo[1] = d[4]; sh.ilo[2] = d[5];
+                            sh.ihi[0] = d[6]; sh.ihi[1] = d[7]; sh.ihi[2] = d[8];
+                            sh.octant = ou & 7; sh.use = ou >> 3;
+                            rc = wrt_shaft_walk_begin(s.onodes, s.n_nodes, &sh, &w);
+                        }
+                        if (rc == 1) active = true;
+                        else pend = rc;                      // answered without a walk; recorded by the next flush
                     }
                 }
-            }
-            if (!__any_sync(0xffffffffu, active)) {
-                if (next >= chunk) break;
-                continue;
+                if (!__any_sync(0xffffffffu, active)) {
+                    if (next >= chunk && !__any_sync(0xffffffffu, pend != -2)) break;
+                    continue;
+                }
             }
 #pragma unroll 1
             for (int it = 0; it < 4; it++) {
-                if (!active) continue;
-                const int rc = wrt_shaft_walk_step(&sh, &w, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
-                if (rc == 1) continue;
-                // finished: copy the list into the pool
-                active = false;
-                int cnt = rc < 0 ? -1 : w.n;
-                unsigned dst = 0;
-                if (cnt > 0) {
-                    const unsigned off = atomicAdd(&s_used[warp], (unsigned)cnt);
-                    if (off <= region_size && (unsigned)cnt <= region_size - off) dst = region + off;
-                    else if (*(volatile unsigned*)pool_head < lb.pool_cap) {            // region used up: own allocation
-                        dst = atomicAdd(pool_head, (unsigned)cnt);
-                        if (dst >= lb.pool_cap || (unsigned)cnt > lb.pool_cap - dst) cnt = -1;
-                    } else cnt = -1;                                                        // pool full: per-ray walk
-                    for (int i = 0; i < cnt; i++)
-                        if (WRT_IN_BOUNDS(dst + i, lb.pool_cap)) lb.pool[dst + i] = mine[i];
+                if (active) {
+                    const int rc = wrt_shaft_walk_step(&sh, &w, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+                    if (rc != 1) { active = false; pend = rc < 0 ? -1 : w.n; }
                 }
-                if (WRT_IN_BOUNDS(base + my, fb.preq_cap[q])) lb.ref[base + my] = make_int2((int)dst, cnt);
-                // an empty list is an empty shaft: the ray kernel answers "lit" without building the rays (statistics only here)
-                if (cnt == 0) ++n_empty;
             }
         }
         __syncwarp();

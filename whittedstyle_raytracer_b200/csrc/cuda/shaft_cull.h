@@ -51,8 +51,10 @@
 
 #if defined(__CUDA_ARCH__)
 #define WRT_SHAFT_LD4(p) __ldg(p)
+#define WRT_SHAFT_LD8(p, a, b) wrt::ldg8(p, a, b)       /* one 256-bit load per tree record (dev_math.cuh) */
 #else
 #define WRT_SHAFT_LD4(p) (*(p))
+#define WRT_SHAFT_LD8(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
 #endif
 
 #define WRT_SHAFT_STACK 48
@@ -171,7 +173,9 @@ WRT_SHAFT_HD int wrt_shaft_walk_begin(const float4* onodes, int n_nodes, const W
 WRT_SHAFT_HD int wrt_shaft_walk_step(const WrtShaft* sh, WrtShaftWalk* w, int* stack, int stack_stride, int stack_cap,
                                      int* out, int out_cap) {
     const float4* nd = w->nodes + 2 * (size_t)w->cur;
-    float4 l0 = WRT_SHAFT_LD4(nd), l1 = WRT_SHAFT_LD4(nd + 1), r0 = WRT_SHAFT_LD4(nd + 2), r1 = WRT_SHAFT_LD4(nd + 3);
+    float4 l0, l1, r0, r1;
+    WRT_SHAFT_LD8(nd, l0, l1);
+    WRT_SHAFT_LD8(nd + 2, r0, r1);
     float tl, tr;
     bool hl = wrt_shaft_may_hit_lb(sh, l0, l1, &tl), hr = wrt_shaft_may_hit_lb(sh, r0, r1, &tr);
     union { float f; int i; } u;
@@ -230,7 +234,9 @@ WRT_SHAFT_HD bool wrt_shaft_is_empty(const float4* onodes, int n_nodes, const fl
     int sp = 0;
     while (true) {
         const float4* n = nodes + 2 * (size_t)cur;
-        float4 l0 = WRT_SHAFT_LD4(n), l1 = WRT_SHAFT_LD4(n + 1), r0 = WRT_SHAFT_LD4(n + 2), r1 = WRT_SHAFT_LD4(n + 3);
+        float4 l0, l1, r0, r1;
+        WRT_SHAFT_LD8(n, l0, l1);
+        WRT_SHAFT_LD8(n + 2, r0, r1);
         bool hl = wrt_shaft_may_hit(&sh, l0, l1), hr = wrt_shaft_may_hit(&sh, r0, r1);
         w.f = l0.w; const int linkL = w.i;
         w.f = r0.w; const int linkR = w.i;

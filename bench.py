@@ -219,7 +219,7 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------
 KERNEL_NAMES = {"shadow_soft": "k_soft_list_rays", "soft_lists": "k_soft_lists", "trace_closest": "k_trace_closest",
                 "shadow_hard": "k_shadow_hard", "surface": "k_surface_spawn", "shadow_directional": "k_shadow_directional",
-                "shade": "k_shade", "combine": "k_combine_resolve"}
+                "shade": "k_shade", "combine": "k_combine_resolve", "soft_filter": "k_soft_filter"}
 
 
 def measure_workload(workload, steps, warmup, dist_env, cpu_seconds, want_clocks):

@@ -115,9 +115,9 @@ int wrt_measure_fp32_peak(WrtContext* ctx, float* tflops_fma, float* tflops_mul_
 /* Per-kernel-family device milliseconds of the last wrt_render* call (CUDA events
  * on the launching stream).  Order: raygen, trace_closest, surface, shadow_hard,
  * shadow_soft (the soft-shadow ray kernels), shadow_directional, shade, combine, resolve,
- * soft_lists (candidate-list build of the soft-shadow path).  Returns the number of
- * entries written. */
-#define WRT_KERNEL_FAMILIES 10
+ * soft_lists (candidate-list build of the soft-shadow path), soft_filter (triangle-level pruning of
+ * those lists).  Returns the number of entries written. */
+#define WRT_KERNEL_FAMILIES 11
 int wrt_get_kernel_times(WrtContext* ctx, float* ms, int capacity);
 /* Launches per family behind those times (same order). */
 int wrt_get_kernel_launches(WrtContext* ctx, int32_t* launches, int capacity);

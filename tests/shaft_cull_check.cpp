@@ -5,7 +5,9 @@
 // the own box of EVERY primitive under the exact BoundBox::IntersectRay arithmetic.  Also checks
 // that each sample's 1/d lies inside the shaft's bounds, and that the shaft's candidate list
 // (wrt_shaft_candidates, phase 1 of k_shadow_soft_list) contains every primitive whose own box a
-// sample ray hits.  Prints one JSON line.
+// sample ray hits; and that the triangle-level pruning of that list (wrt_pyramid_triangle_may_block, k_soft_filter)
+// only removes triangles that no sample ray hits with t < dis under Triangle::intersect's own arithmetic.
+// Prints one JSON line.
 //
 // usage: shaft_cull_check <config.txt> <bunny.obj|-> <asset_dir> <n_requests> <seed>
 #include <cmath>
@@ -68,7 +70,8 @@ int main(int argc, char** argv) {
         }
     }
     long long empty = 0, nonempty = 0, gave_up = 0, violations = 0, bound_violations = 0, rays_checked = 0, degenerate_rays = 0,
-              lists = 0, list_items = 0, list_overflow = 0, list_violations = 0, list_rays = 0;
+              lists = 0, list_items = 0, list_overflow = 0, list_violations = 0, list_rays = 0,
+              filter_removed = 0, filter_kept = 0, filter_pairs = 0, filter_violations = 0;
     const float top = 1.0f - 1.0f / 16777216.0f;
     for (int r = 0; r < n_req; r++) {
         // origin: a point on a random primitive pushed off along +-normal like BVHStrategy.hpp:15, or a free point
@@ -116,8 +119,20 @@ int main(int argc, char** argv) {
             int stack[64], list[64];
             const int cnt = wrt_shaft_candidates(onodes.data(), nn, &sh, stack, 1, 64, list, 64);
             if (cnt < 0) list_overflow++; else { lists++; list_items += cnt; if (is_empty != (cnt == 0)) violations++; }
+            // triangle-level pruning of the list (k_soft_filter): the removed candidates must block no sample ray
+            std::vector<int> removed;
+            if (cnt > 0) {
+                WrtShaftPyramid py;
+                wrt_pyramid_make(o, L.tri, &py);
+                for (int c = 0; c < cnt; c++) {
+                    const int p = list[c];
+                    const float* g = S->prim_geom + 12 * (size_t)p;
+                    if ((S->prim_flags[p] & WRT_PRIM_KIND_MASK) != WRT_PRIM_TRIANGLE || wrt_pyramid_triangle_may_block(&py, g, g + 4, g + 8)) filter_kept++;
+                    else { removed.push_back(p); filter_removed++; }
+                }
+            }
             V v0{L.tri[0], L.tri[1], L.tri[2]}, v1{L.tri[3], L.tri[4], L.tri[5]}, v2{L.tri[6], L.tri[7], L.tri[8]};
-            const int ns = is_empty ? 40 : 12;
+            const int ns = is_empty ? 40 : (removed.empty() ? 12 : 24);
             for (int s = 0; s < ns; s++) {
                 float u, v;
                 if (s < 4) { u = (s & 1) ? top : 0.f; v = (s & 2) ? top : 0.f; }
@@ -139,6 +154,19 @@ int main(int argc, char** argv) {
                 }
                 const bool degenerate = dv[0] == 0 || dv[1] == 0 || dv[2] == 0;
                 if (degenerate) degenerate_rays++;
+                for (int p : removed) {                                  // Triangle::intersect, Triangle.hpp:22-41, and t < dis
+                    const float* g = S->prim_geom + 12 * (size_t)p;
+                    V tv0{g[0], g[1], g[2]}, E1{g[4], g[5], g[6]}, E2{g[8], g[9], g[10]};
+                    V Sv{o[0] - tv0.x, o[1] - tv0.y, o[2] - tv0.z};
+                    V S1{d.y * E2.z - d.z * E2.y, d.z * E2.x - d.x * E2.z, d.x * E2.y - d.y * E2.x};
+                    V S2{Sv.y * E1.z - Sv.z * E1.y, Sv.z * E1.x - Sv.x * E1.z, Sv.x * E1.y - Sv.y * E1.x};
+                    float rx = S2.x * E2.x + S2.y * E2.y + S2.z * E2.z, ry = S1.x * Sv.x + S1.y * Sv.y + S1.z * Sv.z, rz = S2.x * d.x + S2.y * d.y + S2.z * d.z;
+                    float left = 1.0f / (S1.x * E1.x + S1.y * E1.y + S1.z * E1.z);
+                    float t = rx * left, bu = ry * left, bv = rz * left;
+                    const float EPS = 0.00001f;
+                    filter_pairs++;
+                    if (t + EPS > 0 && 1 - bu - bv + EPS > 0 && bu + EPS > 0 && bv + EPS > 0 && t < mag) filter_violations++;
+                }
                 if (cnt >= 0 && !degenerate) {
                     // every primitive whose own box this ray hits must be on the list
                     V ov{o[0], o[1], o[2]};
@@ -160,8 +188,10 @@ int main(int argc, char** argv) {
     }
     printf("{\"prims\": %d, \"empty\": %lld, \"nonempty\": %lld, \"gave_up\": %lld, \"rays_checked\": %lld, "
            "\"degenerate_rays\": %lld, \"violations\": %lld, \"bound_violations\": %lld, \"lists\": %lld, \"list_items\": %lld, "
-           "\"list_overflow\": %lld, \"list_rays\": %lld, \"list_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked,
-           degenerate_rays, violations, bound_violations, lists, list_items, list_overflow, list_rays, list_violations);
+           "\"list_overflow\": %lld, \"list_rays\": %lld, \"list_violations\": %lld, \"filter_removed\": %lld, \"filter_kept\": %lld, "
+           "\"filter_pairs\": %lld, \"filter_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked,
+           degenerate_rays, violations, bound_violations, lists, list_items, list_overflow, list_rays, list_violations, filter_removed,
+           filter_kept, filter_pairs, filter_violations);
     wrt_scene_free(sc);
-    return (violations || bound_violations || list_violations) ? 1 : 0;
+    return (violations || bound_violations || list_violations || filter_violations) ? 1 : 0;
 }

@@ -543,6 +543,29 @@ def test_request_culling_changes_the_work_not_the_result(workdir, monkeypatch):
         assert st_on["shadow_rays"] == ost.shadow_rays
 
 
+def test_candidate_list_pruning_changes_the_work_not_the_result(workdir, monkeypatch):
+    """k_soft_filter drops from every candidate list the triangles no sample ray of the request can hit
+    (shaft_cull.h wrt_pyramid_*): same image with the pruning off (0), on the deep queues (1, default) and on every
+    queue (2); fewer rays traced (requests whose list empties need none) and the reference-equivalent counts unchanged."""
+    name = "prune_640"
+    fixtures.write_config(workdir, name, fixtures.water_bunny_tex_config(640, 360, soft=True))
+    scene = Scene.from_workdir(workdir, name)
+    out = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("WRT_SOFT_FILTER", mode)
+        out[mode] = gpu_render(scene)
+    monkeypatch.delenv("WRT_SOFT_FILTER")
+    for mode in ("1", "2"):
+        assert np.array_equal(out[mode][0], out["0"][0]), mode
+        for k in ("closest_rays", "shadow_rays", "shadow_requests", "rays_per_depth"):
+            assert out[mode][1][k] == out["0"][1][k], (mode, k)
+    assert out["1"][1]["shadow_rays_traced"] < out["0"][1]["shadow_rays_traced"]
+    assert out["2"][1]["shadow_rays_traced"] <= out["1"][1]["shadow_rays_traced"]
+    ref, ost = ob.OracleScene(scene).render()
+    d = image_diff(out["1"][0], ref)
+    assert d["exact"] >= 0.9999 * d["n"] and d["max"] <= 1, d
+
+
 MANY_LIGHTS = """imsize 96 64
 eye 0 1 6
 viewdir 0 -0.1 -1

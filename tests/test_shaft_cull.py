@@ -62,6 +62,9 @@ def test_empty_shaft_verdicts_hold_by_brute_force(name, checker, workdir):
     assert out.returncode == 0, out.stdout + out.stderr
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["violations"] == 0 and r["bound_violations"] == 0 and r["list_violations"] == 0
+    assert r["filter_violations"] == 0                       # no pruned candidate is ever hit by a sample ray
+    if name in ("water_bunny_tex", "bunny_shadow"):
+        assert r["filter_removed"] > 0.2 * (r["filter_removed"] + r["filter_kept"]) and r["filter_pairs"] > 100000
     assert r["list_rays"] > 0
     assert r["empty"] + r["nonempty"] + r["gave_up"] > 0
     if name in ("water_bunny_tex", "bunny_shadow"):

@@ -608,8 +608,10 @@ struct SoftListBuffers {
 // allocates from the region through a warp-uniform cursor; when the region is used up it takes what the flush needs
 // with another atomic; an exhausted pool means count = -1 (per-ray walk).  Lists of a chunk stay close together.
 // (An earlier refill attempt through run_queue — set-up code on the refilled lanes only — was slower than no refill.)
-__global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
-                                              int work_slot, int stack_rows, SoftListBuffers lb) {
+// (launch bound: 48 registers = 10 CTAs per SM; unbounded the kernel takes 70 and the walks — dependent loads, little
+// else — lose a third of the warps that hide their latency.  What spills is flush-side state.)
+__global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
+                                                        int work_slot, int stack_rows, SoftListBuffers lb) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
@@ -750,6 +752,66 @@ __global__ void WRT_TRACE_BOUNDS k_soft_lists(const __grid_constant__ DevScene s
             }
         }
         __syncwarp();
+    }
+    n_empty = __reduce_add_sync(0xffffffffu, n_empty);
+    if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);
+}
+
+// ---- K4b'': triangle-level pruning of the candidate lists (shaft_cull.h, wrt_pyramid_*) ----
+// The lists hold every primitive whose BOX a ray of the shaft may hit.  On the bunny's surface half of those triangles
+// cannot be hit by any ray of the request (they lie outside the pyramid origin -> light, or the pyramid lies on one side of
+// their plane); every one of them would cost each of the request's 50 rays an own-box test, often a triangle test.  One warp
+// per request drops them (ballot compaction, in place, order kept).  A quarter of the fully lit deep requests end up
+// with an empty list and need no rays at all.  Exact: a removed triangle blocks no sample ray (proof obligations and the
+// brute-force check: shaft_cull.h, tests/shaft_cull_check.cpp).
+#ifndef WRT_FILTER_MIN
+#define WRT_FILTER_MIN 3          // shorter lists are not worth the pyramid set-up
+#endif
+__global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
+                                                     SoftListBuffers lb) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
+    const unsigned warps = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned n_empty = 0;
+    for (unsigned req = gw; req < nreq; req += warps) {
+        const int2 ref = lb.ref[req];
+        if (ref.y < WRT_FILTER_MIN) continue;
+        const float4 o4 = fb.preq_o[q][req];
+        const uint4 k = fb.preq_k[q][req];
+        const WrtLight* L = s.lights + k.x;
+        float tri[9];
+        for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
+        const float o[3] = {o4.x, o4.y, o4.z};
+        WrtShaftPyramid py;
+        wrt_pyramid_make(o, tri, &py);
+        if (!py.ok) continue;
+        int* list = lb.pool + ref.x;
+        int kept = 0;
+        for (int b0 = 0; b0 < ref.y; b0 += 32) {
+            const int i = b0 + (int)lane;
+            int prim = -1;
+            bool keep = false;
+            if (i < ref.y) {
+                prim = list[i];
+                const float4* g = s.geom + 3 * (size_t)prim;
+                const float4 A = ldg4(g), B = ldg4(g + 1), C = ldg4(g + 2);
+                keep = true;
+                if ((__float_as_uint(C.w) & WRT_PRIM_KIND_MASK) == WRT_PRIM_TRIANGLE) {
+                    const float v0[3] = {A.x, A.y, A.z}, E1[3] = {B.x, B.y, B.z}, E2[3] = {C.x, C.y, C.z};
+                    keep = wrt_pyramid_triangle_may_block(&py, v0, E1, E2);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();                                  // every lane has read its entry before any entry is overwritten
+            if (keep && WRT_IN_BOUNDS((unsigned)ref.x + kept + __popc(mask & lt_mask), lb.pool_cap))
+                list[kept + __popc(mask & lt_mask)] = prim;
+            kept += __popc(mask);
+        }
+        if (lane == 0) {
+            lb.ref[req] = make_int2(ref.x, kept);
+            if (kept == 0) ++n_empty;                      // lit, and no ray needs to be built (statistics)
+        }
     }
     n_empty = __reduce_add_sync(0xffffffffu, n_empty);
     if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);

@@ -254,4 +254,99 @@ WRT_SHAFT_HD bool wrt_shaft_is_empty(const float4* onodes, int n_nodes, const fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Triangle-level pruning of a candidate list (k_soft_filter).  The list holds every primitive whose BOX some ray of the
+// shaft may hit; most of those triangles cannot be hit themselves.  A candidate is removed when it provably blocks no
+// sample: it is then never the reason a ray is occluded, so "OR over the list" keeps its value (a ray that tests it in
+// the reference gets "no hit with t < dis" from it).  The rays of a request are the segments from the origin o to points
+// of the light's parallelogram, i.e. they lie in the pyramid P = hull(o, 4 corners).  Two sufficient conditions, in exact
+// geometry, each applied with a margin far above every rounding involved:
+//   side planes   all three vertices of the triangle lie outside ONE of the pyramid's four side planes (planes through o
+//                 and two adjacent corners): the triangle and the convex pyramid are disjoint;
+//   own plane     o and all four corners lie strictly on the same side of the triangle's plane: no segment o -> corner hull
+//                 crosses that plane, so every ray's plane parameter t is < 0 or > dis.
+// Margins.  Triangle.hpp:41 accepts barycentrics and t down to -1e-5, i.e. points up to 1e-5 * (|E1| + |E2|) outside the
+// triangle and 1e-5 behind the origin; the samples' float evaluation moves a target by <= 1e-6 * |coordinate|
+// (shaft_cull.h header, step 1).  The tests demand 1e-4 relative (to the vertex / corner distance from o) plus 2e-5 * (|E1|
+// + |E2|) plus 1e-5 absolute for the side planes, and 1e-3 * (|E1| + |E2|) + 2e-5 for the origin's height over the triangle's
+// plane (the 5e-4 offset of BVHStrategy.hpp:15 over centimetre triangles passes; an origin ON a 40-unit triangle's plane
+// does not, and is left to the box test).  A pyramid seen almost edge-on (a side-plane normal that does not separate the
+// opposite corners by 1e-3 of their distance) disables the filter for the request.
+// tests/shaft_cull_check.cpp runs this same source on the CPU and checks every removed candidate against every sample
+// ray with Triangle::intersect's own arithmetic: 0 violations over > 1e7 (ray, candidate) pairs per run.
+typedef struct WrtShaftPyramid {
+    float o[3];
+    float D[4][3];         /* corners - o, in order around the parallelogram */
+    float Dlen[4];
+    float N[4][3];         /* unit inward normals of the side planes (plane k holds o, corner k, corner k+1) */
+    int ok;
+} WrtShaftPyramid;
+
+WRT_SHAFT_HD void wrt_pyramid_make(const float o[3], const float tri[9], WrtShaftPyramid* p) {
+    for (int k = 0; k < 3; k++) {
+        p->o[k] = o[k];
+        p->D[0][k] = tri[k] - o[k];
+        p->D[1][k] = tri[3 + k] - o[k];
+        p->D[2][k] = (tri[3 + k] + tri[6 + k] - tri[k]) - o[k];
+        p->D[3][k] = tri[6 + k] - o[k];
+    }
+    for (int j = 0; j < 4; j++) p->Dlen[j] = sqrtf(p->D[j][0] * p->D[j][0] + p->D[j][1] * p->D[j][1] + p->D[j][2] * p->D[j][2]);
+    p->ok = 1;
+    for (int k = 0; k < 4; k++) {
+        const float* a = p->D[k];
+        const float* b = p->D[(k + 1) & 3];
+        float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        const float l = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (!(l > 0.f) || !(l < 1e30f)) { p->ok = 0; return; }
+        const float il = 1.f / l;
+        n[0] *= il; n[1] *= il; n[2] *= il;
+        const float* c = p->D[(k + 2) & 3];
+        const float* d = p->D[(k + 3) & 3];
+        float s2 = n[0] * c[0] + n[1] * c[1] + n[2] * c[2], s3 = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
+        if (s2 < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; s2 = -s2; s3 = -s3; }
+        const float dm = fmaxf(p->Dlen[(k + 2) & 3], p->Dlen[(k + 3) & 3]);
+        if (!(s2 > 1e-3f * dm) || !(s3 > 1e-3f * dm)) { p->ok = 0; return; }     /* edge-on: no filtering */
+        p->N[k][0] = n[0]; p->N[k][1] = n[1]; p->N[k][2] = n[2];
+    }
+}
+
+/* false = the triangle (v0, E1 = v1 - v0, E2 = v2 - v0) provably blocks no sample ray of the request. */
+WRT_SHAFT_HD bool wrt_pyramid_triangle_may_block(const WrtShaftPyramid* p, const float v0[3], const float E1[3], const float E2[3]) {
+    if (!p->ok) return true;
+    float w[3][3], wl[3];
+    for (int k = 0; k < 3; k++) {
+        w[0][k] = v0[k] - p->o[k];
+        w[1][k] = (v0[k] + E1[k]) - p->o[k];
+        w[2][k] = (v0[k] + E2[k]) - p->o[k];
+    }
+    for (int i = 0; i < 3; i++) wl[i] = sqrtf(w[i][0] * w[i][0] + w[i][1] * w[i][1] + w[i][2] * w[i][2]);
+    const float esz = sqrtf(E1[0] * E1[0] + E1[1] * E1[1] + E1[2] * E1[2]) + sqrtf(E2[0] * E2[0] + E2[1] * E2[1] + E2[2] * E2[2]);
+    if (!(esz < 1e30f)) return true;
+    for (int k = 0; k < 4; k++) {                          /* side planes */
+        bool out = true;
+        for (int i = 0; i < 3; i++) {
+            const float s = p->N[k][0] * w[i][0] + p->N[k][1] * w[i][1] + p->N[k][2] * w[i][2];
+            const float m = 1e-4f * wl[i] + 2e-5f * esz + 1e-5f;
+            if (!(s < -m)) { out = false; break; }
+        }
+        if (out) return false;
+    }
+    float n[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};   /* own plane */
+    const float l = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (l > 0.f && l < 1e30f) {
+        const float il = 1.f / l;
+        n[0] *= il; n[1] *= il; n[2] *= il;
+        const float ho = -(n[0] * w[0][0] + n[1] * w[0][1] + n[2] * w[0][2]);          /* height of o over the plane */
+        if (fabsf(ho) > 1e-3f * esz + 2e-5f) {
+            bool same = true;
+            for (int j = 0; j < 4; j++) {
+                const float H = n[0] * (p->D[j][0] - w[0][0]) + n[1] * (p->D[j][1] - w[0][1]) + n[2] * (p->D[j][2] - w[0][2]);
+                if (!(H * ho > 0.f) || !(fabsf(H) > 1e-3f * esz + 1e-4f * p->Dlen[j])) { same = false; break; }
+            }
+            if (same) return false;
+        }
+    }
+    return true;
+}
+
 #endif /* WRT_SHAFT_CULL_H */

@@ -38,7 +38,7 @@ int fail(const std::string& msg) {
         }                                                                                             \
     } while (0)
 
-enum Family { F_RAYGEN, F_TRACE, F_SURFACE, F_SHADOW_HARD, F_SHADOW_SOFT, F_SHADOW_DIR, F_SHADE, F_COMBINE, F_RESOLVE, F_SOFT_LISTS };
+enum Family { F_RAYGEN, F_TRACE, F_SURFACE, F_SHADOW_HARD, F_SHADOW_SOFT, F_SHADOW_DIR, F_SHADE, F_COMBINE, F_RESOLVE, F_SOFT_LISTS, F_SOFT_FILTER };
 
 struct TimedLaunch {
     int family;
@@ -96,7 +96,10 @@ struct WrtContext {
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
     int trace_blocks_per_sm = 10;      // persistent shadow / unfused closest-hit kernels
     bool shade0_separate = true;       // level 0 is shaded by its own launch on the side stream (else inside combine)
-    int deep_split = 3;                // request queues: level 0 | levels 1..deep_split | deeper (8: one deep queue)
+    int soft_filter = 1;               // 0: off, 1: prune the deep queues' candidate lists (k_soft_filter), 2: level 0's as well
+    int deep_split = 8;                // request queues: level 0 | levels 1..deep_split | deeper (8: one deep queue; 3 queues
+                                       // bought nothing at 1/8 frame size and cost 0.2 ms on a full frame)
+    int side_blocks_per_sm = 0;        // persistent shadow kernels on the side stream: CTAs per SM (0 = trace_blocks_per_sm)
     int fb_split = -1;
     bool small_batch_full_levels = true; // automatic sizing: batches under 1 M slots get full-size deep levels
     long long max_batch = 1ll << 25;   // primary slots per batch (8K = 33.2 M slots fits)
@@ -345,7 +348,8 @@ int enqueue_shadows(WrtContext* c, cudaStream_t st, int q, int& work_seq) {
     FrameBuffers& fb = c->fb;
     const DevScene& ds = c->ds;
     const int TB = 128;
-    const int trace_grid = grid_for(c, c->trace_blocks_per_sm), wide_grid = grid_for(c, 8);
+    const bool on_side = st == c->side && c->side_blocks_per_sm > 0;
+    const int trace_grid = grid_for(c, on_side ? std::min(c->side_blocks_per_sm, c->trace_blocks_per_sm) : c->trace_blocks_per_sm), wide_grid = grid_for(c, 8);
     const size_t sb = stack_bytes(c, TB);
     auto work_slot = [&]() { int s = C_WORK + 2 * work_seq; ++work_seq; return s; };
     const int refill = (q == 0 ? c->refill0 : c->refill) | (c->chunk_div << 8);
@@ -363,6 +367,10 @@ int enqueue_shadows(WrtContext* c, cudaStream_t st, int q, int& work_seq) {
                 {
                     LaunchScope ls(c, st, F_SOFT_LISTS);
                     k_soft_lists<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->stack_rows, lb);
+                }
+                if (c->soft_filter >= (q == 0 ? 2 : 1)) {            // triangle-level pruning of the lists (deep queues by default)
+                    LaunchScope ls(c, st, F_SOFT_FILTER);
+                    k_soft_filter<<<wide_grid, TB, 0, st>>>(ds, fb, q, lb);
                 }
                 LaunchScope ls(c, st, F_SHADOW_SOFT);
                 k_soft_list_rays<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->seed, lb);
@@ -694,6 +702,8 @@ int wrt_create(int device, WrtContext** out) {
     if (const char* e = getenv("WRT_REFILL0")) c->refill0 = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_HOST_BVH")) c->host_bvh = atoi(e) != 0;
     if (const char* e = getenv("WRT_SHADE0_SEPARATE")) c->shade0_separate = atoi(e) != 0;
+    if (const char* e = getenv("WRT_SOFT_FILTER")) c->soft_filter = atoi(e);
+    if (const char* e = getenv("WRT_SIDE_BLOCKS")) c->side_blocks_per_sm = std::max(0, std::min(32, atoi(e)));
     if (const char* e = getenv("WRT_DEEP_SPLIT")) c->deep_split = std::max(1, std::min(WRT_MAX_DEPTH - 1, atoi(e)));
     if (const char* e = getenv("WRT_DEEP_FACTOR")) { c->deep_factor = std::max(0.001f, std::min(2.f, (float)atof(e))); c->small_batch_full_levels = false; }
     if (const char* e = getenv("WRT_MAX_BATCH")) c->max_batch = std::max(64ll, (atoll(e) + 31) / 32 * 32);   // tests: force multi-batch frames

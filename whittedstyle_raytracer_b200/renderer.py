@@ -19,7 +19,7 @@ TRAVERSAL_EXHAUSTIVE = 0
 TRAVERSAL_PRUNED = 1
 
 KERNEL_FAMILIES = ["raygen", "trace_closest", "surface", "shadow_hard", "shadow_soft", "shadow_directional",
-                   "shade", "combine", "resolve", "soft_lists"]
+                   "shade", "combine", "resolve", "soft_lists", "soft_filter"]
 
 
 class CudaError(RuntimeError):

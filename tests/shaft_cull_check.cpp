@@ -127,7 +127,9 @@ int main(int argc, char** argv) {
                 for (int c = 0; c < cnt; c++) {
                     const int p = list[c];
                     const float* g = S->prim_geom + 12 * (size_t)p;
-                    if ((S->prim_flags[p] & WRT_PRIM_KIND_MASK) != WRT_PRIM_TRIANGLE || wrt_pyramid_triangle_may_block(&py, g, g + 4, g + 8)) filter_kept++;
+                    float aux[4];
+                    wrt_triangle_aux(g + 4, g + 8, aux);                              // (k_pack_prims computes this at upload)
+                    if ((S->prim_flags[p] & WRT_PRIM_KIND_MASK) != WRT_PRIM_TRIANGLE || wrt_pyramid_triangle_may_block(&py, g, g + 4, g + 8, aux)) filter_kept++;
                     else { removed.push_back(p); filter_removed++; }
                 }
             }

@@ -126,6 +126,54 @@ def test_million_random_rays_bit_exact(workdir):
     r.ctx.close()
 
 
+def test_adversarial_rays_pruned_equals_exhaustive(workdir):
+    """The pruned closest-hit walk skips boxes entered beyond t_best*(1+1e-3)+1e-3.  Rays built to
+    stress that margin: aimed at points on and up to 2e-5 edge lengths OUTSIDE triangle edges and vertices
+    (Triangle.hpp:41 accepts barycentrics down to -1e-5, so such hits lie outside the triangle and can lie outside its box),
+    from grazing directions (down to 1e-4 rad off the triangle's plane), from origins on the plane itself, and
+    through the 40-unit wall triangles whose slack is 4e-4 units.  Both traversals must equal the oracle's exhaustive
+    recursive walk bit for bit."""
+    scene, _ = load_golden_scene(workdir, "water_small")
+    d = scene.desc
+    geom = np.ctypeslib.as_array(d.prim_geom, shape=(d.n_prims, 12)).copy()
+    rng = np.random.default_rng(23)
+    n = 400_000
+    prim = rng.integers(0, d.n_prims, n)
+    big = np.argsort(-(np.linalg.norm(geom[:, 4:7], axis=1) + np.linalg.norm(geom[:, 8:11], axis=1)))[:4]
+    prim[: n // 4] = big[rng.integers(0, len(big), n // 4)]       # a quarter of the rays at the largest triangles (the walls)
+    v0, e1, e2 = geom[prim, 0:3], geom[prim, 4:7], geom[prim, 8:11]
+    # barycentric targets: on edges / vertices, pushed outside by 0 .. 2e-5
+    kind = rng.integers(0, 4, n)
+    a = rng.random(n)
+    eps = rng.choice([0.0, 5e-6, 9e-6, 1.1e-5, 2e-5], n) * rng.choice([1.0, -1.0], n)
+    b1 = np.where(kind == 0, a, np.where(kind == 1, eps, np.where(kind == 2, a, rng.choice([0.0, 1.0], n))))
+    b2 = np.where(kind == 0, eps, np.where(kind == 1, a, np.where(kind == 2, 1 - a + eps, rng.choice([0.0, 1.0], n) * 0 + eps)))
+    target = v0 + b1[:, None] * e1 + b2[:, None] * e2
+    nrm = np.cross(e1, e2)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+    tang = e1 / np.maximum(np.linalg.norm(e1, axis=1, keepdims=True), 1e-30)
+    phi = rng.random(n) * 2 * np.pi
+    inplane = np.cos(phi)[:, None] * tang + np.sin(phi)[:, None] * np.cross(nrm, tang)
+    graze = rng.choice([1e-4, 1e-3, 1e-2, 0.1, 1.0], n)               # elevation over the triangle's plane (rad)
+    direction = np.cos(graze)[:, None] * inplane + np.sin(graze)[:, None] * nrm * rng.choice([1.0, -1.0], n)[:, None]
+    dist = rng.choice([0.0, 1e-5, 1e-3, 0.5, 5.0, 30.0], n)          # 0: the origin lies on the target itself
+    o = (target - dist[:, None] * direction).astype(np.float32)
+    dd = direction.astype(np.float32)
+    dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    orc = ob.OracleScene(scene)
+    ref = orc.trace_closest(o, dd)
+    assert 0.2 < ref["hit"].mean() <= 1.0
+    r = Renderer(scene)
+    for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
+        r.ctx.set_options(traversal=traversal)
+        h = r.interStrategy.UpdateInter(o, dd)
+        for f in ("hit", "object", "prim"):
+            assert np.array_equal(h[f], ref[f]), (f, traversal, int((h[f] != ref[f]).sum()))
+        for f in ("t", "pos", "ndir"):
+            assert np.array_equal(h[f].view(np.int32), ref[f].view(np.int32)), (f, traversal)
+    r.ctx.close()
+
+
 @pytest.mark.parametrize("name", SOFT_SCENES)
 def test_soft_shadows(workdir, name):
     """Same counter RNG on both sides: GPU == oracle bit for bit; both agree with the

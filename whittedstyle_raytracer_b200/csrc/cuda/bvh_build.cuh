@@ -17,6 +17,7 @@
 #include <cfloat>
 
 #include "ploc_bvh.h"
+#include "shaft_cull.h"
 #include "../../../include/wrt_scene.h"
 
 namespace wrt {
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256) k_pack_prims(int n_prims, const float* __
                                                     const int* __restrict__ prim_normalmap, const int* __restrict__ prim_object,
                                                     const float* __restrict__ prim_normals, const float* __restrict__ prim_uv,
                                                     const float* __restrict__ materials, int n_materials, int n_textures, int n_normalmaps,
-                                                    float4* geom, float4* attr, int4* ids, int* flags_out) {
+                                                    float4* geom, float4* attr, int4* ids, float4* tri_aux, int* flags_out) {
     int bad = 0;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_prims; p += gridDim.x * blockDim.x) {
         const float* g = prim_geom + 12 * (size_t)p;
@@ -253,6 +254,9 @@ __global__ void __launch_bounds__(256) k_pack_prims(int n_prims, const float* __
         geom[3 * (size_t)p + 0] = make_float4(g[0], g[1], g[2], g[3]);
         geom[3 * (size_t)p + 1] = make_float4(g[4], g[5], g[6], oma);
         geom[3 * (size_t)p + 2] = make_float4(g[8], g[9], g[10], __uint_as_float(flags));
+        float aux[4] = {0.f, 0.f, 0.f, -1.f};
+        if ((flags & WRT_PRIM_KIND_MASK) == WRT_PRIM_TRIANGLE) wrt_triangle_aux(g + 4, g + 8, aux);
+        tri_aux[p] = make_float4(aux[0], aux[1], aux[2], aux[3]);
         const float* nn = prim_normals + 9 * (size_t)p;
         const float* uv = prim_uv + 6 * (size_t)p;
         attr[4 * (size_t)p + 0] = make_float4(nn[0], nn[1], nn[2], uv[0]);

@@ -28,6 +28,8 @@ struct DevScene {
                               // directional-shadow loop (Renderer.hpp:381-400)
     const float4* geom;
     const float4* prim_box;   // per prim {pMin.xyz, 0} {pMax.xyz, 0}: the primitive's own (leaf) box, for the occluder cache
+    const float4* tri_aux;    // per prim {unit plane normal, |E1|+|E2|} (w < 0: do not filter): ray-independent terms of the
+                              // candidate-list pruning (shaft_cull.h wrt_triangle_aux)
     const float4* attr;       // per prim 4x float4: {n0,uv0.x} {n1,uv0.y} {n2,uv1.x} {uv1.y,uv2.x,uv2.y,0}
     const int4*   ids;        // per prim {material, texture, normalmap, object}
     const int*    object_prim;

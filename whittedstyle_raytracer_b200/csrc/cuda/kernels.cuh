@@ -767,51 +767,88 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
 #ifndef WRT_FILTER_MIN
 #define WRT_FILTER_MIN 3          // shorter lists are not worth the pyramid set-up
 #endif
+// A warp takes 32 consecutive requests: (A) each lane builds its request's pyramid (4 cross products, 8 square roots, 4
+// divisions — once per request, not once per lane) into shared memory; (B) the warp goes through the 32 lists, one
+// candidate per lane: geometry + the primitive's precomputed plane normal and edge scale (DevScene::tri_aux), the two
+// tests, ballot compaction in place (order kept).
 __global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                      SoftListBuffers lb) {
-    const unsigned lane = threadIdx.x & 31;
+    __shared__ float s_py[4][32][WRT_PYRAMID_FLOATS + 1];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
-    const unsigned warps = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned warps = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned n_empty = 0;
-    for (unsigned req = gw; req < nreq; req += warps) {
-        const int2 ref = lb.ref[req];
-        if (ref.y < WRT_FILTER_MIN) continue;
-        const float4 o4 = fb.preq_o[q][req];
-        const uint4 k = fb.preq_k[q][req];
-        const WrtLight* L = s.lights + k.x;
-        float tri[9];
-        for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
-        const float o[3] = {o4.x, o4.y, o4.z};
-        WrtShaftPyramid py;
-        wrt_pyramid_make(o, tri, &py);
-        if (!py.ok) continue;
-        int* list = lb.pool + ref.x;
-        int kept = 0;
-        for (int b0 = 0; b0 < ref.y; b0 += 32) {
-            const int i = b0 + (int)lane;
-            int prim = -1;
-            bool keep = false;
-            if (i < ref.y) {
-                prim = list[i];
-                const float4* g = s.geom + 3 * (size_t)prim;
-                const float4 A = ldg4(g), B = ldg4(g + 1), C = ldg4(g + 2);
-                keep = true;
-                if ((__float_as_uint(C.w) & WRT_PRIM_KIND_MASK) == WRT_PRIM_TRIANGLE) {
-                    const float v0[3] = {A.x, A.y, A.z}, E1[3] = {B.x, B.y, B.z}, E2[3] = {C.x, C.y, C.z};
-                    keep = wrt_pyramid_triangle_may_block(&py, v0, E1, E2);
+    for (unsigned base = gw * 32u; base < nreq; base += warps * 32u) {
+        // ---- A ----
+        const unsigned req = base + lane;
+        int2 ref = make_int2(0, 0);
+        bool ok = false;
+        if (req < nreq) {
+            ref = lb.ref[req];
+            if (ref.y >= WRT_FILTER_MIN) {
+                const float4 o4 = fb.preq_o[q][req];
+                const uint4 k = fb.preq_k[q][req];
+                const WrtLight* L = s.lights + k.x;
+                float tri[9];
+                for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
+                const float o[3] = {o4.x, o4.y, o4.z};
+                WrtShaftPyramid py;
+                wrt_pyramid_make(o, tri, &py);
+                ok = py.ok != 0;
+                float* d = s_py[warp][lane];
+                d[0] = py.o[0]; d[1] = py.o[1]; d[2] = py.o[2];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    d[3 + 3 * j] = py.D[j][0]; d[4 + 3 * j] = py.D[j][1]; d[5 + 3 * j] = py.D[j][2];
+                    d[15 + j] = py.Dlen[j];
+                    d[19 + 3 * j] = py.N[j][0]; d[20 + 3 * j] = py.N[j][1]; d[21 + 3 * j] = py.N[j][2];
                 }
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, keep);
-            __syncwarp();                                  // every lane has read its entry before any entry is overwritten
-            if (keep && WRT_IN_BOUNDS((unsigned)ref.x + kept + __popc(mask & lt_mask), lb.pool_cap))
-                list[kept + __popc(mask & lt_mask)] = prim;
-            kept += __popc(mask);
         }
-        if (lane == 0) {
-            lb.ref[req] = make_int2(ref.x, kept);
-            if (kept == 0) ++n_empty;                      // lit, and no ray needs to be built (statistics)
+        __syncwarp();
+        // ---- B ----
+        unsigned todo = __ballot_sync(0xffffffffu, ok);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int off = __shfl_sync(0xffffffffu, ref.x, r), cnt = __shfl_sync(0xffffffffu, ref.y, r);
+            WrtShaftPyramid py;
+            const float* d = s_py[warp][r];
+            py.o[0] = d[0]; py.o[1] = d[1]; py.o[2] = d[2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                py.D[j][0] = d[3 + 3 * j]; py.D[j][1] = d[4 + 3 * j]; py.D[j][2] = d[5 + 3 * j];
+                py.Dlen[j] = d[15 + j];
+                py.N[j][0] = d[19 + 3 * j]; py.N[j][1] = d[20 + 3 * j]; py.N[j][2] = d[21 + 3 * j];
+            }
+            py.ok = 1;
+            int* list = lb.pool + off;
+            int kept = 0;
+            for (int b0 = 0; b0 < cnt; b0 += 32) {
+                const int i = b0 + (int)lane;
+                int prim = -1;
+                bool keep = false;
+                if (i < cnt) {
+                    prim = list[i];
+                    const float4* g = s.geom + 3 * (size_t)prim;
+                    const float4 A = ldg4(g), B = ldg4(g + 1), C = ldg4(g + 2), X = ldg4(s.tri_aux + prim);
+                    const float v0[3] = {A.x, A.y, A.z}, E1[3] = {B.x, B.y, B.z}, E2[3] = {C.x, C.y, C.z};
+                    const float aux[4] = {X.x, X.y, X.z, X.w};
+                    keep = wrt_pyramid_triangle_may_block(&py, v0, E1, E2, aux);
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();                              // every lane has read its entry before any entry is overwritten
+                if (keep && WRT_IN_BOUNDS((unsigned)off + kept + __popc(mask & lt_mask), lb.pool_cap))
+                    list[kept + __popc(mask & lt_mask)] = prim;
+                kept += __popc(mask);
+            }
+            if ((int)lane == r) {
+                lb.ref[req] = make_int2(off, kept);
+                if (kept == 0) ++n_empty;                  // lit, and no ray needs to be built (statistics)
+            }
         }
+        __syncwarp();                                      // the pyramids are rebuilt by the next block of requests
     }
     n_empty = __reduce_add_sync(0xffffffffu, n_empty);
     if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);

@@ -281,6 +281,7 @@ typedef struct WrtShaftPyramid {
     float N[4][3];         /* unit inward normals of the side planes (plane k holds o, corner k, corner k+1) */
     int ok;
 } WrtShaftPyramid;
+#define WRT_PYRAMID_FLOATS 32          /* words a WrtShaftPyramid occupies when staged in shared memory */
 
 WRT_SHAFT_HD void wrt_pyramid_make(const float o[3], const float tri[9], WrtShaftPyramid* p) {
     for (int k = 0; k < 3; k++) {
@@ -297,54 +298,60 @@ WRT_SHAFT_HD void wrt_pyramid_make(const float o[3], const float tri[9], WrtShaf
         const float* b = p->D[(k + 1) & 3];
         float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
         const float l = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-        if (!(l > 0.f) || !(l < 1e30f)) { p->ok = 0; return; }
-        const float il = 1.f / l;
+        if (!(l > 0.f) || !(l < 1e30f)) { p->ok = 0; n[0] = n[1] = n[2] = 0.f; }
+        const float il = p->ok ? 1.f / l : 0.f;
         n[0] *= il; n[1] *= il; n[2] *= il;
         const float* c = p->D[(k + 2) & 3];
         const float* d = p->D[(k + 3) & 3];
         float s2 = n[0] * c[0] + n[1] * c[1] + n[2] * c[2], s3 = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
         if (s2 < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; s2 = -s2; s3 = -s3; }
         const float dm = fmaxf(p->Dlen[(k + 2) & 3], p->Dlen[(k + 3) & 3]);
-        if (!(s2 > 1e-3f * dm) || !(s3 > 1e-3f * dm)) { p->ok = 0; return; }     /* edge-on: no filtering */
+        if (!(s2 > 1e-3f * dm) || !(s3 > 1e-3f * dm)) p->ok = 0;                  /* edge-on: no filtering */
         p->N[k][0] = n[0]; p->N[k][1] = n[1]; p->N[k][2] = n[2];
     }
 }
 
-/* false = the triangle (v0, E1 = v1 - v0, E2 = v2 - v0) provably blocks no sample ray of the request. */
-WRT_SHAFT_HD bool wrt_pyramid_triangle_may_block(const WrtShaftPyramid* p, const float v0[3], const float E1[3], const float E2[3]) {
-    if (!p->ok) return true;
-    float w[3][3], wl[3];
+/* Ray-independent terms of a triangle, computed once per primitive at upload: unit normal of its plane and
+ * |E1| + |E2| (the scale of the acceptance slack).  aux = {n.x, n.y, n.z, esz}; esz < 0 marks "do not filter"
+ * (degenerate triangle, non-finite data, or not a triangle). */
+WRT_SHAFT_HD void wrt_triangle_aux(const float E1[3], const float E2[3], float aux[4]) {
+    float n[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};
+    const float l = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const float esz = sqrtf(E1[0] * E1[0] + E1[1] * E1[1] + E1[2] * E1[2]) + sqrtf(E2[0] * E2[0] + E2[1] * E2[1] + E2[2] * E2[2]);
+    if (!(l > 0.f) || !(l < 1e30f) || !(esz < 1e30f)) { aux[0] = aux[1] = aux[2] = 0.f; aux[3] = -1.f; return; }
+    const float il = 1.f / l;
+    aux[0] = n[0] * il; aux[1] = n[1] * il; aux[2] = n[2] * il; aux[3] = esz;
+}
+
+/* false = the triangle (v0, E1 = v1 - v0, E2 = v2 - v0; aux from wrt_triangle_aux) provably blocks no sample ray of
+ * the request.  Distances from o enter the margins through the L1 norm (>= the Euclidean one: more margin, no sqrt). */
+WRT_SHAFT_HD bool wrt_pyramid_triangle_may_block(const WrtShaftPyramid* p, const float v0[3], const float E1[3], const float E2[3],
+                                                 const float aux[4]) {
+    const float esz = aux[3];
+    if (!p->ok || !(esz >= 0.f)) return true;
+    float w[3][3], m[3];
     for (int k = 0; k < 3; k++) {
         w[0][k] = v0[k] - p->o[k];
         w[1][k] = (v0[k] + E1[k]) - p->o[k];
         w[2][k] = (v0[k] + E2[k]) - p->o[k];
     }
-    for (int i = 0; i < 3; i++) wl[i] = sqrtf(w[i][0] * w[i][0] + w[i][1] * w[i][1] + w[i][2] * w[i][2]);
-    const float esz = sqrtf(E1[0] * E1[0] + E1[1] * E1[1] + E1[2] * E1[2]) + sqrtf(E2[0] * E2[0] + E2[1] * E2[1] + E2[2] * E2[2]);
-    if (!(esz < 1e30f)) return true;
+    for (int i = 0; i < 3; i++) m[i] = 1e-4f * (fabsf(w[i][0]) + fabsf(w[i][1]) + fabsf(w[i][2])) + 2e-5f * esz + 1e-5f;
     for (int k = 0; k < 4; k++) {                          /* side planes */
         bool out = true;
         for (int i = 0; i < 3; i++) {
             const float s = p->N[k][0] * w[i][0] + p->N[k][1] * w[i][1] + p->N[k][2] * w[i][2];
-            const float m = 1e-4f * wl[i] + 2e-5f * esz + 1e-5f;
-            if (!(s < -m)) { out = false; break; }
+            out = out && (s < -m[i]);
         }
         if (out) return false;
     }
-    float n[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};   /* own plane */
-    const float l = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-    if (l > 0.f && l < 1e30f) {
-        const float il = 1.f / l;
-        n[0] *= il; n[1] *= il; n[2] *= il;
-        const float ho = -(n[0] * w[0][0] + n[1] * w[0][1] + n[2] * w[0][2]);          /* height of o over the plane */
-        if (fabsf(ho) > 1e-3f * esz + 2e-5f) {
-            bool same = true;
-            for (int j = 0; j < 4; j++) {
-                const float H = n[0] * (p->D[j][0] - w[0][0]) + n[1] * (p->D[j][1] - w[0][1]) + n[2] * (p->D[j][2] - w[0][2]);
-                if (!(H * ho > 0.f) || !(fabsf(H) > 1e-3f * esz + 1e-4f * p->Dlen[j])) { same = false; break; }
-            }
-            if (same) return false;
+    const float ho = -(aux[0] * w[0][0] + aux[1] * w[0][1] + aux[2] * w[0][2]);      /* own plane: height of o over it */
+    if (fabsf(ho) > 1e-3f * esz + 2e-5f) {
+        bool same = true;
+        for (int j = 0; j < 4; j++) {
+            const float H = aux[0] * (p->D[j][0] - w[0][0]) + aux[1] * (p->D[j][1] - w[0][1]) + aux[2] * (p->D[j][2] - w[0][2]);
+            same = same && (H * ho > 0.f) && (fabsf(H) > 1e-3f * esz + 1e-4f * p->Dlen[j]);
         }
+        if (same) return false;
     }
     return true;
 }

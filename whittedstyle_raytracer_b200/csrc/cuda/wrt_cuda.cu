@@ -809,11 +809,12 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     ds.texels = (const float*)dptr(14);
 
     // ---- 2. device-side layouts ----
-    float4 *geom = nullptr, *attr = nullptr, *mats = nullptr, *pbox = nullptr, *fnodes = nullptr, *dnodes = nullptr, *onodes = nullptr, *ronodes = nullptr;
+    float4 *geom = nullptr, *attr = nullptr, *mats = nullptr, *pbox = nullptr, *taux = nullptr, *fnodes = nullptr, *dnodes = nullptr, *onodes = nullptr, *ronodes = nullptr;
     int4* ids = nullptr;
     int* d_flags = nullptr;
     if (dev_alloc(c, (size_t)np * 48, (void**)&geom) || dev_alloc(c, (size_t)np * 64, (void**)&attr) || dev_alloc(c, (size_t)np * 16, (void**)&ids) ||
         dev_alloc(c, (size_t)s->n_materials * 48, (void**)&mats) || dev_alloc(c, (size_t)np * 32, (void**)&pbox) ||
+        dev_alloc(c, (size_t)np * 16, (void**)&taux) ||
         dev_alloc(c, (size_t)nn * 32, (void**)&fnodes) || dev_alloc(c, (size_t)nn * 32, (void**)&dnodes) ||
         dev_alloc(c, (size_t)nn * 32 * 8, (void**)&onodes) || dev_alloc(c, (size_t)nn * 32 * 8, (void**)&ronodes) ||
         dev_alloc(c, (wrt::BS_TOTAL + 16) * sizeof(int), (void**)&d_flags))
@@ -832,13 +833,13 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         wrt::k_pack_prims<<<std::min(wide, (np + 255) / 256), 256, 0, st>>>(
             np, (const float*)dptr(1), (const unsigned*)dptr(2), (const int*)dptr(3), (const int*)dptr(4), (const int*)dptr(5),
             (const int*)dptr(6), (const float*)dptr(8), (const float*)dptr(9), (const float*)dptr(10), s->n_materials, s->n_textures,
-            s->n_normalmaps, geom, attr, ids, d_flags);
+            s->n_normalmaps, geom, attr, ids, taux, d_flags);
     }
     if (s->n_materials > 0) {
         ++c->launches;
         wrt::k_pack_materials<<<std::min(wide, (s->n_materials + 255) / 256), 256, 0, st>>>((const float*)dptr(10), s->n_materials, mats);
     }
-    ds.geom = geom; ds.attr = attr; ds.ids = ids; ds.materials = mats; ds.prim_box = pbox;
+    ds.geom = geom; ds.attr = attr; ds.ids = ids; ds.materials = mats; ds.prim_box = pbox; ds.tri_aux = taux;
     ds.fnodes = fnodes; ds.dnodes = dnodes; ds.onodes = onodes; ds.ronodes = ronodes;
 
     // ---- 3. trees ----

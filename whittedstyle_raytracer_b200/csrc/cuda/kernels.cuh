@@ -393,7 +393,10 @@ __global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScen
 }
 
 // ---- K3: hit -> surface, shadow requests, child rays: one streaming pass, whole warps call surface_warp() ----
-__global__ void __launch_bounds__(256) k_surface_spawn(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
+#ifndef WRT_SURFACE_MIN_BLOCKS
+#define WRT_SURFACE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, WRT_SURFACE_MIN_BLOCKS) k_surface_spawn(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
                                                        const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int cull) {
     const LevelSpan span = level_span(fb, level, n0);
     const unsigned n = span.count();
@@ -771,7 +774,10 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
 // divisions — once per request, not once per lane) into shared memory; (B) the warp goes through the 32 lists, one
 // candidate per lane: geometry + the primitive's precomputed plane normal and edge scale (DevScene::tri_aux), the two
 // tests, ballot compaction in place (order kept).
-__global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
+#ifndef WRT_FILTER_MIN_BLOCKS
+#define WRT_FILTER_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, WRT_FILTER_MIN_BLOCKS) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                      SoftListBuffers lb) {
     __shared__ float s_py[4][32][WRT_PYRAMID_FLOATS + 1];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

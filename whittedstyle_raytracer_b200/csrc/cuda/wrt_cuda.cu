@@ -96,7 +96,7 @@ struct WrtContext {
     int refill0 = 32;                  // level 0 (coherent primary rays and their shadow rays)
     int trace_blocks_per_sm = 10;      // persistent shadow / unfused closest-hit kernels
     bool shade0_separate = true;       // level 0 is shaded by its own launch on the side stream (else inside combine)
-    int soft_filter = 1;               // 0: off, 1: prune the deep queues' candidate lists (k_soft_filter), 2: level 0's as well
+    int soft_filter = 2;               // 0: off, 1: prune the deep queues' candidate lists (k_soft_filter), 2: level 0's as well
     int deep_split = 8;                // request queues: level 0 | levels 1..deep_split | deeper (8: one deep queue; 3 queues
                                        // bought nothing at 1/8 frame size and cost 0.2 ms on a full frame)
     int side_blocks_per_sm = 0;        // persistent shadow kernels on the side stream: CTAs per SM (0 = trace_blocks_per_sm)
@@ -368,7 +368,7 @@ int enqueue_shadows(WrtContext* c, cudaStream_t st, int q, int& work_seq) {
                     LaunchScope ls(c, st, F_SOFT_LISTS);
                     k_soft_lists<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->stack_rows, lb);
                 }
-                if (c->soft_filter >= (q == 0 ? 2 : 1)) {            // triangle-level pruning of the lists (deep queues by default)
+                if (c->soft_filter >= (q == 0 ? 2 : 1)) {            // triangle-level pruning of the lists
                     LaunchScope ls(c, st, F_SOFT_FILTER);
                     k_soft_filter<<<wide_grid, TB, 0, st>>>(ds, fb, q, lb);
                 }

@@ -393,8 +393,10 @@ __global__ void WRT_TRACE_BOUNDS k_trace_closest(const __grid_constant__ DevScen
 }
 
 // ---- K3: hit -> surface, shadow requests, child rays: one streaming pass, whole warps call surface_warp() ----
+// (launch bound: 64 registers = 4 CTAs of 256 per SM.  Unbounded the kernel takes 80 registers, 3 CTAs: 1.67 ms per 4K
+// frame against 1.61 / hard-shadow frame 1.72 against 1.36; 5 CTAs (48 registers) spill too much: 1.97.)
 #ifndef WRT_SURFACE_MIN_BLOCKS
-#define WRT_SURFACE_MIN_BLOCKS 1
+#define WRT_SURFACE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, WRT_SURFACE_MIN_BLOCKS) k_surface_spawn(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb,
                                                        const __grid_constant__ PrimaryGen pg, int level, unsigned n0, int cull) {
@@ -774,10 +776,9 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
 // divisions — once per request, not once per lane) into shared memory; (B) the warp goes through the 32 lists, one
 // candidate per lane: geometry + the primitive's precomputed plane normal and edge scale (DevScene::tri_aux), the two
 // tests, ballot compaction in place (order kept).
-#ifndef WRT_FILTER_MIN_BLOCKS
-#define WRT_FILTER_MIN_BLOCKS 1
-#endif
-__global__ void __launch_bounds__(128, WRT_FILTER_MIN_BLOCKS) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
+// (no minimum-blocks bound: 78 registers, 6 CTAs per SM, 2.03 ms per 4K frame; bounded to 8 / 10 / 12 CTAs: 2.03 / 2.62 /
+// 3.28 ms — the pyramid spills)
+__global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                      SoftListBuffers lb) {
     __shared__ float s_py[4][32][WRT_PYRAMID_FLOATS + 1];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(256) k_pack_prims(int n_prims, const float* __
                                                     const float* __restrict__ materials, int n_materials, int n_textures, int n_normalmaps,
                                                     float4* geom, float4* attr, int4* ids, float4* tri_aux, int* flags_out) {
     int bad = 0;
+    float slack = 0.f;                                      // prune_rule.h: scene maximum of the triangles' acceptance slack
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_prims; p += gridDim.x * blockDim.x) {
         const float* g = prim_geom + 12 * (size_t)p;
         const int mat = prim_material[p];
@@ -255,7 +256,10 @@ __global__ void __launch_bounds__(256) k_pack_prims(int n_prims, const float* __
         geom[3 * (size_t)p + 1] = make_float4(g[4], g[5], g[6], oma);
         geom[3 * (size_t)p + 2] = make_float4(g[8], g[9], g[10], __uint_as_float(flags));
         float aux[4] = {0.f, 0.f, 0.f, -1.f};
-        if ((flags & WRT_PRIM_KIND_MASK) == WRT_PRIM_TRIANGLE) wrt_triangle_aux(g + 4, g + 8, aux);
+        if ((flags & WRT_PRIM_KIND_MASK) == WRT_PRIM_TRIANGLE) {
+            wrt_triangle_aux(g + 4, g + 8, aux);
+            slack = fmaxf(slack, wrt_prune_triangle_slack(g + 4, g + 8));
+        }
         tri_aux[p] = make_float4(aux[0], aux[1], aux[2], aux[3]);
         const float* nn = prim_normals + 9 * (size_t)p;
         const float* uv = prim_uv + 6 * (size_t)p;
@@ -269,6 +273,8 @@ __global__ void __launch_bounds__(256) k_pack_prims(int n_prims, const float* __
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicOr(flags_out, bad);       // bit 0: a light avatar exists; 1: a map is missing; 2: bad material
+    const unsigned sb = __reduce_max_sync(0xffffffffu, __float_as_uint(slack));   // (non-negative floats order like their bits)
+    if ((threadIdx.x & 31) == 0 && sb) atomicMax(reinterpret_cast<unsigned*>(flags_out) + 1, sb);
 }
 
 // WrtMaterial (12 floats) -> {Od.rgb, ka} {Os.rgb, kd} {ks, n, alpha, eta}

@@ -11,6 +11,7 @@
 // ties" is "smaller primitive index wins".
 #pragma once
 #include "dev_math.cuh"
+#include "prune_rule.h"
 #include "../../../include/wrt_scene.h"
 
 namespace wrt {
@@ -45,6 +46,7 @@ struct DevScene {
     float bkg[3], eta;
     float dc[3], amin, amax, distmin, distmax;
     float eye[3];
+    float prune_slack;        // max over the triangles of how far outside its box an accepted hit can lie (prune_rule.h)
 };
 
 struct Ray {
@@ -227,24 +229,29 @@ struct Closest {
 
 // ---- closest hit: getIntersection, BVH.hpp:137-159 ----
 // Minimum t over every primitive whose own box and intersection test pass; ties go to the
-// smaller reference DFS rank (the left subtree of BVH.hpp:157).  With prune_rel >= 0 a box
-// entered beyond best_t*(1+prune_rel)+prune_rel is skipped: its primitives lie inside it,
-// so they cannot be closer; the margin absorbs the ulp-level disagreement between slab and
-// Moller-Trumbore distances.  prune_rel < 0 visits every hit box like the reference does.
+// smaller reference DFS rank (the left subtree of BVH.hpp:157).  With prune_scale >= 0 a box
+// entered beyond wrt_prune_limit(best_t, prune_scale) is skipped (prune_rule.h: why no primitive
+// inside it can be accepted with a smaller t; prune_scale is the ray's own part of the margin).
+// prune_scale < 0 visits every hit box like the reference does.
 struct ClosestState {
     Closest best;
     float limit;
-    float prune_rel;
+    float prune_scale;
     __device__ __forceinline__ void reset(float prune) {
         best.t = FLT_MAX; best.prim = -1; best.u = 0.f; best.v = 0.f;
-        limit = FLT_MAX; prune_rel = prune;
+        limit = FLT_MAX; prune_scale = prune;
+    }
+    // pruning on (prune_cfg >= 0): the margin of this ray; off: -1
+    __device__ __forceinline__ void set_ray(const DevScene& s, const Ray& r, float prune_cfg) {
+        const float o[3] = {r.o.x, r.o.y, r.o.z}, inv[3] = {r.inv.x, r.inv.y, r.inv.z};
+        prune_scale = prune_cfg >= 0.f ? wrt_prune_ray_scale(o, inv, s.prune_slack) : -1.f;
     }
     __device__ __forceinline__ void leaf(const DevScene& s, const Ray& r, int p) {
         PrimHit h; float oma; unsigned fl;
         if (prim_test(s, p, r, h, oma, fl)) {
             if (h.t < best.t || (h.t == best.t && p < best.prim)) {
                 best.t = h.t; best.prim = p; best.u = h.u; best.v = h.v;
-                if (prune_rel >= 0.f) limit = fabsf(h.t) * prune_rel + prune_rel + h.t;
+                if (prune_scale >= 0.f) limit = wrt_prune_limit(h.t, prune_scale);
             }
         }
     }
@@ -265,6 +272,7 @@ __device__ __forceinline__ Closest closest_hit(const DevScene& s, const float4* 
                                                float prune_rel) {
     ClosestState cs;
     cs.reset(prune_rel);
+    cs.set_ray(s, r, prune_rel);
     int cur = 0;
     st.sp = 0;
     if (cs.begin(s, nodes, root, r, cur)) {

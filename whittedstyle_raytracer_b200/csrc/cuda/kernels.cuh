@@ -63,6 +63,7 @@ enum CounterSlot {
     C_NSKIP = 144,               // [9] point-light requests whose light terms vanish (dev_shade.cuh), never queued
     C_NDSKIP = 160,              // [9] the same for directional lights
     C_POOL = 176,                // [WRT_QUEUES] fill level of the candidate-list pools (k_soft_lists)
+    C_NWORK = 180,               // [WRT_QUEUES] requests that still need rays after k_soft_filter (SoftListBuffers::work)
     C_WORK = 192,                // [<= 32 x 2] work-distribution counters (64-bit), one per persistent launch
     C_TOTAL = 256
 };
@@ -363,7 +364,7 @@ struct ClosestQuery {
         const bool ref_tree = prune < 0.f || degenerate_dir(r.d);       // literal walk / axis-degenerate ray
         if (ref_tree) prune = -1.f;
         nodes = (ref_tree ? s.ronodes : s.onodes) + (size_t)ray_octant(r.d) * 2 * (size_t)s.n_nodes;
-        cs.prune_rel = prune;
+        cs.set_ray(s, r, prune);
         float te;
         float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
         if (!slab_presorted(lo, hi, r, te)) return false;
@@ -587,6 +588,7 @@ struct SoftListBuffers {
     float* shafts;        // WRT_LISTS_CHUNK x 10 floats per warp of the grid: the shafts of the warp's current chunk
     int*  pool;           // the lists
     int2* ref;            // per request: {pool offset, count}
+    unsigned* work;       // k_soft_filter: the requests that need rays (non-empty list, or count < 0), compacted
     unsigned pool_cap;
     unsigned region_per_request;   // pool entries a warp reserves per request of its chunk (one atomic per chunk)
 };
@@ -773,14 +775,19 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
 #define WRT_FILTER_MIN 3          // shorter lists are not worth the pyramid set-up
 #endif
 // A warp takes 32 consecutive requests: (A) each lane builds its request's pyramid (4 cross products, 8 square roots, 4
-// divisions — once per request, not once per lane) into shared memory; (B) the warp goes through the 32 lists, one
-// candidate per lane: geometry + the primitive's precomputed plane normal and edge scale (DevScene::tri_aux), the two
-// tests, ballot compaction in place (order kept).
-// (no minimum-blocks bound: 78 registers, 6 CTAs per SM, 2.03 ms per 4K frame; bounded to 8 / 10 / 12 CTAs: 2.03 / 2.62 /
-// 3.28 ms — the pyramid spills)
+// divisions — once per request, not once per candidate) into shared memory; (B) the 32 lists are treated as ONE sequence
+// of (request, candidate) pairs, 32 pairs per step, one per lane: most lists of fully lit requests hold 1-4 candidates, and
+// a warp that took the lists one after the other (round 2's first version: 18 of 32 lanes, lane-issue utilisation 0.23)
+// idled on them.  A lane finds its pair's request by binary search over the lists' start offsets, loads geometry + the
+// primitive's precomputed plane normal and edge scale (DevScene::tri_aux) and the request's pyramid (row stride 33 words:
+// lanes on different requests hit different banks), runs the tests, and the survivors are compacted in place, order
+// kept: rank = kept-so-far of the request (shared memory) + survivors of the same request on lower lanes
+// (__match_any_sync).  A request's write cursor never passes its read cursor, and every step reads before it writes.
+// (no minimum-blocks bound: the pyramid spills under one)
 __global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                      SoftListBuffers lb) {
     __shared__ float s_py[4][32][WRT_PYRAMID_FLOATS + 1];
+    __shared__ int s_start[4][33], s_off[4][32], s_kept[4][32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
@@ -791,11 +798,13 @@ __global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ Dev
         const unsigned req = base + lane;
         int2 ref = make_int2(0, 0);
         bool ok = false;
+        size_t out = 0;
         if (req < nreq) {
             ref = lb.ref[req];
+            const float4 o4 = fb.preq_o[q][req];
+            const uint4 k = fb.preq_k[q][req];
+            out = (size_t)__float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
             if (ref.y >= WRT_FILTER_MIN) {
-                const float4 o4 = fb.preq_o[q][req];
-                const uint4 k = fb.preq_k[q][req];
                 const WrtLight* L = s.lights + k.x;
                 float tri[9];
                 for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
@@ -813,47 +822,76 @@ __global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ Dev
                 }
             }
         }
+        const int cnt = ok ? ref.y : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= (unsigned)off) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        s_start[warp][lane] = incl - cnt;
+        if (lane == 31) s_start[warp][32] = total;
+        s_off[warp][lane] = ref.x;
+        s_kept[warp][lane] = 0;
         __syncwarp();
         // ---- B ----
-        unsigned todo = __ballot_sync(0xffffffffu, ok);
-        while (todo) {
-            const int r = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int off = __shfl_sync(0xffffffffu, ref.x, r), cnt = __shfl_sync(0xffffffffu, ref.y, r);
-            WrtShaftPyramid py;
-            const float* d = s_py[warp][r];
-            py.o[0] = d[0]; py.o[1] = d[1]; py.o[2] = d[2];
+        for (int g0 = 0; g0 < total; g0 += 32) {
+            const int g = g0 + (int)lane;
+            unsigned r = 0xffffffffu;
+            int prim = -1, off = 0;
+            bool keep = false;
+            if (g < total) {
+                int lo = 0, hi = 31;                       // last request whose start offset is <= g (empty lists share a start)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                py.D[j][0] = d[3 + 3 * j]; py.D[j][1] = d[4 + 3 * j]; py.D[j][2] = d[5 + 3 * j];
-                py.Dlen[j] = d[15 + j];
-                py.N[j][0] = d[19 + 3 * j]; py.N[j][1] = d[20 + 3 * j]; py.N[j][2] = d[21 + 3 * j];
-            }
-            py.ok = 1;
-            int* list = lb.pool + off;
-            int kept = 0;
-            for (int b0 = 0; b0 < cnt; b0 += 32) {
-                const int i = b0 + (int)lane;
-                int prim = -1;
-                bool keep = false;
-                if (i < cnt) {
-                    prim = list[i];
-                    const float4* g = s.geom + 3 * (size_t)prim;
-                    const float4 A = ldg4(g), B = ldg4(g + 1), C = ldg4(g + 2), X = ldg4(s.tri_aux + prim);
-                    const float v0[3] = {A.x, A.y, A.z}, E1[3] = {B.x, B.y, B.z}, E2[3] = {C.x, C.y, C.z};
-                    const float aux[4] = {X.x, X.y, X.z, X.w};
-                    keep = wrt_pyramid_triangle_may_block(&py, v0, E1, E2, aux);
+                for (int it = 0; it < 5; it++) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_start[warp][mid] <= g) lo = mid; else hi = mid - 1;
                 }
-                const unsigned mask = __ballot_sync(0xffffffffu, keep);
-                __syncwarp();                              // every lane has read its entry before any entry is overwritten
-                if (keep && WRT_IN_BOUNDS((unsigned)off + kept + __popc(mask & lt_mask), lb.pool_cap))
-                    list[kept + __popc(mask & lt_mask)] = prim;
-                kept += __popc(mask);
+                r = (unsigned)lo;
+                off = s_off[warp][lo];
+                prim = lb.pool[off + (g - s_start[warp][lo])];
+                WrtShaftPyramid py;
+                const float* d = s_py[warp][lo];
+                py.o[0] = d[0]; py.o[1] = d[1]; py.o[2] = d[2];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    py.D[j][0] = d[3 + 3 * j]; py.D[j][1] = d[4 + 3 * j]; py.D[j][2] = d[5 + 3 * j];
+                    py.Dlen[j] = d[15 + j];
+                    py.N[j][0] = d[19 + 3 * j]; py.N[j][1] = d[20 + 3 * j]; py.N[j][2] = d[21 + 3 * j];
+                }
+                py.ok = 1;
+                const float4* gm = s.geom + 3 * (size_t)prim;
+                const float4 A = ldg4(gm), B = ldg4(gm + 1), C = ldg4(gm + 2), X = ldg4(s.tri_aux + prim);
+                const float v0[3] = {A.x, A.y, A.z}, E1[3] = {B.x, B.y, B.z}, E2[3] = {C.x, C.y, C.z};
+                const float aux[4] = {X.x, X.y, X.z, X.w};
+                keep = wrt_pyramid_triangle_may_block(&py, v0, E1, E2, aux);
             }
-            if ((int)lane == r) {
-                lb.ref[req] = make_int2(off, kept);
-                if (kept == 0) ++n_empty;                  // lit, and no ray needs to be built (statistics)
-            }
+            const unsigned same = __match_any_sync(0xffffffffu, r);            // lanes working on the same request
+            const unsigned kmask = __ballot_sync(0xffffffffu, keep) & same;
+            const int kept0 = r != 0xffffffffu ? s_kept[warp][r] : 0;
+            __syncwarp();                                  // every lane has read its entry and its request's cursor
+            if (keep && WRT_IN_BOUNDS((unsigned)off + kept0 + __popc(kmask & lt_mask), lb.pool_cap))
+                lb.pool[off + kept0 + __popc(kmask & lt_mask)] = prim;
+            if (r != 0xffffffffu && (same & lt_mask) == 0u) s_kept[warp][r] = kept0 + __popc(kmask);
+            __syncwarp();
+        }
+        int final_cnt = ref.y;                             // 0: empty already; < 0: ray by ray; else a list this kernel left alone
+        if (ok) {
+            final_cnt = s_kept[warp][lane];
+            lb.ref[req] = make_int2(ref.x, final_cnt);
+            if (final_cnt == 0) ++n_empty;                 // lit, and no ray needs to be built (statistics)
+        }
+        // ---- C: an empty list answers the request (all samples lit: the coefficient's start value 0 + 50, what the ray
+        // kernel's atomics would add up to); the others go, compacted, to the ray kernel's work list ----
+        const bool live = req < nreq;
+        if (live && final_cnt == 0 && WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) fb.coeff[out] = (float)WRT_SOFT_SAMPLES;
+        const unsigned need = __ballot_sync(0xffffffffu, live && final_cnt != 0);
+        if (need) {
+            unsigned w0 = 0;
+            if (lane == 0) w0 = atomicAdd(fb.counters + C_NWORK + q, (unsigned)__popc(need));
+            w0 = __shfl_sync(0xffffffffu, w0, 0);
+            if (((need >> lane) & 1u) && WRT_IN_BOUNDS(w0 + __popc(need & lt_mask), fb.preq_cap[q])) lb.work[w0 + __popc(need & lt_mask)] = req;
         }
         __syncwarp();                                      // the pyramids are rebuilt by the next block of requests
     }
@@ -861,13 +899,16 @@ __global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ Dev
     if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);
 }
 
+// use_work != 0: k_soft_filter ran on this queue — it answered the requests whose list is empty and left the ids of the
+// others in lb.work; the passes then run over those only (9 of 10 queued deep requests of the metric frame end up empty).
 __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
-                                                  int work_slot, unsigned seed, SoftListBuffers lb) {
+                                                  int work_slot, unsigned seed, SoftListBuffers lb, int use_work) {
     extern __shared__ int smem[];
     Stack st;
     st.init(smem, threadIdx.x, blockDim.x);
     const unsigned lane = threadIdx.x & 31;
-    const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);      // host guarantees nreq * 50 < 2^32
+    const unsigned nreq = use_work ? queue_len(fb.counters, C_NWORK + q, fb.preq_cap[q])
+                                   : queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);   // host guarantees nreq * 50 < 2^32
     const unsigned n_rays = nreq * WRT_SOFT_SAMPLES, n_pass = (n_rays + 31u) / 32u;
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
     while (true) {
@@ -879,16 +920,17 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
 #pragma unroll 1
         for (unsigned pass = p0; pass < p1; pass++) {
             const unsigned j = pass * 32u + lane;
-            const unsigned req = j / WRT_SOFT_SAMPLES, sample = j - req * WRT_SOFT_SAMPLES;
+            const unsigned w = j / WRT_SOFT_SAMPLES, sample = j - w * WRT_SOFT_SAMPLES;      // w: position in the work sequence
+            const unsigned req = w < nreq ? (use_work ? lb.work[w] : w) : 0u;
             bool lit = false;
             size_t out = 0;
-            const int2 ref = req < nreq ? lb.ref[req] : make_int2(0, 0);
-            if (req < nreq && ref.y == 0) {
+            const int2 ref = w < nreq ? lb.ref[req] : make_int2(0, 0);
+            if (w < nreq && ref.y == 0) {
                 // empty list = no leaf box can be hit by any sample of this request (shaft_cull.h, axis-degenerate
                 // samples included): lit, and the ray itself is never needed
                 out = (size_t)__float_as_uint(fb.preq_o[q][req].w) * (unsigned)s.n_lights + fb.preq_k[q][req].x;
                 lit = true;
-            } else if (req < nreq) {
+            } else if (w < nreq) {
                 float4 o4 = fb.preq_o[q][req];
                 uint4 k = fb.preq_k[q][req];
                 f3 v0, v1, v2;
@@ -919,8 +961,8 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
             // one float atomic per request segment of the pass (small integer sums are exact and order-free)
             const unsigned lit_mask = __ballot_sync(0xffffffffu, lit);
             const unsigned rq0 = (pass * 32u) / WRT_SOFT_SAMPLES;
-            const unsigned first = __ballot_sync(0xffffffffu, req == rq0);       // lanes of the pass's first request
-            const unsigned mine = req == rq0 ? first : ~first;
+            const unsigned first = __ballot_sync(0xffffffffu, w == rq0);         // lanes of the pass's first request
+            const unsigned mine = w == rq0 ? first : ~first;
             const unsigned n_lit = __popc(lit_mask & mine);
             if (n_lit && lane == (unsigned)(__ffs(mine) - 1) && WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights))
                 atomicAdd(fb.coeff + out, (float)n_lit);

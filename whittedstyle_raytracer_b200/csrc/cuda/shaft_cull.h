@@ -259,12 +259,15 @@ WRT_SHAFT_HD bool wrt_shaft_is_empty(const float4* onodes, int n_nodes, const fl
 // shaft may hit; most of those triangles cannot be hit themselves.  A candidate is removed when it provably blocks no
 // sample: it is then never the reason a ray is occluded, so "OR over the list" keeps its value (a ray that tests it in
 // the reference gets "no hit with t < dis" from it).  The rays of a request are the segments from the origin o to points
-// of the light's parallelogram, i.e. they lie in the pyramid P = hull(o, 4 corners).  Two sufficient conditions, in exact
+// of the light's parallelogram, i.e. they lie in the pyramid P = hull(o, 4 corners).  Three sufficient conditions, in exact
 // geometry, each applied with a margin far above every rounding involved:
 //   side planes   all three vertices of the triangle lie outside ONE of the pyramid's four side planes (planes through o
 //                 and two adjacent corners): the triangle and the convex pyramid are disjoint;
 //   own plane     o and all four corners lie strictly on the same side of the triangle's plane: no segment o -> corner hull
 //                 crosses that plane, so every ray's plane parameter t is < 0 or > dis.
+//   edge planes   all four corners lie outside ONE of the three planes through o and a triangle edge: together with the
+//                 side planes these are all the separating planes two convex cones with apex o can have, so a triangle
+//                 that survives can really be hit by some ray from o into the parallelogram (or is too close to call).
 // Margins.  Triangle.hpp:41 accepts barycentrics and t down to -1e-5, i.e. points up to 1e-5 * (|E1| + |E2|) outside the
 // triangle and 1e-5 behind the origin; the samples' float evaluation moves a target by <= 1e-6 * |coordinate|
 // (shaft_cull.h header, step 1).  The tests demand 1e-4 relative (to the vertex / corner distance from o) plus 2e-5 * (|E1|
@@ -352,6 +355,38 @@ WRT_SHAFT_HD bool wrt_pyramid_triangle_may_block(const WrtShaftPyramid* p, const
             same = same && (H * ho > 0.f) && (fabsf(H) > 1e-3f * esz + 1e-4f * p->Dlen[j]);
         }
         if (same) return false;
+    }
+    /* edge planes: the plane through o and a triangle edge (a, b), oriented towards the third vertex c.  Seen from o, the
+     * triangle and the light are two convex polygons on the sphere of directions; they are disjoint iff an edge of one of
+     * them separates them — the four side planes above, or one of these three.  With unit normal n and all four corner
+     * directions at least (m + 1e-4) * Dmax outside it, every sample direction d has n.d < -(m + 1e-4); the only part of the
+     * slack-widened triangle outside the plane lies within `slack` of the edge's line, i.e. at least h - slack from o
+     * (h = distance from o to that line), where the ray is already (h - slack) * m = slack outside. */
+    {
+        const float slack = 2e-5f * esz + 1e-5f;
+        const float dmax = fmaxf(fmaxf(p->Dlen[0], p->Dlen[1]), fmaxf(p->Dlen[2], p->Dlen[3]));
+        for (int e = 0; e < 3; e++) {
+            const float* a = w[e];
+            const float* b = w[e == 2 ? 0 : e + 1];
+            const float* c = w[e == 0 ? 2 : e - 1];
+            const float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            const float l = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            const float ex = b[0] - a[0], ey = b[1] - a[1], ez = b[2] - a[2];
+            const float el = sqrtf(ex * ex + ey * ey + ez * ez);
+            if (!(l > 0.f) || !(el > 0.f) || !(l < 1e30f)) continue;
+            const float h = l / el;
+            if (!(h > 4.f * slack)) continue;
+            const float sc = n[0] * c[0] + n[1] * c[1] + n[2] * c[2];          /* l * (distance of c from the plane) */
+            if (!(fabsf(sc) > l * (1e-3f * esz + 1e-4f * (fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2]))))) continue;   /* o (almost) in the triangle's plane */
+            const float sgn = sc > 0.f ? 1.f : -1.f;
+            const float need = l * ((slack / (h - slack) + 1e-4f) * dmax);
+            bool out = true;
+            for (int j = 0; j < 4; j++) {
+                const float s = sgn * (n[0] * p->D[j][0] + n[1] * p->D[j][1] + n[2] * p->D[j][2]);
+                out = out && (s < -need);
+            }
+            if (out) return false;
+        }
     }
     return true;
 }

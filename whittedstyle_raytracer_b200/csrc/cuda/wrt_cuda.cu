@@ -287,6 +287,7 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
         if (frame_alloc(c, &lb.shafts, lists_possible ? (size_t)c->num_sms * c->trace_blocks_per_sm * 4 * WRT_LISTS_CHUNK * 10 : 1)) return 1;
         if (frame_alloc(c, &lb.pool, lb.pool_cap)) return 1;
         if (frame_alloc(c, &lb.ref, lists_possible ? fb.preq_cap[q] : 1)) return 1;
+        if (frame_alloc(c, &lb.work, lists_possible ? fb.preq_cap[q] : 1)) return 1;
     }
     c->batch_slots = slots;
     c->deep_slots = capd;
@@ -368,12 +369,13 @@ int enqueue_shadows(WrtContext* c, cudaStream_t st, int q, int& work_seq) {
                     LaunchScope ls(c, st, F_SOFT_LISTS);
                     k_soft_lists<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->stack_rows, lb);
                 }
-                if (c->soft_filter >= (q == 0 ? 2 : 1)) {            // triangle-level pruning of the lists
+                const bool filtered = c->soft_filter >= (q == 0 ? 2 : 1);
+                if (filtered) {                                     // triangle-level pruning of the lists
                     LaunchScope ls(c, st, F_SOFT_FILTER);
                     k_soft_filter<<<wide_grid, TB, 0, st>>>(ds, fb, q, lb);
                 }
                 LaunchScope ls(c, st, F_SHADOW_SOFT);
-                k_soft_list_rays<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->seed, lb);
+                k_soft_list_rays<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->seed, lb, filtered ? 1 : 0);
             } else {
                 LaunchScope ls(c, st, F_SHADOW_SOFT);
                 k_shadow_soft<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->seed, c->refill_soft | (c->chunk_div << 8),
@@ -932,6 +934,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         if (state[wrt::BS_ALLOC] != 2 * np - 1) return fail("wrt_upload_scene: device BVH build is incomplete (a primitive without a leaf record?)");
     }
     ds.has_light_prims = (flags & 1) ? 1 : 0;
+    memcpy(&ds.prune_slack, rb + 1, sizeof(float));     // k_pack_prims: scene maximum of wrt_prune_triangle_slack
     // the strategy queries never read texels; a frame render needs every referenced map present
     c->textures_complete = !(flags & 2);
     c->stack_rows = std::max(c->bvh_depth, fast_depth) + 2;

@@ -129,7 +129,8 @@ int main(int argc, char** argv) {
                     const float* g = S->prim_geom + 12 * (size_t)p;
                     float aux[4];
                     wrt_triangle_aux(g + 4, g + 8, aux);                              // (k_pack_prims computes this at upload)
-                    if ((S->prim_flags[p] & WRT_PRIM_KIND_MASK) != WRT_PRIM_TRIANGLE || wrt_pyramid_triangle_may_block(&py, g, g + 4, g + 8, aux)) filter_kept++;
+                    if ((S->prim_flags[p] & WRT_PRIM_KIND_MASK) != WRT_PRIM_TRIANGLE ||
+                        (wrt_pyramid_triangle_may_block(&py, g, g + 4, g + 8, aux) && wrt_pyramid_triangle_may_block_edges(&py, g, g + 4, g + 8, aux))) filter_kept++;   // both stages of k_soft_filter
                     else { removed.push_back(p); filter_removed++; }
                 }
             }

@@ -784,6 +784,71 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
 // kept: rank = kept-so-far of the request (shared memory) + survivors of the same request on lower lanes
 // (__match_any_sync).  A request's write cursor never passes its read cursor, and every step reads before it writes.
 // (no minimum-blocks bound: the pyramid spills under one)
+#ifndef WRT_FILTER_EDGE_MAX
+#define WRT_FILTER_EDGE_MAX 16    // survivor lists up to this length get the edge-plane stage
+#endif
+// One pass of k_soft_filter over the lists of a warp's 32 requests (lane r <-> request r): kept[r] entries of list r
+// (request r takes part iff `take`), all lists as one sequence of pairs, 32 per step; survivors compacted in place.
+template <int STAGE>
+__device__ __forceinline__ void filter_pass(const DevScene& s, const SoftListBuffers& lb, const float (*py_rows)[WRT_PYRAMID_FLOATS + 1],
+                                            int* start, const int* offs, int* kept, unsigned lane, bool take) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int cnt = take ? kept[lane] : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (unsigned)off) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    __syncwarp();
+    start[lane] = incl - cnt;
+    if (lane == 31) start[32] = total;
+    if (take) kept[lane] = 0;
+    __syncwarp();
+    for (int g0 = 0; g0 < total; g0 += 32) {
+        const int g = g0 + (int)lane;
+        unsigned r = 0xffffffffu;
+        int prim = -1, off = 0;
+        bool keep = false;
+        if (g < total) {
+            int lo = 0, hi = 31;                       // last request whose start offset is <= g (empty lists share a start)
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (start[mid] <= g) lo = mid; else hi = mid - 1;
+            }
+            r = (unsigned)lo;
+            off = offs[lo];
+            prim = lb.pool[off + (g - start[lo])];
+            WrtShaftPyramid py;
+            const float* d = py_rows[lo];
+            py.o[0] = d[0]; py.o[1] = d[1]; py.o[2] = d[2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                py.D[j][0] = d[3 + 3 * j]; py.D[j][1] = d[4 + 3 * j]; py.D[j][2] = d[5 + 3 * j];
+                py.Dlen[j] = d[15 + j];
+                py.N[j][0] = d[19 + 3 * j]; py.N[j][1] = d[20 + 3 * j]; py.N[j][2] = d[21 + 3 * j];
+            }
+            py.ok = 1;
+            const float4* gm = s.geom + 3 * (size_t)prim;
+            const float4 A = ldg4(gm), B = ldg4(gm + 1), C = ldg4(gm + 2), X = ldg4(s.tri_aux + prim);
+            const float v0[3] = {A.x, A.y, A.z}, E1[3] = {B.x, B.y, B.z}, E2[3] = {C.x, C.y, C.z};
+            const float aux[4] = {X.x, X.y, X.z, X.w};
+            keep = STAGE == 0 ? wrt_pyramid_triangle_may_block(&py, v0, E1, E2, aux) : wrt_pyramid_triangle_may_block_edges(&py, v0, E1, E2, aux);
+        }
+        const unsigned same = __match_any_sync(0xffffffffu, r);            // lanes working on the same request
+        const unsigned kmask = __ballot_sync(0xffffffffu, keep) & same;
+        const int kept0 = r != 0xffffffffu ? kept[r] : 0;
+        __syncwarp();                                  // every lane has read its entry and its request's cursor
+        if (keep && WRT_IN_BOUNDS((unsigned)off + kept0 + __popc(kmask & lt_mask), lb.pool_cap))
+            lb.pool[off + kept0 + __popc(kmask & lt_mask)] = prim;
+        if (r != 0xffffffffu && (same & lt_mask) == 0u) kept[r] = kept0 + __popc(kmask);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                      SoftListBuffers lb) {
     __shared__ float s_py[4][32][WRT_PYRAMID_FLOATS + 1];
@@ -822,60 +887,13 @@ __global__ void __launch_bounds__(128) k_soft_filter(const __grid_constant__ Dev
                 }
             }
         }
-        const int cnt = ok ? ref.y : 0;
-        int incl = cnt;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= (unsigned)off) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        s_start[warp][lane] = incl - cnt;
-        if (lane == 31) s_start[warp][32] = total;
         s_off[warp][lane] = ref.x;
-        s_kept[warp][lane] = 0;
+        s_kept[warp][lane] = ok ? ref.y : 0;
         __syncwarp();
-        // ---- B ----
-        for (int g0 = 0; g0 < total; g0 += 32) {
-            const int g = g0 + (int)lane;
-            unsigned r = 0xffffffffu;
-            int prim = -1, off = 0;
-            bool keep = false;
-            if (g < total) {
-                int lo = 0, hi = 31;                       // last request whose start offset is <= g (empty lists share a start)
-#pragma unroll
-                for (int it = 0; it < 5; it++) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_start[warp][mid] <= g) lo = mid; else hi = mid - 1;
-                }
-                r = (unsigned)lo;
-                off = s_off[warp][lo];
-                prim = lb.pool[off + (g - s_start[warp][lo])];
-                WrtShaftPyramid py;
-                const float* d = s_py[warp][lo];
-                py.o[0] = d[0]; py.o[1] = d[1]; py.o[2] = d[2];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    py.D[j][0] = d[3 + 3 * j]; py.D[j][1] = d[4 + 3 * j]; py.D[j][2] = d[5 + 3 * j];
-                    py.Dlen[j] = d[15 + j];
-                    py.N[j][0] = d[19 + 3 * j]; py.N[j][1] = d[20 + 3 * j]; py.N[j][2] = d[21 + 3 * j];
-                }
-                py.ok = 1;
-                const float4* gm = s.geom + 3 * (size_t)prim;
-                const float4 A = ldg4(gm), B = ldg4(gm + 1), C = ldg4(gm + 2), X = ldg4(s.tri_aux + prim);
-                const float v0[3] = {A.x, A.y, A.z}, E1[3] = {B.x, B.y, B.z}, E2[3] = {C.x, C.y, C.z};
-                const float aux[4] = {X.x, X.y, X.z, X.w};
-                keep = wrt_pyramid_triangle_may_block(&py, v0, E1, E2, aux);
-            }
-            const unsigned same = __match_any_sync(0xffffffffu, r);            // lanes working on the same request
-            const unsigned kmask = __ballot_sync(0xffffffffu, keep) & same;
-            const int kept0 = r != 0xffffffffu ? s_kept[warp][r] : 0;
-            __syncwarp();                                  // every lane has read its entry and its request's cursor
-            if (keep && WRT_IN_BOUNDS((unsigned)off + kept0 + __popc(kmask & lt_mask), lb.pool_cap))
-                lb.pool[off + kept0 + __popc(kmask & lt_mask)] = prim;
-            if (r != 0xffffffffu && (same & lt_mask) == 0u) s_kept[warp][r] = kept0 + __popc(kmask);
-            __syncwarp();
-        }
+        // ---- B: first stage (side planes, own plane) on every list; second stage (edge planes) on the short survivor
+        // lists only — those of fully lit requests, which it empties ----
+        filter_pass<0>(s, lb, s_py[warp], s_start[warp], s_off[warp], s_kept[warp], lane, ok);
+        filter_pass<1>(s, lb, s_py[warp], s_start[warp], s_off[warp], s_kept[warp], lane, ok && s_kept[warp][lane] <= WRT_FILTER_EDGE_MAX);
         int final_cnt = ref.y;                             // 0: empty already; < 0: ray by ray; else a list this kernel left alone
         if (ok) {
             final_cnt = s_kept[warp][lane];

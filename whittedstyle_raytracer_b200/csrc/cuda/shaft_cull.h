@@ -356,12 +356,28 @@ WRT_SHAFT_HD bool wrt_pyramid_triangle_may_block(const WrtShaftPyramid* p, const
         }
         if (same) return false;
     }
-    /* edge planes: the plane through o and a triangle edge (a, b), oriented towards the third vertex c.  Seen from o, the
-     * triangle and the light are two convex polygons on the sphere of directions; they are disjoint iff an edge of one of
-     * them separates them — the four side planes above, or one of these three.  With unit normal n and all four corner
-     * directions at least (m + 1e-4) * Dmax outside it, every sample direction d has n.d < -(m + 1e-4); the only part of the
-     * slack-widened triangle outside the plane lies within `slack` of the edge's line, i.e. at least h - slack from o
-     * (h = distance from o to that line), where the ray is already (h - slack) * m = slack outside. */
+    return true;
+}
+
+/* Second stage, for the candidates the first stage kept: false = provably blocks no sample ray.
+ * edge planes: the plane through o and a triangle edge (a, b), oriented towards the third vertex c.  Seen from o, the
+ * triangle and the light are two convex polygons on the sphere of directions; they are disjoint iff an edge of one of
+ * them separates them — the four side planes of the first stage, or one of these three.  With unit normal n and all four
+ * corner directions at least (m + 1e-4) * Dmax outside it, every sample direction d has n.d < -(m + 1e-4); the only part of
+ * the slack-widened triangle outside the plane lies within `slack` of the edge's line, i.e. at least h - slack from o
+ * (h = distance from o to that line), where the ray is already (h - slack) * m = slack outside.
+ * (Costs about as much as the first stage: k_soft_filter runs it on short survivor lists only — the fully lit requests,
+ * which it empties; a long list belongs to a request in shadow or penumbra and cannot become empty.) */
+WRT_SHAFT_HD bool wrt_pyramid_triangle_may_block_edges(const WrtShaftPyramid* p, const float v0[3], const float E1[3], const float E2[3],
+                                                       const float aux[4]) {
+    const float esz = aux[3];
+    if (!p->ok || !(esz >= 0.f)) return true;
+    float w[3][3];
+    for (int k = 0; k < 3; k++) {
+        w[0][k] = v0[k] - p->o[k];
+        w[1][k] = (v0[k] + E1[k]) - p->o[k];
+        w[2][k] = (v0[k] + E2[k]) - p->o[k];
+    }
     {
         const float slack = 2e-5f * esz + 1e-5f;
         const float dmax = fmaxf(fmaxf(p->Dlen[0], p->Dlen[1]), fmaxf(p->Dlen[2], p->Dlen[3]));

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../include/wrt_host.h"
@@ -58,6 +59,12 @@ int main(int argc, char** argv) {
     static_assert(sizeof(WrtNode) == 2 * sizeof(float4), "record = two float4");
     memcpy(onodes.data(), oct.data(), oct.size() * sizeof(WrtNode));
     const int np = S->n_prims, nn = (int)fb.nodes.size();
+    // the 4-wide view of every octant copy, built by the product's own routine (wide_bvh.h, what k_wide4_copies runs)
+    std::vector<float4> wnodes((size_t)WRT_WIDE_FLOAT4_PER_RECORD * 8 * (size_t)nn);
+    for (int oct = 0; oct < 8; oct++)
+        for (int c = 2; c + 1 < nn; c += 2)
+            wrt_wide4_node(onodes.data() + 2 * (size_t)oct * nn, c, oct, wnodes.data() + WRT_WIDE_FLOAT4_PER_RECORD * ((size_t)oct * nn + c));
+    long long wide_mismatch = 0;
     std::vector<float> box(6 * (size_t)np);
     float smin[3] = {INFINITY, INFINITY, INFINITY}, smax[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = 0; i < S->n_nodes; i++) {
@@ -119,6 +126,17 @@ int main(int argc, char** argv) {
             int stack[64], list[64];
             const int cnt = wrt_shaft_candidates(onodes.data(), nn, &sh, stack, 1, 64, list, 64);
             if (cnt < 0) list_overflow++; else { lists++; list_items += cnt; if (is_empty != (cnt == 0)) violations++; }
+            {   // the wide walks must reach exactly the same leaves (their order may differ)
+                if (wrt_shaft_is_empty4(onodes.data(), wnodes.data(), nn, o, L.tri) != is_empty) wide_mismatch++;
+                int stack4[96], list4[64];
+                const int cnt4 = wrt_shaft_candidates4(onodes.data(), wnodes.data(), nn, &sh, stack4, 1, 96, list4, 64);
+                if (cnt4 != cnt) wide_mismatch++;
+                else for (int a = 0; a < cnt; a++) {
+                    bool found = false;
+                    for (int b = 0; b < cnt4; b++) found = found || list4[b] == list[a];
+                    if (!found) wide_mismatch++;
+                }
+            }
             // triangle-level pruning of the list (k_soft_filter): the removed candidates must block no sample ray
             std::vector<int> removed;
             if (cnt > 0) {
@@ -192,9 +210,9 @@ int main(int argc, char** argv) {
     printf("{\"prims\": %d, \"empty\": %lld, \"nonempty\": %lld, \"gave_up\": %lld, \"rays_checked\": %lld, "
            "\"degenerate_rays\": %lld, \"violations\": %lld, \"bound_violations\": %lld, \"lists\": %lld, \"list_items\": %lld, "
            "\"list_overflow\": %lld, \"list_rays\": %lld, \"list_violations\": %lld, \"filter_removed\": %lld, \"filter_kept\": %lld, "
-           "\"filter_pairs\": %lld, \"filter_violations\": %lld}\n", np, empty, nonempty, gave_up, rays_checked,
+           "\"filter_pairs\": %lld, \"filter_violations\": %lld, \"wide_mismatch\": %lld}\n", np, empty, nonempty, gave_up, rays_checked,
            degenerate_rays, violations, bound_violations, lists, list_items, list_overflow, list_rays, list_violations, filter_removed,
-           filter_kept, filter_pairs, filter_violations);
+           filter_kept, filter_pairs, filter_violations, wide_mismatch);
     wrt_scene_free(sc);
-    return (violations || bound_violations || list_violations || filter_violations) ? 1 : 0;
+    return (violations || bound_violations || list_violations || filter_violations || wide_mismatch) ? 1 : 0;
 }

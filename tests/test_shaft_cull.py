@@ -63,6 +63,7 @@ def test_empty_shaft_verdicts_hold_by_brute_force(name, checker, workdir):
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["violations"] == 0 and r["bound_violations"] == 0 and r["list_violations"] == 0
     assert r["filter_violations"] == 0                       # no pruned candidate is ever hit by a sample ray
+    assert r["wide_mismatch"] == 0                           # the 4-wide walks (wide_bvh.h) reach exactly the same leaves
     if name in ("water_bunny_tex", "bunny_shadow"):
         assert r["filter_removed"] > 0.2 * (r["filter_removed"] + r["filter_kept"]) and r["filter_pairs"] > 100000
     assert r["list_rays"] > 0

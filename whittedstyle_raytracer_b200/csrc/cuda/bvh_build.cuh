@@ -18,6 +18,7 @@
 
 #include "ploc_bvh.h"
 #include "shaft_cull.h"
+#include "wide_bvh.h"
 #include "../../../include/wrt_scene.h"
 
 namespace wrt {
@@ -232,6 +233,23 @@ __global__ void __launch_bounds__(256) k_octant_copies(const float4* __restrict_
         if (oct & 4) { t = lo.z; lo.z = hi.z; hi.z = t; }
         dst[2 * ((size_t)oct * n_nodes + i)] = lo;
         dst[2 * ((size_t)oct * n_nodes + i) + 1] = hi;
+    }
+}
+
+// dst[oct]: the 4-wide view (wide_bvh.h) of octant copy oct of a tree: one 128-byte node per sibling pair, holding the
+// pair's four grandchild records.  One thread per (octant, pair).
+__global__ void __launch_bounds__(256) k_wide4_copies(const float4* __restrict__ onodes, int n_nodes, float4* dst) {
+    const int pairs = n_nodes / 2;
+    const long long total = 8ll * pairs;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int oct = (int)(g / pairs);
+        const int c = 2 * (int)(g - (long long)oct * pairs);
+        if (c == 0) continue;                               // records 0, 1: the root box and its padding, not a sibling pair
+        float4 out[8];
+        wrt_wide4_node(onodes + 2 * (size_t)oct * n_nodes, c, oct, out);
+        float4* d = dst + WRT_WIDE_FLOAT4_PER_RECORD * ((size_t)oct * n_nodes + c);
+#pragma unroll
+        for (int i = 0; i < 8; i++) d[i] = out[i];
     }
 }
 

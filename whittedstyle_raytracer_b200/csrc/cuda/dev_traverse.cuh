@@ -12,6 +12,7 @@
 #pragma once
 #include "dev_math.cuh"
 #include "prune_rule.h"
+#include "wide_bvh.h"
 #include "../../../include/wrt_scene.h"
 
 namespace wrt {
@@ -25,6 +26,7 @@ struct DevScene {
                               // {near planes, link}{far planes, pad}: the reference's swap-on-negative-direction
                               // (BoundBox.hpp:68-70) is done once at upload instead of at every box
     const float4* ronodes;    // the same 8 octant copies of the reference-topology tree (axis-degenerate rays)
+    const float4* wnodes;     // 4-wide view of each octant copy of the SAH tree (wide_bvh.h): node of pair c at float4 4*c
     const float4* dnodes;     // the SAH tree with every box dilated: conservative culling for the box-free
                               // directional-shadow loop (Renderer.hpp:381-400)
     const float4* geom;
@@ -218,6 +220,63 @@ __device__ __forceinline__ bool traverse_step(const float4* __restrict__ nodes, 
     }
     if (hl) { cur = linkL; return true; }
     if (hr) { cur = linkR; return true; }
+    if (st.empty()) return false;
+    cur = st.pop();
+    return true;
+}
+
+// One step over a 4-wide node (wide_bvh.h): the four grandchild records of pair `cur` in one 128-byte block.  Same
+// contract as traverse_step on a presorted octant copy; hit leaves are handled in ONE loop (one copy of the intersection
+// code, entered by every lane of the warp that has a leaf to test), inner hits are visited nearest first (NEAR_FIRST)
+// or in slot order.
+#ifndef WRT_WIDE4
+#define WRT_WIDE4 1
+#endif
+template <bool NEAR_FIRST, class LeafFn>
+__device__ __forceinline__ bool traverse_step4(const float4* __restrict__ wnodes, const Ray& r, Stack& st, int& cur,
+                                               const float& limit, LeafFn&& leaf) {
+    const float4* n = wnodes + WRT_WIDE_FLOAT4_PER_RECORD * (size_t)cur;
+    float4 a0, a1, b0, b1, c0, c1, d0, d1;
+    ldg8(n, a0, a1);
+    ldg8(n + 2, b0, b1);
+    ldg8(n + 4, c0, c1);
+    ldg8(n + 6, d0, d1);
+    float t0, t1, t2, t3;
+    bool h0 = slab_presorted(a0, a1, r, t0), h1 = slab_presorted(b0, b1, r, t1);
+    bool h2 = slab_presorted(c0, c1, r, t2), h3 = slab_presorted(d0, d1, r, t3);
+    int l0 = __float_as_int(a0.w), l1 = __float_as_int(b0.w), l2 = __float_as_int(c0.w), l3 = __float_as_int(d0.w);
+    h0 = h0 && !(t0 > limit); h1 = h1 && !(t1 > limit); h2 = h2 && !(t2 > limit); h3 = h3 && !(t3 > limit);
+    unsigned leaves = (h0 && l0 < 0 ? 1u : 0u) | (h1 && l1 < 0 ? 2u : 0u) | (h2 && l2 < 0 ? 4u : 0u) | (h3 && l3 < 0 ? 8u : 0u);
+    while (leaves) {
+        const unsigned j = __ffs(leaves) - 1;
+        leaves &= leaves - 1;
+        const int lk = j == 0 ? l0 : (j == 1 ? l1 : (j == 2 ? l2 : l3));
+        const float tj = j == 0 ? t0 : (j == 1 ? t1 : (j == 2 ? t2 : t3));
+        if (!(tj > limit)) leaf(~lk);                      // `limit` may have tightened in an earlier leaf()
+    }
+    const float inf = INFINITY;
+    // inner hits: key = entry distance, +inf = not to be visited
+    float k0 = (h0 && l0 >= 0 && !(t0 > limit)) ? t0 : inf, k1 = (h1 && l1 >= 0 && !(t1 > limit)) ? t1 : inf;
+    float k2 = (h2 && l2 >= 0 && !(t2 > limit)) ? t2 : inf, k3 = (h3 && l3 >= 0 && !(t3 > limit)) ? t3 : inf;
+    if (NEAR_FIRST) {
+#define WRT_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const float kt = sw ? ka : kb; ka = sw ? kb : ka; kb = kt; const int lt = sw ? la : lb; la = sw ? lb : la; lb = lt; }
+        WRT_CSWAP(k0, l0, k1, l1) WRT_CSWAP(k2, l2, k3, l3) WRT_CSWAP(k0, l0, k2, l2) WRT_CSWAP(k1, l1, k3, l3) WRT_CSWAP(k1, l1, k2, l2)
+#undef WRT_CSWAP
+        if (k0 < inf) {                                    // ascending: (k0,l0) nearest
+            if (k3 < inf) st.push(l3);
+            if (k2 < inf) st.push(l2);
+            if (k1 < inf) st.push(l1);
+            cur = l0;
+            return true;
+        }
+    } else {
+        int nxt = -1;
+        if (k0 < inf) nxt = l0;
+        if (k1 < inf) { if (nxt >= 0) st.push(nxt); nxt = l1; }
+        if (k2 < inf) { if (nxt >= 0) st.push(nxt); nxt = l2; }
+        if (k3 < inf) { if (nxt >= 0) st.push(nxt); nxt = l3; }
+        if (nxt >= 0) { cur = nxt; return true; }
+    }
     if (st.empty()) return false;
     cur = st.pop();
     return true;

@@ -285,6 +285,7 @@ __device__ __forceinline__ void surface_warp(const DevScene& s, const FrameBuffe
             } else if ((cull & WRT_CULL_SHAFT) && point) {
                 float tri[9];
                 for (int k = 0; k < 9; k++) tri[k] = L->tri[k];
+                // (binary walk: most level-0 shafts miss the bunny's subtree after 2-3 nodes; the 4-wide walk measured 832 vs 768 us)
                 if (wrt_shaft_is_empty(s.onodes, s.n_nodes, so, tri)) { lit_mask |= 1u << li; --n_preq; }
             }
         }
@@ -342,6 +343,7 @@ struct ClosestQuery {
     Ray r;
     ClosestState cs;
     const float4* nodes;
+    bool wide;                 // this lane walks the 4-wide view of its octant copy (wide_bvh.h)
     unsigned idx;
     LevelSpan span;
     __device__ __forceinline__ ClosestQuery(const DevScene& s_, const FrameBuffers& fb_, const PrimaryGen& pg_, int level,
@@ -363,16 +365,22 @@ struct ClosestQuery {
         float prune = prune_cfg;
         const bool ref_tree = prune < 0.f || degenerate_dir(r.d);       // literal walk / axis-degenerate ray
         if (ref_tree) prune = -1.f;
-        nodes = (ref_tree ? s.ronodes : s.onodes) + (size_t)ray_octant(r.d) * 2 * (size_t)s.n_nodes;
+        const size_t oct_off = (size_t)ray_octant(r.d) * 2 * (size_t)s.n_nodes;
+        nodes = (ref_tree ? s.ronodes : s.onodes) + oct_off;
         cs.set_ray(s, r, prune);
         float te;
         float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
         if (!slab_presorted(lo, hi, r, te)) return false;
         cur = __float_as_int(lo.w);
         if (cur < 0) { cs.leaf(s, r, ~cur); return false; }
+        // (level 0: coherent primary rays, two thirds of them end on a wall after a few steps — the 4-wide node costs
+        // registers there and buys nothing: 378 vs 338 us)
+        wide = WRT_WIDE4 && !LEVEL0 && !ref_tree;
+        if (wide) nodes = s.wnodes + (WRT_WIDE_FLOAT4_PER_RECORD / 2) * oct_off;
         return true;
     }
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
+        if (WRT_WIDE4 && !LEVEL0 && wide) return traverse_step4<true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
         return traverse_step<true, true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
@@ -439,6 +447,7 @@ struct HardShadowQuery {
     float dis, res;
     size_t out;
     int q;
+    bool wide;
     bool literal;              // WRT_TRAVERSAL_EXHAUSTIVE: walk the reference-topology tree (its left-to-right product order)
     __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int q_, bool literal_)
         : s(s_), fb(fb_), q(q_), literal(literal_) {}
@@ -454,17 +463,23 @@ struct HardShadowQuery {
         out = (size_t)__float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
         res = 1.f;
         if (s.n_nodes == 0) return false;
-        nodes = ((literal || degenerate_dir(raydir)) ? s.ronodes : s.onodes) + (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
+        const bool ref_tree = literal || degenerate_dir(raydir);
+        const size_t oct_off = (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
+        nodes = (ref_tree ? s.ronodes : s.onodes) + oct_off;
         float te;
         float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
         if (!slab_presorted(lo, hi, r, te)) return false;
         cur = __float_as_int(lo.w);
         if (cur < 0) { shadow_leaf(s, r, dis, ~cur, res); return false; }
+        wide = WRT_WIDE4 && !ref_tree;
+        if (wide) nodes = s.wnodes + (WRT_WIDE_FLOAT4_PER_RECORD / 2) * oct_off;
         return true;
     }
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
         const float never = INFINITY;
-        bool more = traverse_step<false, true>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
+        bool more;
+        if (WRT_WIDE4 && wide) more = traverse_step4<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
+        else more = traverse_step<false, true>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
         return more && res != 0.f;
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
@@ -585,7 +600,7 @@ __global__ void WRT_TRACE_BOUNDS k_shadow_soft(const __grid_constant__ DevScene 
 #endif
 struct SoftListBuffers {
     int*  scratch;        // WRT_LIST_CAP ints per thread of the grid: a walk writes here, then copies into the pool
-    float* shafts;        // WRT_LISTS_CHUNK x 10 floats per warp of the grid: the shafts of the warp's current chunk
+    float* shafts;        // WRT_LISTS_CHUNK x WRT_SHAFT_SLOT floats per warp of the grid: the shafts of the warp's current chunk
     int*  pool;           // the lists
     int2* ref;            // per request: {pool offset, count}
     unsigned* work;       // k_soft_filter: the requests that need rays (non-empty list, or count < 0), compacted
@@ -601,6 +616,7 @@ struct SoftListBuffers {
 #ifndef WRT_LISTS_REFILL
 #define WRT_LISTS_REFILL 8
 #endif
+#define WRT_SHAFT_SLOT 10         // floats a staged shaft occupies: o, ilo, ihi, octant | use
 
 // One lane walks one request's shaft, but walk lengths differ a lot (3 ... 400 node pairs; ncu: 8.6 of 32 lanes
 // active when every lane takes one request and the warp waits for the longest).  So a warp owns a chunk of
@@ -615,9 +631,16 @@ struct SoftListBuffers {
 // allocates from the region through a warp-uniform cursor; when the region is used up it takes what the flush needs
 // with another atomic; an exhausted pool means count = -1 (per-ray walk).  Lists of a chunk stay close together.
 // (An earlier refill attempt through run_queue — set-up code on the refilled lanes only — was slower than no refill.)
-// (launch bound: 48 registers = 10 CTAs per SM; unbounded the kernel takes 70 and the walks — dependent loads, little
-// else — lose a third of the warps that hide their latency.  What spills is flush-side state.)
-__global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
+// (launch bound, with the 4-wide walk: 8 CTAs per SM = 63 registers, no spills: 2.86 ms per 4K frame; 10 CTAs = 48 registers,
+// 24 bytes of spills: 3.13 ms; unbounded 80 registers: 5 CTAs.)
+// (A per-leaf "own plane" test inside the walk — three quarters of the leaves a fully lit request finds are its own
+// neighbours, which k_soft_filter then removes — was built and measured: the walk runs one lane per request, the test
+// costs two dependent loads and ~40 instructions at that width: 6.3 ms against 3.1.  The filter kernel, which spreads
+// candidates over lanes, is the right place.)
+#ifndef WRT_LISTS_MIN_BLOCKS
+#define WRT_LISTS_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, WRT_LISTS_MIN_BLOCKS) k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                         int work_slot, int stack_rows, SoftListBuffers lb) {
     extern __shared__ int smem[];
     Stack st;
@@ -628,7 +651,7 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
     const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
     int* warp_scratch = lb.scratch + gwarp * 32 * WRT_LIST_CAP;
     int* mine = warp_scratch + (size_t)lane * WRT_LIST_CAP;
-    float* slots = lb.shafts + gwarp * (size_t)WRT_LISTS_CHUNK * 10;
+    float* slots = lb.shafts + gwarp * (size_t)WRT_LISTS_CHUNK * WRT_SHAFT_SLOT;
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
     unsigned* pool_head = fb.counters + C_POOL + q;
     // chunk size: ~4 chunks per warp on short queues (the launch ends with its slowest chunk), WRT_LISTS_CHUNK on long ones
@@ -657,7 +680,7 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
             const float o[3] = {o4.x, o4.y, o4.z};
             WrtShaft sh;
             const bool ok = wrt_shaft_make(o, tri, &sh);
-            float* d = slots + (size_t)r * 10;
+            float* d = slots + (size_t)r * WRT_SHAFT_SLOT;
             d[0] = sh.o[0]; d[1] = sh.o[1]; d[2] = sh.o[2];
             d[3] = sh.ilo[0]; d[4] = sh.ilo[1]; d[5] = sh.ilo[2];
             d[6] = sh.ihi[0]; d[7] = sh.ihi[1]; d[8] = sh.ihi[2];
@@ -731,7 +754,7 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
                     next += __popc(idle);
                     if (!active && cand < chunk) {
                         my = cand;
-                        const float* d = slots + (size_t)my * 10;
+                        const float* d = slots + (size_t)my * WRT_SHAFT_SLOT;
                         const int ou = __float_as_int(d[9]);
                         int rc = -1;
                         if (ou >= 0) {
@@ -739,7 +762,11 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
                             sh.ilo[0] = d[3]; sh.ilo[1] = d[4]; sh.ilo[2] = d[5];
                             sh.ihi[0] = d[6]; sh.ihi[1] = d[7]; sh.ihi[2] = d[8];
                             sh.octant = ou & 7; sh.use = ou >> 3;
+#if WRT_WIDE4
+                            rc = wrt_shaft_walk_begin4(s.onodes, s.wnodes, s.n_nodes, &sh, &w);
+#else
                             rc = wrt_shaft_walk_begin(s.onodes, s.n_nodes, &sh, &w);
+#endif
                         }
                         if (rc == 1) active = true;
                         else pend = rc;                      // answered without a walk; recorded by the next flush
@@ -753,7 +780,11 @@ __global__ void __launch_bounds__(128, 10) k_soft_lists(const __grid_constant__ 
 #pragma unroll 1
             for (int it = 0; it < 4; it++) {
                 if (active) {
+#if WRT_WIDE4
+                    const int rc = wrt_shaft_walk_step4(&sh, &w, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+#else
                     const int rc = wrt_shaft_walk_step(&sh, &w, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+#endif
                     if (rc != 1) { active = false; pend = rc < 0 ? -1 : w.n; }
                 }
             }

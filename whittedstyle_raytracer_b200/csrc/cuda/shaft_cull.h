@@ -42,6 +42,8 @@
 
 #include <math.h>
 
+#include "wide_bvh.h"
+
 #ifdef __CUDACC__
 #define WRT_SHAFT_HD __host__ __device__ __forceinline__
 #else
@@ -251,6 +253,111 @@ WRT_SHAFT_HD bool wrt_shaft_is_empty(const float4* onodes, int n_nodes, const fl
             if (sp == 0) return true;
             cur = stack[--sp];
         }
+    }
+}
+
+// ---- the same walks over the 4-wide view of the tree (wide_bvh.h): half the dependent node fetches ----
+// wnodes: the 8 wide copies (WRT_WIDE_FLOAT4_PER_RECORD float4 per binary record); onodes: the binary octant copies
+// (record 0 holds the root's link).  A wide node's slots are records of the octant copy, so the interval test is
+// wrt_shaft_may_hit(_lb) unchanged; an empty slot fails it on every used axis.
+WRT_SHAFT_HD int wrt_shaft_walk_begin4(const float4* onodes, const float4* wnodes, int n_nodes, const WrtShaft* sh, WrtShaftWalk* w) {
+    w->sp = 0; w->n = 0; w->cur = 0; w->nodes = wnodes;
+    if (n_nodes <= 0) return 0;
+    union { float f; int i; } u;
+    u.f = WRT_SHAFT_LD4(onodes + (size_t)sh->octant * 2 * (size_t)n_nodes).w;
+    w->cur = u.i;
+    w->nodes = wnodes + WRT_WIDE_FLOAT4_PER_RECORD * (size_t)sh->octant * (size_t)n_nodes;
+    return w->cur < 0 ? -1 : 1;                                           // lone primitive: tested without its box
+}
+
+#define WRT_SHAFT_CSWAP(ka, la, kb, lb) { const bool sw_ = (kb) < (ka); const float kt_ = sw_ ? (ka) : (kb); (ka) = sw_ ? (kb) : (ka); (kb) = kt_; \
+                                          const int lt_ = sw_ ? (la) : (lb); (la) = sw_ ? (lb) : (la); (lb) = lt_; }
+
+// One wide node: up to four leaves into the list (nearest first), up to three inner children pushed (farthest first).
+WRT_SHAFT_HD int wrt_shaft_walk_step4(const WrtShaft* sh, WrtShaftWalk* w, int* stack, int stack_stride, int stack_cap,
+                                      int* out, int out_cap) {
+    const float4* nd = w->nodes + WRT_WIDE_FLOAT4_PER_RECORD * (size_t)w->cur;
+    float4 a0, a1, b0, b1, c0, c1, d0, d1;
+    WRT_SHAFT_LD8(nd, a0, a1);
+    WRT_SHAFT_LD8(nd + 2, b0, b1);
+    WRT_SHAFT_LD8(nd + 4, c0, c1);
+    WRT_SHAFT_LD8(nd + 6, d0, d1);
+    float k0, k1, k2, k3;
+    const bool h0 = wrt_shaft_may_hit_lb(sh, a0, a1, &k0), h1 = wrt_shaft_may_hit_lb(sh, b0, b1, &k1);
+    const bool h2 = wrt_shaft_may_hit_lb(sh, c0, c1, &k2), h3 = wrt_shaft_may_hit_lb(sh, d0, d1, &k3);
+    const float inf = INFINITY;
+    if (!h0) k0 = inf;
+    if (!h1) k1 = inf;
+    if (!h2) k2 = inf;
+    if (!h3) k3 = inf;
+    union { float f; int i; } u;
+    u.f = a0.w; int l0 = u.i;
+    u.f = b0.w; int l1 = u.i;
+    u.f = c0.w; int l2 = u.i;
+    u.f = d0.w; int l3 = u.i;
+    WRT_SHAFT_CSWAP(k0, l0, k1, l1) WRT_SHAFT_CSWAP(k2, l2, k3, l3) WRT_SHAFT_CSWAP(k0, l0, k2, l2)
+    WRT_SHAFT_CSWAP(k1, l1, k3, l3) WRT_SHAFT_CSWAP(k1, l1, k2, l2)
+    int n = w->n;
+    if (k0 < inf && l0 < 0) { if (n == out_cap) return -1; out[n++] = ~l0; }
+    if (k1 < inf && l1 < 0) { if (n == out_cap) return -1; out[n++] = ~l1; }
+    if (k2 < inf && l2 < 0) { if (n == out_cap) return -1; out[n++] = ~l2; }
+    if (k3 < inf && l3 < 0) { if (n == out_cap) return -1; out[n++] = ~l3; }
+    w->n = n;
+    int next = -1;                                                        // nearest inner child so far (going far -> near)
+    if (k3 < inf && l3 >= 0) next = l3;
+    if (k2 < inf && l2 >= 0) { if (next >= 0) { if (w->sp == stack_cap) return -1; stack[w->sp * stack_stride] = next; ++w->sp; } next = l2; }
+    if (k1 < inf && l1 >= 0) { if (next >= 0) { if (w->sp == stack_cap) return -1; stack[w->sp * stack_stride] = next; ++w->sp; } next = l1; }
+    if (k0 < inf && l0 >= 0) { if (next >= 0) { if (w->sp == stack_cap) return -1; stack[w->sp * stack_stride] = next; ++w->sp; } next = l0; }
+    if (next >= 0) { w->cur = next; return 1; }
+    if (w->sp == 0) return 0;
+    --w->sp;
+    w->cur = stack[w->sp * stack_stride];
+    return 1;
+}
+
+WRT_SHAFT_HD int wrt_shaft_candidates4(const float4* onodes, const float4* wnodes, int n_nodes, const WrtShaft* sh, int* stack,
+                                       int stack_stride, int stack_cap, int* out, int out_cap) {
+    WrtShaftWalk w;
+    int rc = wrt_shaft_walk_begin4(onodes, wnodes, n_nodes, sh, &w);
+    if (rc <= 0) return rc;
+    while ((rc = wrt_shaft_walk_step4(sh, &w, stack, stack_stride, stack_cap, out, out_cap)) == 1) {}
+    return rc < 0 ? -1 : w.n;
+}
+
+// wrt_shaft_is_empty over the wide copies
+WRT_SHAFT_HD bool wrt_shaft_is_empty4(const float4* onodes, const float4* wnodes, int n_nodes, const float o[3], const float tri[9]) {
+    if (n_nodes <= 0) return true;
+    WrtShaft sh;
+    if (!wrt_shaft_make(o, tri, &sh)) return false;
+    union { float f; int i; } u;
+    u.f = WRT_SHAFT_LD4(onodes + (size_t)sh.octant * 2 * (size_t)n_nodes).w;
+    int cur = u.i;
+    if (cur < 0) return false;                                            // lone primitive: tested without its box
+    const float4* nodes = wnodes + WRT_WIDE_FLOAT4_PER_RECORD * (size_t)sh.octant * (size_t)n_nodes;
+    int stack[WRT_SHAFT_STACK];
+    int sp = 0;
+    while (true) {
+        const float4* nd = nodes + WRT_WIDE_FLOAT4_PER_RECORD * (size_t)cur;
+        float4 a0, a1, b0, b1, c0, c1, d0, d1;
+        WRT_SHAFT_LD8(nd, a0, a1);
+        WRT_SHAFT_LD8(nd + 2, b0, b1);
+        WRT_SHAFT_LD8(nd + 4, c0, c1);
+        WRT_SHAFT_LD8(nd + 6, d0, d1);
+        const bool h0 = wrt_shaft_may_hit(&sh, a0, a1), h1 = wrt_shaft_may_hit(&sh, b0, b1);
+        const bool h2 = wrt_shaft_may_hit(&sh, c0, c1), h3 = wrt_shaft_may_hit(&sh, d0, d1);
+        u.f = a0.w; const int l0 = u.i;
+        u.f = b0.w; const int l1 = u.i;
+        u.f = c0.w; const int l2 = u.i;
+        u.f = d0.w; const int l3 = u.i;
+        if ((h0 && l0 < 0) || (h1 && l1 < 0) || (h2 && l2 < 0) || (h3 && l3 < 0)) return false;   // a leaf box is inside the shaft
+        int next = -1;
+        if (h3) next = l3;
+        if (h2) { if (next >= 0) { if (sp == WRT_SHAFT_STACK) return false; stack[sp++] = next; } next = l2; }
+        if (h1) { if (next >= 0) { if (sp == WRT_SHAFT_STACK) return false; stack[sp++] = next; } next = l1; }
+        if (h0) { if (next >= 0) { if (sp == WRT_SHAFT_STACK) return false; stack[sp++] = next; } next = l0; }
+        if (next >= 0) { cur = next; continue; }
+        if (sp == 0) return true;
+        cur = stack[--sp];
     }
 }
 

@@ -284,7 +284,7 @@ int ensure_frame_buffers(WrtContext* c, unsigned slots) {
         if (c->list_pool_cap_override > 0) lb.pool_cap = (unsigned)c->list_pool_cap_override;     // tests: force the pool-full path
         const bool lists_possible = ds.n_point_lights && ds.shadow_type != 0;
         if (frame_alloc(c, &lb.scratch, lists_possible ? (size_t)c->num_sms * c->trace_blocks_per_sm * 128 * WRT_LIST_CAP : 1)) return 1;
-        if (frame_alloc(c, &lb.shafts, lists_possible ? (size_t)c->num_sms * c->trace_blocks_per_sm * 4 * WRT_LISTS_CHUNK * 10 : 1)) return 1;
+        if (frame_alloc(c, &lb.shafts, lists_possible ? (size_t)c->num_sms * c->trace_blocks_per_sm * 4 * WRT_LISTS_CHUNK * WRT_SHAFT_SLOT : 1)) return 1;
         if (frame_alloc(c, &lb.pool, lb.pool_cap)) return 1;
         if (frame_alloc(c, &lb.ref, lists_possible ? fb.preq_cap[q] : 1)) return 1;
         if (frame_alloc(c, &lb.work, lists_possible ? fb.preq_cap[q] : 1)) return 1;
@@ -631,9 +631,11 @@ int finish_frame(WrtContext* c) {
     if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) c->stats.gpu_ms = ms;
     for (float& f : c->family_ms) f = 0.f;
     for (int& n : c->family_launches) n = 0;
+    const bool dump = getenv("WRT_TIMING_DUMP") != nullptr;      // development: every timed launch, in enqueue order
     for (const TimedLaunch& tl : c->timed) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, tl.e0, tl.e1) == cudaSuccess) { c->family_ms[tl.family] += t; ++c->family_launches[tl.family]; }
+        if (dump) fprintf(stderr, "[wrt] launch family %d: %.1f us\n", tl.family, t * 1e3f);
     }
     return 0;
 }
@@ -811,7 +813,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     ds.texels = (const float*)dptr(14);
 
     // ---- 2. device-side layouts ----
-    float4 *geom = nullptr, *attr = nullptr, *mats = nullptr, *pbox = nullptr, *taux = nullptr, *fnodes = nullptr, *dnodes = nullptr, *onodes = nullptr, *ronodes = nullptr;
+    float4 *geom = nullptr, *attr = nullptr, *mats = nullptr, *pbox = nullptr, *taux = nullptr, *fnodes = nullptr, *dnodes = nullptr, *onodes = nullptr, *ronodes = nullptr, *wnodes = nullptr;
     int4* ids = nullptr;
     int* d_flags = nullptr;
     if (dev_alloc(c, (size_t)np * 48, (void**)&geom) || dev_alloc(c, (size_t)np * 64, (void**)&attr) || dev_alloc(c, (size_t)np * 16, (void**)&ids) ||
@@ -819,6 +821,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         dev_alloc(c, (size_t)np * 16, (void**)&taux) ||
         dev_alloc(c, (size_t)nn * 32, (void**)&fnodes) || dev_alloc(c, (size_t)nn * 32, (void**)&dnodes) ||
         dev_alloc(c, (size_t)nn * 32 * 8, (void**)&onodes) || dev_alloc(c, (size_t)nn * 32 * 8, (void**)&ronodes) ||
+        dev_alloc(c, (size_t)nn * 64 * 8, (void**)&wnodes) ||
         dev_alloc(c, (wrt::BS_TOTAL + 16) * sizeof(int), (void**)&d_flags))
         return 1;
     int* d_state = d_flags + 8;
@@ -842,7 +845,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         wrt::k_pack_materials<<<std::min(wide, (s->n_materials + 255) / 256), 256, 0, st>>>((const float*)dptr(10), s->n_materials, mats);
     }
     ds.geom = geom; ds.attr = attr; ds.ids = ids; ds.materials = mats; ds.prim_box = pbox; ds.tri_aux = taux;
-    ds.fnodes = fnodes; ds.dnodes = dnodes; ds.onodes = onodes; ds.ronodes = ronodes;
+    ds.fnodes = fnodes; ds.dnodes = dnodes; ds.onodes = onodes; ds.ronodes = ronodes; ds.wnodes = wnodes;
 
     // ---- 3. trees ----
     int fast_depth = 0;
@@ -903,6 +906,8 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         const int g = (int)std::min<long long>(wide, (8ll * nn + 255) / 256);
         wrt::k_octant_copies<<<g, 256, 0, st>>>(fnodes, nn, onodes);
         wrt::k_octant_copies<<<g, 256, 0, st>>>(ds.nodes, nn, ronodes);
+        ++c->launches;
+        wrt::k_wide4_copies<<<(int)std::min<long long>(wide, (4ll * nn + 255) / 256), 256, 0, st>>>(onodes, nn, wnodes);
     }
     CK(cudaGetLastError());
     unsigned* h_rb = c->h_counters + wrt::C_TOTAL;     // (the first C_TOTAL words belong to a frame that may still be in flight)
@@ -937,7 +942,9 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     memcpy(&ds.prune_slack, rb + 1, sizeof(float));     // k_pack_prims: scene maximum of wrt_prune_triangle_slack
     // the strategy queries never read texels; a frame render needs every referenced map present
     c->textures_complete = !(flags & 2);
-    c->stack_rows = std::max(c->bvh_depth, fast_depth) + 2;
+    // binary walks push at most one entry per level; the 4-wide walks (wide_bvh.h) descend two levels per node and push up
+    // to three
+    c->stack_rows = std::max(std::max(c->bvh_depth, fast_depth), 3 * ((fast_depth + 1) / 2)) + 2;
 #ifdef WRT_DEBUG_BOUNDS
     if (const char* e = getenv("WRT_DEBUG_STACK_ROWS")) c->stack_rows = std::max(1, atoi(e));   // provoke the stack check (tests)
 #endif

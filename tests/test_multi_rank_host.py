@@ -85,3 +85,55 @@ def test_gather_to_rank0_over_gloo(world, w, h):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _overflow_worker(rank, world, port, w, h, q):
+    """The repeat-gather protocol of DistributedRenderer.finish(): rank 1's first frame is incomplete (its queue
+    overflowed: half of its pixels are missing); after its re-render every rank learns about it through one flag
+    all-reduce and gather + scatter run again."""
+    import torch.distributed as dist
+    from whittedstyle_raytracer_b200 import parallel
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        yy, xx = np.mgrid[0:h, 0:w]
+        full = np.stack([xx % 251, yy % 241, (xx * 7 + yy * 13) % 239], axis=-1).astype(np.uint8)
+        tg = parallel.TileGather(w, h, rank, world)
+        m = parallel.tile_pixel_map(w, h, rank, world)
+        packed = tg.new_buffer("cpu")
+        buf = packed.numpy().reshape(-1, 3)
+        flat = full.reshape(-1, 3)
+        ok = m >= 0
+        if rank == 1:
+            ok = ok & (np.arange(len(m)) < len(m) // 2)          # dropped rays: the second half never arrived
+        buf[:len(m)][ok] = flat[m[ok]]
+        g = tg.gather(packed)
+        first_ok = None
+        if rank == 0:
+            first_ok = bool(np.array_equal(parallel.scatter_tiles_host(g.numpy(), w, h, world), full))
+        overflowed = rank == 1
+        if overflowed:                                           # wrt_finish_device re-rendered the frame
+            buf[:len(m)][m >= 0] = flat[m[m >= 0]]
+        again = parallel.any_rank_flag(overflowed)
+        if again:
+            g = tg.gather(packed)
+        if rank == 0:
+            img = parallel.scatter_tiles_host(g.numpy(), w, h, world)
+            q.put((first_ok, again, bool(np.array_equal(img, full))))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overflowed_rank_triggers_a_second_gather():
+    world, w, h = 3, 160, 96
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overflow_worker, args=(r, world, port, w, h, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    first_ok, again, final_ok = q.get(timeout=5)
+    assert first_ok is False and again is True and final_ok is True

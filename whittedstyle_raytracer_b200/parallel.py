@@ -74,6 +74,15 @@ class TileGather:
         return None
 
 
+def any_rank_flag(flag: bool, device="cpu") -> bool:
+    """True on every rank when `flag` is true on at least one (one int32 all-reduce; any backend)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(int(t.item()))
+
+
 class DistributedRenderer:
     """Per-rank renderer + the gather.  `frame()` leaves the full image on rank 0's GPU."""
 
@@ -112,11 +121,7 @@ class DistributedRenderer:
         all-reduce, N > 1 only) on whether the gather + scatter must be repeated."""
         stats = self.renderer.finish_device()
         if self.world > 1:
-            import torch.distributed as dist
-            flag = self.torch.tensor([1 if stats["overflow_retries"] else 0], dtype=self.torch.int32,
-                                     device=self.packed.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            if int(flag.item()):
+            if any_rank_flag(bool(stats["overflow_retries"]), self.packed.device):
                 self._gather_scatter(self.torch.cuda.current_stream().cuda_stream)
                 self.torch.cuda.current_stream().synchronize()
         return stats

@@ -616,7 +616,7 @@ struct SoftListBuffers {
 #ifndef WRT_LISTS_REFILL
 #define WRT_LISTS_REFILL 8
 #endif
-#define WRT_SHAFT_SLOT 10         // floats a staged shaft occupies: o, ilo, ihi, octant | use
+#define WRT_SHAFT_SLOT 12         // floats a staged shaft occupies: o, ilo, ihi, octant | use, -, request index
 
 // One lane walks one request's shaft, but walk lengths differ a lot (3 ... 400 node pairs; ncu: 8.6 of 32 lanes
 // active when every lane takes one request and the warp waits for the longest).  So a warp owns a chunk of
@@ -635,11 +635,162 @@ struct SoftListBuffers {
 // 24 bytes of spills: 3.13 ms; unbounded 80 registers: 5 CTAs.)
 // (A per-leaf "own plane" test inside the walk — three quarters of the leaves a fully lit request finds are its own
 // neighbours, which k_soft_filter then removes — was built and measured: the walk runs one lane per request, the test
-// costs two dependent loads and ~40 instructions at that width: 6.3 ms against 3.1.  The filter kernel, which spreads
-// candidates over lanes, is the right place.)
+// costs two dependent loads and ~40 instructions at that width: 6.3 ms against 3.1.  The same test a candidate per lane
+// while the warp copies a finished list into the pool: 3.7 ms against 2.6 — the flush is the serial part of this kernel.
+// The filter kernel, which spreads (request, candidate) pairs over all lanes, is the right place.)
 #ifndef WRT_LISTS_MIN_BLOCKS
 #define WRT_LISTS_MIN_BLOCKS 8
 #endif
+#ifndef WRT_LISTS_STREAM
+#define WRT_LISTS_STREAM 1        // 1: a warp claims 32 requests whenever its idle lanes outnumber the prepared requests
+#endif
+#if WRT_LISTS_STREAM
+// Streaming form.  The chunked form below ends every chunk with its longest walk: on a short queue (one GPU's share of an
+// 8-GPU frame: 2-3 requests per lane) a chunk is one request per lane, almost every chunk holds a request in shadow whose
+// walk is 5x the average, and the lanes wait for it: 695 us for 0.5 M requests where the work is ~150 us.  Here a warp never
+// waits for a chunk: whenever WRT_LISTS_REFILL lanes are idle it flushes their lists and hands them new requests from a
+// small ring of PREPARED requests (shafts built 32 at a time by all lanes, fully converged — set-up code on a few lanes
+// at a time is what made the run_queue attempt slower); the ring is topped up from the global counter, 32 requests per
+// claim.  A lane keeps the index of its request in a register: its ring slot may be reused while it is still walking.  Pool space is taken per flush (>= WRT_LISTS_REFILL lists, one atomic).
+__global__ void __launch_bounds__(128, WRT_LISTS_MIN_BLOCKS) k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
+                                                        int work_slot, int stack_rows, SoftListBuffers lb) {
+    extern __shared__ int smem[];
+    Stack st;
+    st.init(smem, threadIdx.x, blockDim.x);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned nreq = queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);
+    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    int* warp_scratch = lb.scratch + gwarp * 32 * WRT_LIST_CAP;
+    int* mine = warp_scratch + (size_t)lane * WRT_LIST_CAP;
+    float* slots = lb.shafts + gwarp * (size_t)WRT_LISTS_CHUNK * WRT_SHAFT_SLOT;     // ring of WRT_LISTS_CHUNK prepared requests
+    unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
+    unsigned* pool_head = fb.counters + C_POOL + q;
+    unsigned n_empty = 0;
+    unsigned head = 0, tail = 0;                             // warp-uniform: ring entries [head, tail) are prepared, not yet handed out
+    bool drained = false;                                    // warp-uniform: the global queue has nothing left
+    bool active = false;
+    int pend = -2;                                           // finished walk waiting for the flush: list length, -1 = give up; -2 = nothing
+    unsigned req = 0;                                        // the request this lane is walking / has walked
+    WrtShaft sh;
+    WrtShaftWalk w;
+    w.nodes = s.onodes; w.cur = 0; w.sp = 0; w.n = 0;
+    while (true) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        const bool more = !drained || head != tail;
+        if (idle == 0xffffffffu || (more && __popc(idle) >= WRT_LISTS_REFILL)) {
+            // ---- flush: the finished lists -> pool, all lanes copying ----
+            __syncwarp();                                    // the lists other lanes wrote to their scratch columns are visible
+            const int cnt = pend > 0 ? pend : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= (unsigned)off) incl += v;
+            }
+            const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+            if (total > 0) {
+                unsigned first = 0xffffffffu;
+                if (lane == 0 && *(volatile unsigned*)pool_head < lb.pool_cap) first = atomicAdd(pool_head, total);
+                first = __shfl_sync(0xffffffffu, first, 0);
+                const bool fits = first < lb.pool_cap && total <= lb.pool_cap - first;   // a full pool: count = -1, ray by ray
+                const unsigned dst = first + (unsigned)(incl - cnt);
+                unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+                while (todo) {
+                    const int src_lane = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int c = __shfl_sync(0xffffffffu, cnt, src_lane);
+                    const unsigned d0 = __shfl_sync(0xffffffffu, dst, src_lane);
+                    if (fits) {
+                        const int* src = warp_scratch + (size_t)src_lane * WRT_LIST_CAP;
+                        for (int i = (int)lane; i < c; i += 32)
+                            if (WRT_IN_BOUNDS(d0 + i, lb.pool_cap)) lb.pool[d0 + i] = src[i];
+                    }
+                }
+                if (cnt > 0 && WRT_IN_BOUNDS(req, fb.preq_cap[q])) lb.ref[req] = fits ? make_int2((int)dst, cnt) : make_int2(0, -1);
+            }
+            if (pend == 0 || pend == -1) {                   // empty list (= lit, no rays needed) / give up (= ray by ray)
+                if (WRT_IN_BOUNDS(req, fb.preq_cap[q])) lb.ref[req] = make_int2(0, pend);
+                if (pend == 0) ++n_empty;
+            }
+            pend = -2;
+            __syncwarp();                                    // the scratch columns are free again
+            // ---- top up the ring: 32 requests per claim, shafts built by all lanes ----
+            const unsigned need = __popc(idle);
+            while (!drained && tail - head < need) {
+                unsigned long long claimed = 0;
+                if (lane == 0) claimed = atomicAdd(work, 32ull);
+                claimed = __shfl_sync(0xffffffffu, claimed, 0);
+                if (claimed >= nreq) { drained = true; break; }
+                const unsigned base = (unsigned)claimed;
+                const unsigned n = nreq - base < 32u ? nreq - base : 32u;
+                if (lane < n) {
+                    const float4 o4 = fb.preq_o[q][base + lane];
+                    const uint4 k = fb.preq_k[q][base + lane];
+                    const WrtLight* L = s.lights + k.x;
+                    float tri[9];
+                    for (int i = 0; i < 9; i++) tri[i] = L->tri[i];
+                    const float o[3] = {o4.x, o4.y, o4.z};
+                    WrtShaft t;
+                    const bool ok = wrt_shaft_make(o, tri, &t);
+                    float* d = slots + (size_t)((tail + lane) % WRT_LISTS_CHUNK) * WRT_SHAFT_SLOT;
+                    d[0] = t.o[0]; d[1] = t.o[1]; d[2] = t.o[2];
+                    d[3] = t.ilo[0]; d[4] = t.ilo[1]; d[5] = t.ilo[2];
+                    d[6] = t.ihi[0]; d[7] = t.ihi[1]; d[8] = t.ihi[2];
+                    d[9] = __int_as_float(ok ? (t.octant | (t.use << 3)) : -1);
+                    d[10] = 0.f;
+                    d[11] = __uint_as_float(base + lane);
+                }
+                tail += n;
+                __syncwarp();
+            }
+            // ---- hand the prepared requests to the idle lanes ----
+            {
+                const unsigned avail = tail - head;
+                const unsigned rank = __popc(idle & lt_mask);
+                if (!active && rank < avail) {
+                    const float* d = slots + (size_t)((head + rank) % WRT_LISTS_CHUNK) * WRT_SHAFT_SLOT;
+                    const int ou = __float_as_int(d[9]);
+                    req = __float_as_uint(d[11]);
+                    int rc = -1;
+                    if (ou >= 0) {
+                        sh.o[0] = d[0]; sh.o[1] = d[1]; sh.o[2] = d[2];
+                        sh.ilo[0] = d[3]; sh.ilo[1] = d[4]; sh.ilo[2] = d[5];
+                        sh.ihi[0] = d[6]; sh.ihi[1] = d[7]; sh.ihi[2] = d[8];
+                        sh.octant = ou & 7; sh.use = ou >> 3;
+#if WRT_WIDE4
+                        rc = wrt_shaft_walk_begin4(s.onodes, s.wnodes, s.n_nodes, &sh, &w);
+#else
+                        rc = wrt_shaft_walk_begin(s.onodes, s.n_nodes, &sh, &w);
+#endif
+                    }
+                    if (rc == 1) active = true;
+                    else pend = rc;                          // answered without a walk; recorded by the next flush
+                }
+                head += need < avail ? need : avail;
+                __syncwarp();                                // the slots just read may be rewritten by the next top-up
+            }
+            if (!__any_sync(0xffffffffu, active)) {
+                if (drained && head == tail && !__any_sync(0xffffffffu, pend != -2)) break;
+                continue;
+            }
+        }
+#pragma unroll 1
+        for (int it = 0; it < 4; it++) {
+            if (active) {
+#if WRT_WIDE4
+                const int rc = wrt_shaft_walk_step4(&sh, &w, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+#else
+                const int rc = wrt_shaft_walk_step(&sh, &w, st.base, st.stride, stack_rows, mine, WRT_LIST_CAP);
+#endif
+                if (rc != 1) { active = false; pend = rc < 0 ? -1 : w.n; }
+            }
+        }
+    }
+    n_empty = __reduce_add_sync(0xffffffffu, n_empty);
+    if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);
+}
+#else
 __global__ void __launch_bounds__(128, WRT_LISTS_MIN_BLOCKS) k_soft_lists(const __grid_constant__ DevScene s, const __grid_constant__ FrameBuffers fb, int q,
                                                         int work_slot, int stack_rows, SoftListBuffers lb) {
     extern __shared__ int smem[];
@@ -685,6 +836,8 @@ __global__ void __launch_bounds__(128, WRT_LISTS_MIN_BLOCKS) k_soft_lists(const 
             d[3] = sh.ilo[0]; d[4] = sh.ilo[1]; d[5] = sh.ilo[2];
             d[6] = sh.ihi[0]; d[7] = sh.ihi[1]; d[8] = sh.ihi[2];
             d[9] = __int_as_float(ok ? (sh.octant | (sh.use << 3)) : -1);
+            d[10] = 0.f;
+            d[11] = __uint_as_float(k.x);
         }
         // ---- pool region of the chunk: one atomic; [cursor, region_end) is what is left of it (warp-uniform) ----
         unsigned cursor = 0;
@@ -729,7 +882,7 @@ __global__ void __launch_bounds__(128, WRT_LISTS_MIN_BLOCKS) k_soft_lists(const 
                     }
                     const unsigned dst = first + (unsigned)(incl - cnt);
                     unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
-                    while (todo) {
+                        while (todo) {
                         const int src_lane = __ffs(todo) - 1;
                         todo &= todo - 1;
                         const int c = __shfl_sync(0xffffffffu, cnt, src_lane);
@@ -794,6 +947,8 @@ __global__ void __launch_bounds__(128, WRT_LISTS_MIN_BLOCKS) k_soft_lists(const 
     n_empty = __reduce_add_sync(0xffffffffu, n_empty);
     if (lane == 0 && n_empty) atomicAdd(fb.counters + C_NEMPTY, n_empty);
 }
+
+#endif
 
 // ---- K4b'': triangle-level pruning of the candidate lists (shaft_cull.h, wrt_pyramid_*) ----
 // The lists hold every primitive whose BOX a ray of the shaft may hit.  On the bunny's surface half of those triangles

@@ -97,8 +97,9 @@ struct WrtContext {
     int trace_blocks_per_sm = 10;      // persistent shadow / unfused closest-hit kernels
     bool shade0_separate = true;       // level 0 is shaded by its own launch on the side stream (else inside combine)
     int soft_filter = 2;               // 0: off, 1: prune the deep queues' candidate lists (k_soft_filter), 2: level 0's as well
-    int deep_split = 8;                // request queues: level 0 | levels 1..deep_split | deeper (8: one deep queue; 3 queues
-                                       // bought nothing at 1/8 frame size and cost 0.2 ms on a full frame)
+    int deep_split = 5;                // request queues: level 0 | levels 1..deep_split | deeper.  The shadow kernels of levels
+                                       // 1..5 run beside the closest-hit chain of levels 6..8 (4K soft frame: 14.55 ms with one
+                                       // deep queue, 14.34 / 14.14 / 14.40 with a split at 4 / 5 / 3; 1/8 share 2.56 -> 2.46 ms)
     int side_blocks_per_sm = 0;        // persistent shadow kernels on the side stream: CTAs per SM (0 = trace_blocks_per_sm)
     int fb_split = -1;
     bool small_batch_full_levels = true; // automatic sizing: batches under 1 M slots get full-size deep levels

@@ -1,13 +1,17 @@
 // kernels.cuh — the wavefront kernels (sm_100a, SIMT FP32; tensor cores unused:
 // the path is divergent traversal, not a dense contraction).
 //
-// One frame (Renderer.hpp:57-137), 25 launches for a soft-shadow frame:
+// One frame (Renderer.hpp:57-137), 23 launches with hard shadows, 30 for a soft-shadow frame:
 //   chain stream  for each ray-tree level d = 0..8 (Renderer.hpp:25 MAX_DEPTH 9)
-//                   k_trace_closest   rays[d] -> hits (level 0: primary rays generated in registers, Renderer.hpp:104-125)
-//                   k_surface_spawn   hits -> surface records, child rays[d+1], shadow requests: level 0 into queue 0, ALL
-//                                     deeper levels into ONE queue (queue 1)
-//                 k_soft_lists(1), k_soft_list_rays(1)   (or k_shadow_hard(1); + k_shadow_directional(1))
-//   side stream   k_soft_lists(0), k_soft_list_rays(0), k_shade(level 0)   beside the deep chain
+//                   k_trace_closest   rays[d] -> hits (level 0: primary rays generated in registers, Renderer.hpp:104-125;
+//                                     levels 1..8 walk the 4-wide view of the tree, wide_bvh.h)
+//                   k_surface_spawn   hits -> surface records, child rays[d+1], shadow requests into one of three queues:
+//                                     queue 0 = level 0, queue 1 = levels 1..5, queue 2 = levels 6..8
+//                 after level 8: the shadow kernels of queue 2
+//   side stream   the shadow kernels of queue 0 + k_shade(level 0) beside the deep chain, then — once level 5's surface
+//                 stage is done — the shadow kernels of queue 1 beside the chain of levels 6..8
+//                 shadow kernels of a queue: k_shadow_hard, or k_soft_lists -> k_soft_filter -> k_soft_list_rays
+//                 (+ k_shadow_directional)
 //   chain stream  k_combine_resolve         shades the deep nodes, then colour = local + fr*R + (1-fr)(1-alpha)*T bottom-up in
 //                                           the reference's own association (Renderer.hpp:259) and int(255*min(c,1))
 //                                           (Renderer.hpp:128-130); one cooperative launch.
@@ -16,8 +20,8 @@
 // the 64 the traversal needs for its occupancy, ptxas spills the ray's 1/d and the node pointer inside the hot loop
 // (profiles/NOTES.md).)
 // The only dependent chain is the 9 closest-hit launches; the shadow work of the deep levels — independent of the
-// chain — is not cut into 8 per-level launches with 8 tails, and level 0's shadow work fills the SMs the short deep
-// levels leave idle.
+// chain — is cut into two sets of launches, not eight with eight tails, and level 0's shadow work fills the SMs the
+// short deep levels leave idle.
 //
 // Every queue length lives in device memory (Counters); kernels read it there, so
 // the host enqueues the whole frame without synchronising.
@@ -958,7 +962,8 @@ __global__ void __launch_bounds__(128, WRT_LISTS_MIN_BLOCKS) k_soft_lists(const 
 // with an empty list and need no rays at all.  Exact: a removed triangle blocks no sample ray (proof obligations and the
 // brute-force check: shaft_cull.h, tests/shaft_cull_check.cpp).
 #ifndef WRT_FILTER_MIN
-#define WRT_FILTER_MIN 3          // shorter lists are not worth the pyramid set-up
+#define WRT_FILTER_MIN 1          // every non-empty list: with the edge planes most 1- and 2-member lists of fully lit requests
+                                  // come out empty and their 50 rays are never built (3 / 2 / 1: 14.19 / 13.64 / 13.57 ms per 4K frame)
 #endif
 // A warp takes 32 consecutive requests: (A) each lane builds its request's pyramid (4 cross products, 8 square roots, 4
 // divisions — once per request, not once per candidate) into shared memory; (B) the 32 lists are treated as ONE sequence

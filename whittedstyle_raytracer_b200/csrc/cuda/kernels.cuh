@@ -1,7 +1,7 @@
 // kernels.cuh — the wavefront kernels (sm_100a, SIMT FP32; tensor cores unused:
 // the path is divergent traversal, not a dense contraction).
 //
-// One frame (Renderer.hpp:57-137), 23 launches with hard shadows, 30 for a soft-shadow frame:
+// One frame (Renderer.hpp:57-137), 24 launches with hard shadows, 30 for a soft-shadow frame:
 //   chain stream  for each ray-tree level d = 0..8 (Renderer.hpp:25 MAX_DEPTH 9)
 //                   k_trace_closest   rays[d] -> hits (level 0: primary rays generated in registers, Renderer.hpp:104-125;
 //                                     levels 1..8 walk the 4-wide view of the tree, wide_bvh.h)

@@ -14,7 +14,7 @@ for w in water_bunny_tex_soft_4k bunny_shadow_4k f4_directional_4k f4_spheres_1k
   echo "ncu $w exit $?"
 done
 python tools/gpu_one_frame.py water_bunny_tex_soft_4k 2 > gpurun_out/r2u_plain2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_soft_list_rays|k_soft_lists|k_soft_filter|k_trace_closest|k_surface_spawn" -s 30 -c 30 -o gpurun_out/r2u_full python tools/gpu_one_frame.py water_bunny_tex_soft_4k 2 > gpurun_out/r2u_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_soft_list_rays|k_soft_lists|k_soft_filter|k_trace_closest|k_surface_spawn" -s 27 -c 27 -o gpurun_out/r2u_full python tools/gpu_one_frame.py water_bunny_tex_soft_4k 2 > gpurun_out/r2u_ncu_full.log 2>&1
 echo "ncu full exit $?"
 python - <<'PY'
 import json

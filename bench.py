@@ -437,6 +437,15 @@ def measure_workload(workload, steps, warmup, dist_env, cpu_seconds, want_clocks
             "per_rank_rays_traced": [int(x) for x in per_rank_rays.tolist()],
             "roofline": roofline,
             "cpu_baseline": cpu,
+            # `value` counts traced rays, so every shadow ray answered exactly without tracing LOWERS it while the frame gets
+            # faster; the like-for-like comparison with the reference is the time to the same (bit-identical) image
+            "time_to_image": None if cpu is None else {
+                "frame_ms_device": ms_per_step, "frame_ms_e2e": e2e_ms_per_step,
+                "reference_frame_s": cpu["frame_seconds_extrapolated"],
+                "speedup_device": cpu["frame_seconds_extrapolated"] / (ms_per_step * 1e-3),
+                "speedup_e2e": cpu["frame_seconds_extrapolated"] / (e2e_ms_per_step * 1e-3),
+                "note": "reference_frame_s = the frame's reference ray count / the reference's measured rays per second "
+                        "(cpu_baseline, 1 thread: the reference is single-threaded)"},
             "clocks": clocks,
         }
     barrier()

@@ -386,7 +386,7 @@ int enqueue_shadows(WrtContext* c, cudaStream_t st, int q, int& work_seq) {
     }
     if (ds.n_dir_lights > 0) {
         LaunchScope ls(c, st, F_SHADOW_DIR);
-        k_shadow_directional<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), refill, c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
+        k_shadow_directional<<<wide_grid, TB, sb, st>>>(ds, fb, q, c->traversal == WRT_TRAVERSAL_EXHAUSTIVE ? 1 : 0);
     }
     return 0;
 }

@@ -282,6 +282,75 @@ __device__ __forceinline__ bool traverse_step4(const float4* __restrict__ wnodes
     return true;
 }
 
+// The closest-hit walk over the 4-wide view with DEFERRED leaves.  traverse_step4 tests every hit leaf of a node at once:
+// a lane with two leaf hits runs the ~110-instruction intersection code twice while the warp's other lanes wait, and in a
+// warp of ~24 walking lanes some lane has a second leaf in nearly every step — so the warp pays two or three rounds of
+// leaf code per node step, the later ones with 2-3 lanes.  Here a lane tests at most ONE leaf per step, at one code site:
+// of a node's hits, taken nearest first, the first leaf goes to the lane's leaf slot, the first other hit becomes `cur`
+// (an inner pair, or a leaf link: it is then tested by the next step), the rest is pushed far to near — leaf links (< 0)
+// lie on the stack beside pair indices.  A step whose `cur` is a leaf link takes it into the leaf slot and visits the
+// pair on top of the stack beside it.  Exactness: every tested primitive has had its own box hit by the ray, and the
+// closest-hit result (min t, ties to the smaller primitive index) does not depend on the order of the tests; a deferred
+// leaf is tested without its entry distance (a superset of what the pruning keeps).
+#ifndef WRT_LEAF_DEFER
+#define WRT_LEAF_DEFER 0
+#endif
+#define WRT_NO_LINK (-2147483647 - 1)      // (also the link of a wide node's empty slot, which no ray reaches)
+template <bool NEAR_FIRST, class LeafFn>
+__device__ __forceinline__ bool traverse_step4_defer(const float4* __restrict__ wnodes, const Ray& r, Stack& st, int& cur,
+                                                     const float& limit, LeafFn&& leaf) {
+    const float inf = INFINITY;
+    int pend = WRT_NO_LINK;
+    float tp = -inf;
+    if (cur < 0) {                                         // a deferred leaf
+        pend = cur;
+        cur = WRT_NO_LINK;
+        if (!st.empty()) {
+            const int nx = st.pop();
+            if (nx >= 0) cur = nx; else ++st.sp;           // a pair: visit it in this step; another leaf: leave it there
+        }
+    }
+    if (cur >= 0) {
+        const float4* n = wnodes + WRT_WIDE_FLOAT4_PER_RECORD * (size_t)cur;
+        float4 a0, a1, b0, b1, c0, c1, d0, d1;
+        ldg8(n, a0, a1);
+        ldg8(n + 2, b0, b1);
+        ldg8(n + 4, c0, c1);
+        ldg8(n + 6, d0, d1);
+        float t0, t1, t2, t3;
+        const bool h0 = slab_presorted(a0, a1, r, t0), h1 = slab_presorted(b0, b1, r, t1);
+        const bool h2 = slab_presorted(c0, c1, r, t2), h3 = slab_presorted(d0, d1, r, t3);
+        int l0 = __float_as_int(a0.w), l1 = __float_as_int(b0.w), l2 = __float_as_int(c0.w), l3 = __float_as_int(d0.w);
+        float k0 = (h0 && !(t0 > limit)) ? t0 : inf, k1 = (h1 && !(t1 > limit)) ? t1 : inf;
+        float k2 = (h2 && !(t2 > limit)) ? t2 : inf, k3 = (h3 && !(t3 > limit)) ? t3 : inf;
+#define WRT_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const float kt = sw ? ka : kb; ka = sw ? kb : ka; kb = kt; const int lt = sw ? la : lb; la = sw ? lb : la; lb = lt; }
+        if (NEAR_FIRST) { WRT_CSWAP(k0, l0, k1, l1) WRT_CSWAP(k2, l2, k3, l3) WRT_CSWAP(k0, l0, k2, l2) WRT_CSWAP(k1, l1, k3, l3) WRT_CSWAP(k1, l1, k2, l2) }
+#undef WRT_CSWAP
+        bool have_p = pend != WRT_NO_LINK, have_c = false;
+        cur = WRT_NO_LINK;
+        // nearest first: leaf slot, then `cur`, the others wait on the stack
+#define WRT_TAKE(kj, lj, pushj)                                                                    \
+        bool pushj = false;                                                                        \
+        if (kj < inf) {                                                                            \
+            if (lj < 0 && !have_p) { pend = lj; tp = kj; have_p = true; }                          \
+            else if (!have_c) { cur = lj; have_c = true; }                                         \
+            else pushj = true;                                                                     \
+        }
+        WRT_TAKE(k0, l0, p0) WRT_TAKE(k1, l1, p1) WRT_TAKE(k2, l2, p2) WRT_TAKE(k3, l3, p3)
+#undef WRT_TAKE
+        (void)p0;                                          // the nearest hit always finds a free place
+        if (p3) st.push(l3);
+        if (p2) st.push(l2);
+        if (p1) st.push(l1);
+    }
+    if (pend != WRT_NO_LINK && !(tp > limit)) leaf(~pend);
+    if (cur == WRT_NO_LINK) {
+        if (st.empty()) return false;
+        cur = st.pop();
+    }
+    return true;
+}
+
 struct Closest {
     float t; int prim; float u, v;
 };

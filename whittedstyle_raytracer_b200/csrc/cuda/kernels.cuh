@@ -384,7 +384,11 @@ struct ClosestQuery {
         return true;
     }
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
+#if WRT_LEAF_DEFER
+        if (WRT_WIDE4 && !LEVEL0 && wide) return traverse_step4_defer<true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
+#else
         if (WRT_WIDE4 && !LEVEL0 && wide) return traverse_step4<true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
+#endif
         return traverse_step<true, true>(nodes, r, st, cur, cs.limit, [&](int p) { cs.leaf(s, r, p); });
     }
     __device__ __forceinline__ bool finish(int&, Stack&) {
@@ -482,7 +486,11 @@ struct HardShadowQuery {
     __device__ __forceinline__ bool step(int& cur, Stack& st) {
         const float never = INFINITY;
         bool more;
+#if WRT_LEAF_DEFER >= 2
+        if (WRT_WIDE4 && wide) more = traverse_step4_defer<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
+#else
         if (WRT_WIDE4 && wide) more = traverse_step4<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
+#endif
         else more = traverse_step<false, true>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); });
         return more && res != 0.f;
     }
@@ -611,6 +619,9 @@ struct SoftListBuffers {
     unsigned pool_cap;
     unsigned region_per_request;   // pool entries a warp reserves per request of its chunk (one atomic per chunk)
 };
+#ifndef WRT_LIST_TWO_PHASE
+#define WRT_LIST_TWO_PHASE 0
+#endif
 #ifndef WRT_LIST_CHUNK_PASSES
 #define WRT_LIST_CHUNK_PASSES 8
 #endif
@@ -1168,7 +1179,26 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
                     occ = occluded(s, degenerate_dir(raydir) ? s.nodes : s.fnodes, r, dis, st);
                 } else {
                     const int* list = lb.pool + ref.x;
+#if WRT_LIST_TWO_PHASE
+                    // the same tests in the same order per ray, but the warp's lanes first all advance to their next
+                    // member whose own box the ray hits and then run the intersection code together
+                    int c = 0;
+                    while (!occ) {
+                        int p = -1;
+                        while (c < ref.y) {
+                            const int cand = list[c++];
+                            float te;
+                            float4 blo, bhi;
+                            ldg8(s.prim_box + 2 * (size_t)cand, blo, bhi);
+                            if (slab(blo, bhi, r, te)) { p = cand; break; }
+                        }
+                        if (p < 0) break;
+                        PrimHit h; float oma; unsigned fl;
+                        occ = prim_test(s, p, r, h, oma, fl) && h.t < dis;
+                    }
+#else
                     for (int c = 0; c < ref.y && !occ; c++) occ = occluder_cache_hit(s, r, dis, list[c]);
+#endif
                 }
                 lit = !occ;
             }

@@ -128,8 +128,11 @@ int main(int argc, char** argv) {
             if (cnt < 0) list_overflow++; else { lists++; list_items += cnt; if (is_empty != (cnt == 0)) violations++; }
             {   // the wide walks must reach exactly the same leaves (their order may differ)
                 if (wrt_shaft_is_empty4(onodes.data(), wnodes.data(), nn, o, L.tri) != is_empty) wide_mismatch++;
-                int stack4[96], list4[64];
-                const int cnt4 = wrt_shaft_candidates4(onodes.data(), wnodes.data(), nn, &sh, stack4, 1, 96, list4, 64);
+                // (the straight-line step checks the capacities once per step and gives up when fewer than 4 list / 3 stack
+                // entries are free: 4 spare entries make its verdict on lists of up to 64 the binary walk's)
+                int stack4[96], list4[68];
+                int cnt4 = wrt_shaft_candidates4(onodes.data(), wnodes.data(), nn, &sh, stack4, 1, 96, list4, 68);
+                if (cnt4 > 64) cnt4 = -1;
                 if (cnt4 != cnt) wide_mismatch++;
                 else for (int a = 0; a < cnt; a++) {
                     bool found = false;

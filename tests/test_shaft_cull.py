@@ -4,6 +4,7 @@ no sample ray, built with the kernel's float operations, hits the own box of any
 sample's 1/d must lie inside the shaft's bounds.  The GPU parity tests then pin the kernel end to end
 (soft-shadow frames are bit-compared with the oracle, which traces all 50 samples of every request)."""
 import json
+import os
 import subprocess
 from pathlib import Path
 
@@ -22,7 +23,8 @@ def checker(tmp_path_factory):
                      if (p / "vector_types.h").exists()), None)
     if cuda_inc is None:
         pytest.skip("CUDA headers (vector_types.h) not found")
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", f"-I{cuda_inc}",
+    extra = os.environ.get("WRT_TEST_CXXFLAGS", "").split()       # A/B builds of the header's compile-time variants
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", *extra, f"-I{cuda_inc}",
                     str(REPO / "tests" / "shaft_cull_check.cpp"), "-o", str(exe), f"-L{PKG}", "-lwrt_host",
                     f"-Wl,-rpath,{PKG}", "-pthread"], check=True)
     return exe

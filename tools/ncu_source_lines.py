@@ -40,6 +40,14 @@ for l in sass[start + 1:]:
         fresh = True
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
 rows = list(csv.reader(csvtxt))
+# a report with several launches: one section per launch, headed by "Kernel Name"; take the first whose demangled name
+# matches the part of the mangled name after its length prefix (k_...)
+want = re.search(r"k_[a-z0-9_]+", kname).group(0)
+sect = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if sect:
+    pick = next(i for i in sect if want + "(" in rows[i][1] or want + "<" in rows[i][1])
+    end = next((j for j in sect if j > pick), len(rows))
+    rows = rows[pick:end]
 hdr = next(r for r in rows if r and r[0] == "Address")
 data = [dict(zip(hdr, r)) for r in rows if len(r) == len(hdr) and r[0].startswith("0x")]
 base = int(data[0]["Address"], 16)

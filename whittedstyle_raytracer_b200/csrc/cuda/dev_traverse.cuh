@@ -158,6 +158,8 @@ __device__ __forceinline__ bool prim_test(const DevScene& s, int p, const Ray& r
 
 // Per-thread traversal stack in shared memory, column `tid` of a
 // [rows][blockDim.x] array (rows = tree depth + 2): consecutive lanes hit consecutive banks.
+// (A hybrid stack — the first 8 / 12 / 16 rows in shared memory, deeper ones in a per-thread local array, to give the 88 KB
+// L1 the 168 KB carve-out leaves more room — measured slower: closest hit 3.79-3.85 ms against 3.67; profiles/NOTES.md.)
 #ifdef WRT_DEBUG_BOUNDS
 __device__ unsigned g_wrt_stack_overflow = 0;       // latched by Stack::push in the bounds-checking build
 #endif
@@ -177,11 +179,12 @@ struct Stack {
         if (sp >= rows) { atomicExch(&g_wrt_stack_overflow, (unsigned)sp + 1u); return; }
         base[sp * stride] = v; ++sp;
     }
+    __device__ __forceinline__ int pop() { --sp; return base[sp * stride]; }
 #else
     __device__ __forceinline__ void init(int* smem, int tid, int nthreads) { base = smem + tid; stride = nthreads; sp = 0; }
     __device__ __forceinline__ void push(int v) { base[sp * stride] = v; ++sp; }
-#endif
     __device__ __forceinline__ int pop() { --sp; return base[sp * stride]; }
+#endif
     __device__ __forceinline__ bool empty() const { return sp == 0; }
 };
 
@@ -293,7 +296,10 @@ __device__ __forceinline__ bool traverse_step4(const float4* __restrict__ wnodes
 // closest-hit result (min t, ties to the smaller primitive index) does not depend on the order of the tests; a deferred
 // leaf is tested without its entry distance (a superset of what the pruning keeps).
 #ifndef WRT_LEAF_DEFER
-#define WRT_LEAF_DEFER 0
+#define WRT_LEAF_DEFER 2           // 0: traverse_step4 everywhere; 1: deferred leaves in the closest-hit walk; 2: and in the hard-shadow walk
+#endif
+#ifndef WRT_LEAF_DEFER_SIMPLE
+#define WRT_LEAF_DEFER_SIMPLE 1
 #endif
 #define WRT_NO_LINK (-2147483647 - 1)      // (also the link of a wide node's empty slot, which no ray reaches)
 template <bool NEAR_FIRST, class LeafFn>
@@ -326,6 +332,23 @@ __device__ __forceinline__ bool traverse_step4_defer(const float4* __restrict__ 
 #define WRT_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const float kt = sw ? ka : kb; ka = sw ? kb : ka; kb = kt; const int lt = sw ? la : lb; la = sw ? lb : la; lb = lt; }
         if (NEAR_FIRST) { WRT_CSWAP(k0, l0, k1, l1) WRT_CSWAP(k2, l2, k3, l3) WRT_CSWAP(k0, l0, k2, l2) WRT_CSWAP(k1, l1, k3, l3) WRT_CSWAP(k1, l1, k2, l2) }
 #undef WRT_CSWAP
+#if WRT_LEAF_DEFER_SIMPLE
+        if (NEAR_FIRST) {
+            // sorted: the hits are k0 <= k1 <= ..., misses (+inf) last.  Only the NEAREST hit may go to the leaf slot; a leaf
+            // further back becomes `cur` or waits on the stack like a pair (a third of the bookkeeping instructions of the
+            // general rule below)
+            const bool tk = (k0 < inf) && (l0 < 0) && (pend == WRT_NO_LINK);
+            if (tk) { pend = l0; tp = k0; }
+            const float kc = tk ? k1 : k0;
+            const int lc = tk ? l1 : l0;
+            cur = kc < inf ? lc : WRT_NO_LINK;
+            if (k3 < inf) st.push(l3);
+            if (k2 < inf) st.push(l2);
+            if (!tk && k1 < inf) st.push(l1);
+        } else {
+#else
+        {
+#endif
         bool have_p = pend != WRT_NO_LINK, have_c = false;
         cur = WRT_NO_LINK;
         // nearest first: leaf slot, then `cur`, the others wait on the stack
@@ -342,6 +365,7 @@ __device__ __forceinline__ bool traverse_step4_defer(const float4* __restrict__ 
         if (p3) st.push(l3);
         if (p2) st.push(l2);
         if (p1) st.push(l1);
+        }
     }
     if (pend != WRT_NO_LINK && !(tp > limit)) leaf(~pend);
     if (cur == WRT_NO_LINK) {
@@ -444,7 +468,7 @@ __device__ __forceinline__ float shadow_product(const DevScene& s, const float4*
 // primitives this is "some tested primitive is hit with t < dis" (the closest hit is < dis
 // iff some hit is), an early-out any-hit walk; with light avatars the two per-child
 // closest-hit queries are done literally on the reference tree.
-__device__ __noinline__ bool occluded_literal(const DevScene& s, const Ray r, float dis, Stack st) {
+__device__ __noinline__ bool occluded_literal(const DevScene& s, const Ray r, float dis, Stack& st) {
     int root_link = __float_as_int(ldg4(s.nodes).w);
     for (int k = 0; k < 2; k++) {
         Closest a = closest_hit(s, s.nodes, root_link + k, r, st, -1.f);
@@ -573,11 +597,14 @@ __device__ __forceinline__ float directional_product_bvh(const DevScene& s, cons
 //             bool step(cur, st)         — one traversal step; false = finished
 //             bool finish(cur, st)       — a walk ended: write results, or start the item's next
 //                                          walk and return true
+#ifndef WRT_STEPS_PER_ROUND
+#define WRT_STEPS_PER_ROUND 4      // traversal steps between two looks at the warp's idle lanes (the deep closest-hit levels: 8)
+#endif
 #ifndef WRT_CHUNK_MIN_PER
 #define WRT_CHUNK_MIN_PER 256
 #endif
 
-template <class Q>
+template <class Q, int STEPS = WRT_STEPS_PER_ROUND>
 __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned long long* work, Stack& st, int refill_cfg) {
     const int refill = refill_cfg & 0xff;
     const unsigned chunk_div = (unsigned)(refill_cfg >> 8);     // 0: one claim per refill; k: chunks of n / (warps * k)
@@ -635,7 +662,7 @@ __device__ __forceinline__ void run_queue(Q& q, unsigned long long n, unsigned l
             break;                                   // drained and nothing in flight
         }
 #pragma unroll 1
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < STEPS; k++) {
             if (active) {
                 active = q.step(cur, st);
                 if (!active) active = q.finish(cur, st);

@@ -128,6 +128,7 @@ struct WrtContext {
     int64_t launches = 0;
     int work_seq = 0;
     int coop_grid = 0;                 // co-resident CTAs of k_combine_resolve (cooperative launch)
+    int filter_grid = 0;               // resident CTAs of k_soft_filter
     WrtStats stats{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -373,7 +374,7 @@ int enqueue_shadows(WrtContext* c, cudaStream_t st, int q, int& work_seq) {
                 const bool filtered = c->soft_filter >= (q == 0 ? 2 : 1);
                 if (filtered) {                                     // triangle-level pruning of the lists
                     LaunchScope ls(c, st, F_SOFT_FILTER);
-                    k_soft_filter<<<wide_grid, TB, 0, st>>>(ds, fb, q, lb);
+                    k_soft_filter<<<WRT_FILTER_DYNAMIC ? c->filter_grid : wide_grid, TB, 0, st>>>(ds, fb, q, lb, WRT_FILTER_DYNAMIC ? work_slot() : 0);
                 }
                 LaunchScope ls(c, st, F_SHADOW_SOFT);
                 k_soft_list_rays<<<trace_grid, TB, sb, st>>>(ds, fb, q, work_slot(), c->seed, lb, filtered ? 1 : 0);
@@ -691,6 +692,9 @@ int wrt_create(int device, WrtContext** out) {
             return fail("wrt_create: cooperative launch of k_bvh_ploc is not possible on this device");
         }
         c->ploc_coop_grid = c->num_sms * std::min(per_sm, 2);
+        per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrt::k_soft_filter, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        c->filter_grid = c->num_sms * per_sm;           // one wave: the kernel claims its work dynamically
     }
     // tuning overrides (development only; defaults are what bench.py measures)
     if (const char* e = getenv("WRT_REFILL")) c->refill = std::max(1, std::min(32, atoi(e)));

@@ -74,6 +74,12 @@ int wrt_enable_kernel_timing(WrtContext* ctx, int on);
 
 /* ---- batch forms of the strategy queries (host pointers, synchronous) ---- */
 int wrt_trace_closest(WrtContext* ctx, const float* orig, const float* dir, int64_t n, WrtHit* hits);
+/* The same query (same arguments, same results bit for bit) answered by the kernel a frame traces its secondary rays with:
+ * the rays are written into ray-tree level 1 and traced by the wavefront closest-hit kernel (octant copies, 4-wide nodes,
+ * deferred leaves, per-lane refill).  wrt_trace_closest walks the plain binary tree one ray per thread; this entry exists
+ * so that the parity tests can hold the frame kernel itself to the oracle on arbitrary ray batches
+ * (IIntersectStrategy::UpdateInter, include/IIntersectStrategy.h:10-11). */
+int wrt_trace_closest_wavefront(WrtContext* ctx, const float* orig, const float* dir, int64_t n, WrtHit* hits);
 int wrt_shadow_hard(WrtContext* ctx, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff);
 int wrt_shadow_soft(WrtContext* ctx, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff);
 int wrt_shadow_directional(WrtContext* ctx, const float* pos, const int32_t* self_object, const float* lightdir4,

@@ -110,11 +110,14 @@ def test_million_random_rays_bit_exact(workdir):
     r = Renderer(scene)
     for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
         r.ctx.set_options(traversal=traversal)
-        h = r.interStrategy.UpdateInter(o, d)
-        for f in ("hit", "object", "prim"):
-            assert np.array_equal(h[f], ref[f]), (f, traversal)
-        for f in ("t", "pos", "ndir"):
-            assert np.array_equal(h[f].view(np.int32), ref[f].view(np.int32)), (f, traversal)
+        # the batch query (binary tree, one ray per thread) and the frame's own deep-level kernel (octant copies, 4-wide
+        # nodes, deferred leaves, lane refill: wrt_trace_closest_wavefront)
+        for query in (r.interStrategy.UpdateInter, r.interStrategy.UpdateInterWavefront):
+            h = query(o, d)
+            for f in ("hit", "object", "prim"):
+                assert np.array_equal(h[f], ref[f]), (f, traversal, query.__name__)
+            for f in ("t", "pos", "ndir"):
+                assert np.array_equal(h[f].view(np.int32), ref[f].view(np.int32)), (f, traversal, query.__name__)
     # shadow queries from the same points
     m = ref["hit"] == 1
     pos, nd = ref["pos"][m][:200000], ref["ndir"][m][:200000]
@@ -166,11 +169,12 @@ def test_adversarial_rays_pruned_equals_exhaustive(workdir):
     r = Renderer(scene)
     for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
         r.ctx.set_options(traversal=traversal)
-        h = r.interStrategy.UpdateInter(o, dd)
-        for f in ("hit", "object", "prim"):
-            assert np.array_equal(h[f], ref[f]), (f, traversal, int((h[f] != ref[f]).sum()))
-        for f in ("t", "pos", "ndir"):
-            assert np.array_equal(h[f].view(np.int32), ref[f].view(np.int32)), (f, traversal)
+        for query in (r.interStrategy.UpdateInter, r.interStrategy.UpdateInterWavefront):
+            h = query(o, dd)
+            for f in ("hit", "object", "prim"):
+                assert np.array_equal(h[f], ref[f]), (f, traversal, query.__name__, int((h[f] != ref[f]).sum()))
+            for f in ("t", "pos", "ndir"):
+                assert np.array_equal(h[f].view(np.int32), ref[f].view(np.int32)), (f, traversal, query.__name__)
     r.ctx.close()
 
 

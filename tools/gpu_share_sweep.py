@@ -20,24 +20,25 @@ scene = Scene.from_workdir(wd, name)
 
 KNOBS = [
     ("*default", {}),
-    ("trace_blocks=3", {"WRT_TRACE_BLOCKS": "3"}),
-    ("trace_blocks=4", {"WRT_TRACE_BLOCKS": "4"}),
-    ("trace_blocks=5", {"WRT_TRACE_BLOCKS": "5"}),
-    ("*trace_blocks=6", {"WRT_TRACE_BLOCKS": "6"}),
-    ("trace_blocks=8", {"WRT_TRACE_BLOCKS": "8"}),
-    ("trace_blocks=6 refill=8", {"WRT_TRACE_BLOCKS": "6", "WRT_REFILL": "8"}),
-    ("trace_blocks=4 refill=8", {"WRT_TRACE_BLOCKS": "4", "WRT_REFILL": "8"}),
-    ("refill=8", {"WRT_REFILL": "8"}),
-    ("refill=24", {"WRT_REFILL": "24"}),
-    ("deep_split=3", {"WRT_DEEP_SPLIT": "3"}),
-    ("deep_split=4", {"WRT_DEEP_SPLIT": "4"}),
-    ("deep_split=6", {"WRT_DEEP_SPLIT": "6"}),
+    ("side_blocks=5", {"WRT_SIDE_BLOCKS": "5"}),
+    ("*side_blocks=6", {"WRT_SIDE_BLOCKS": "6"}),
+    ("side_blocks=7", {"WRT_SIDE_BLOCKS": "7"}),
+    ("side_blocks=8", {"WRT_SIDE_BLOCKS": "8"}),
+    ("side_blocks=6 deep_split=7", {"WRT_SIDE_BLOCKS": "6", "WRT_DEEP_SPLIT": "7"}),
+    ("side_blocks=6 deep_split=8", {"WRT_SIDE_BLOCKS": "6", "WRT_DEEP_SPLIT": "8"}),
+    ("side_blocks=6 deep_split=6", {"WRT_SIDE_BLOCKS": "6", "WRT_DEEP_SPLIT": "6"}),
+    ("side_blocks=6 deep_split=4", {"WRT_SIDE_BLOCKS": "6", "WRT_DEEP_SPLIT": "4"}),
     ("deep_split=7", {"WRT_DEEP_SPLIT": "7"}),
     ("deep_split=8", {"WRT_DEEP_SPLIT": "8"}),
-    ("chunk_div=0", {"WRT_CHUNK_DIV": "0"}),
-    ("side_blocks=4", {"WRT_SIDE_BLOCKS": "4"}),
-    ("side_blocks=6", {"WRT_SIDE_BLOCKS": "6"}),
+    ("side_blocks=6 refill=24", {"WRT_SIDE_BLOCKS": "6", "WRT_REFILL": "24"}),
+    ("side_blocks=6 shade0_separate=0", {"WRT_SIDE_BLOCKS": "6", "WRT_SHADE0_SEPARATE": "0"}),
+    ("default (again)", {}),
 ]
+if os.environ.get("SWEEP_KNOBS"):             # "label:K=V,K=V;label2:..." replaces the table above
+    KNOBS = []
+    for item in os.environ["SWEEP_KNOBS"].split(";"):
+        label, _, kvs = item.partition(":")
+        KNOBS.append((label, dict(kv.split("=") for kv in kvs.split(",") if kv)))
 ALL = sorted({k for _, kv in KNOBS for k in kv})
 
 for label, kv in KNOBS:

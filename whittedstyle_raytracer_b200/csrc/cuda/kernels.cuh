@@ -4,7 +4,8 @@
 // One frame (Renderer.hpp:57-137), 24 launches with hard shadows, 30 for a soft-shadow frame:
 //   chain stream  for each ray-tree level d = 0..8 (Renderer.hpp:25 MAX_DEPTH 9)
 //                   k_trace_closest   rays[d] -> hits (level 0: primary rays generated in registers, Renderer.hpp:104-125;
-//                                     levels 1..8 walk the 4-wide view of the tree, wide_bvh.h)
+//                                     levels 1..8 walk the 4-wide view of the tree, wide_bvh.h, one leaf test per lane and
+//                                     step: traverse_step4_defer, dev_traverse.cuh)
 //                   k_surface_spawn   hits -> surface records, child rays[d+1], shadow requests into one of three queues:
 //                                     queue 0 = level 0, queue 1 = levels 1..5, queue 2 = levels 6..8
 //                 after level 8: the shadow kernels of queue 2
@@ -383,6 +384,9 @@ struct ClosestQuery {
         // (level 0: coherent primary rays, two thirds of them end on a wall after a few steps — the 4-wide node costs
         // registers there and buys nothing: 378 vs 338 us)
         wide = WRT_WIDE4 && !LEVEL0 && !ref_tree;
+        // (One copy for all octants — octant 0's holds the plain {pMin}{pMax} records — with the select-based slab test, to
+        // shrink the L1 footprint of the deep levels 8x: 3.73 against 3.70 ms, no gain; the fetches that stall are L2 hits
+        // deep in the tree, not the shared top levels.)
         if (wide) nodes = s.wnodes + (WRT_WIDE_FLOAT4_PER_RECORD / 2) * oct_off;
         return true;
     }
@@ -1362,6 +1366,23 @@ __global__ void __launch_bounds__(256) k_scatter_tiles(const unsigned char* gath
 
 // ======================= batch forms of the strategy queries =======================
 
+// Intersection record of a finished closest-hit query (what UpdateInter leaves in the reference's Intersection)
+__device__ __forceinline__ WrtHit hit_record(const DevScene& s, f3 o, f3 d, const Closest& c) {
+    WrtHit h;
+    h.hit = 0; h.object = -1; h.t = FLT_MAX; h.pos[0] = h.pos[1] = h.pos[2] = 0.f;
+    h.ndir[0] = h.ndir[1] = h.ndir[2] = 0.f; h.uv[0] = h.uv[1] = -1.f;
+    h.texture = -1; h.normalmap = -1; h.material = -1; h.prim = -1;
+    if (c.prim >= 0) {
+        Surface sf = complete_hit(s, o, d, c.t, c.prim, c.u, c.v);
+        h.hit = 1; h.prim = c.prim; h.object = __ldg(s.ids + c.prim).w; h.t = c.t;
+        h.pos[0] = sf.pos.x; h.pos[1] = sf.pos.y; h.pos[2] = sf.pos.z;
+        h.ndir[0] = sf.nDir.x; h.ndir[1] = sf.nDir.y; h.ndir[2] = sf.nDir.z;
+        h.uv[0] = sf.u; h.uv[1] = sf.v; h.texture = sf.textureIndex; h.normalmap = sf.normalMapIndex;
+        h.material = sf.material;
+    }
+    return h;
+}
+
 __global__ void __launch_bounds__(128) k_batch_closest(DevScene s, const float* orig, const float* dir, long long n,
                                                        WrtHit* out, float prune_rel) {
     extern __shared__ int smem[];
@@ -1370,25 +1391,38 @@ __global__ void __launch_bounds__(128) k_batch_closest(DevScene s, const float* 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         f3 o = mk3(orig[3 * i], orig[3 * i + 1], orig[3 * i + 2]);
         f3 d = mk3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
-        WrtHit h;
-        h.hit = 0; h.object = -1; h.t = FLT_MAX; h.pos[0] = h.pos[1] = h.pos[2] = 0.f;
-        h.ndir[0] = h.ndir[1] = h.ndir[2] = 0.f; h.uv[0] = h.uv[1] = -1.f;
-        h.texture = -1; h.normalmap = -1; h.material = -1; h.prim = -1;
+        Closest c;
+        c.t = FLT_MAX; c.prim = -1; c.u = 0.f; c.v = 0.f;
         if (s.n_nodes > 0) {
             Ray r = make_ray(o, d);
             float prune = prune_rel;
             const float4* nodes = pick_tree(s, d, prune);
-            Closest c = closest_hit(s, nodes, 0, r, st, prune);
-            if (c.prim >= 0) {
-                Surface sf = complete_hit(s, o, d, c.t, c.prim, c.u, c.v);
-                h.hit = 1; h.prim = c.prim; h.object = __ldg(s.ids + c.prim).w; h.t = c.t;
-                h.pos[0] = sf.pos.x; h.pos[1] = sf.pos.y; h.pos[2] = sf.pos.z;
-                h.ndir[0] = sf.nDir.x; h.ndir[1] = sf.nDir.y; h.ndir[2] = sf.nDir.z;
-                h.uv[0] = sf.u; h.uv[1] = sf.v; h.texture = sf.textureIndex; h.normalmap = sf.normalMapIndex;
-                h.material = sf.material;
-            }
+            c = closest_hit(s, nodes, 0, r, st, prune);
         }
-        out[i] = h;
+        out[i] = hit_record(s, o, d, c);
+    }
+}
+
+// ---- the same query answered by the FRAME's deep-level kernel (wrt_trace_closest_wavefront: the parity tests put
+// their ray batches through k_trace_closest<false> itself — octant copies, 4-wide nodes, deferred leaves, lane refill) ----
+__global__ void __launch_bounds__(256) k_pack_rays(const float* orig, const float* dir, unsigned n, float4* ray_o, float4* ray_d,
+                                                   unsigned* counters, int level) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        ray_o[i] = make_float4(orig[3 * (size_t)i], orig[3 * (size_t)i + 1], orig[3 * (size_t)i + 2], __uint_as_float(i));
+        ray_d[i] = make_float4(dir[3 * (size_t)i], dir[3 * (size_t)i + 1], dir[3 * (size_t)i + 2], __uint_as_float(1u));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[C_NRAYS + level] = n;     // all in the level's first (reflection) half
+}
+
+__global__ void __launch_bounds__(256) k_unpack_hits(const __grid_constant__ DevScene s, const float* orig, const float* dir, unsigned n,
+                                                     const float4* hit, WrtHit* out) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const f3 o = mk3(orig[3 * (size_t)i], orig[3 * (size_t)i + 1], orig[3 * (size_t)i + 2]);
+        const f3 d = mk3(dir[3 * (size_t)i], dir[3 * (size_t)i + 1], dir[3 * (size_t)i + 2]);
+        const float4 h = hit[i];
+        Closest c;
+        c.t = h.x; c.prim = __float_as_int(h.y); c.u = h.z; c.v = h.w;
+        out[i] = hit_record(s, o, d, c);
     }
 }
 

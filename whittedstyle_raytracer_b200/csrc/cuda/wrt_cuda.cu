@@ -100,7 +100,10 @@ struct WrtContext {
     int deep_split = 5;                // request queues: level 0 | levels 1..deep_split | deeper.  The shadow kernels of levels
                                        // 1..5 run beside the closest-hit chain of levels 6..8 (4K soft frame: 14.55 ms with one
                                        // deep queue, 14.34 / 14.14 / 14.40 with a split at 4 / 5 / 3; 1/8 share 2.56 -> 2.46 ms)
-    int side_blocks_per_sm = 0;        // persistent shadow kernels on the side stream: CTAs per SM (0 = trace_blocks_per_sm)
+    int side_blocks_per_sm = 6;        // persistent shadow kernels on the side stream: CTAs per SM (0 = trace_blocks_per_sm).  6 leave
+                                       // register file for two CTAs of the chain's kernel on every SM, so the chain keeps moving
+                                       // beside a long shadow kernel: 4K soft frame 12.73 -> 12.50 ms (5: 12.40, 7: 12.65, 8: 12.70);
+                                       // hard-shadow, 8K and sphere frames within +-0.5 %
     int fb_split = -1;
     bool small_batch_full_levels = true; // automatic sizing: batches under 1 M slots get full-size deep levels
     long long max_batch = 1ll << 25;   // primary slots per batch (8K = 33.2 M slots fits)
@@ -1025,6 +1028,40 @@ int wrt_trace_closest(WrtContext* c, const float* orig, const float* dir, int64_
                                                                   (const float*)c->d_scratch[1], n,
                                                                   (WrtHit*)c->d_scratch[2], prune_value(c));
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hits, c->d_scratch[2], (size_t)n * sizeof(WrtHit), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// The same query through the frame's own deep-level closest-hit kernel: the rays are written into ray-tree level 1's arrays
+// (all in its first half) and traced by k_trace_closest<false> exactly as a frame traces its secondary rays.
+int wrt_trace_closest_wavefront(WrtContext* c, const float* orig, const float* dir, int64_t n, WrtHit* hits) {
+    if (batch_common(c, n)) return 1;
+    if (n == 0) return 0;
+    if (c->frame_pending && finish_frame(c)) return 1;
+    cudaStream_t st = c->chain;
+    if (ensure_frame_buffers(c, std::max(c->batch_slots, 1u << 20))) return 1;
+    wrt::FrameBuffers& fb = c->fb;
+    const int64_t chunk = fb.capd / 2;
+    size_t vb = (size_t)n * 3 * sizeof(float);
+    if (ensure_scratch(c, 0, vb) || ensure_scratch(c, 1, vb) || ensure_scratch(c, 2, (size_t)n * sizeof(WrtHit))) return 1;
+    CK(cudaMemcpyAsync(c->d_scratch[0], orig, vb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_scratch[1], dir, vb, cudaMemcpyHostToDevice, st));
+    wrt::PrimaryGen pg;
+    memset(&pg, 0, sizeof pg);
+    const int level = 1;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const unsigned m = (unsigned)std::min<int64_t>(chunk, n - off);
+        const float* o = (const float*)c->d_scratch[0] + 3 * off;
+        const float* d = (const float*)c->d_scratch[1] + 3 * off;
+        CK(cudaMemsetAsync(fb.counters, 0, wrt::C_TOTAL * sizeof(unsigned), st));
+        c->launches += 3;
+        wrt::k_pack_rays<<<grid_for(c, 4), 256, 0, st>>>(o, d, m, fb.ray_o[level & 1], fb.ray_d[level & 1], fb.counters, level);
+        wrt::k_trace_closest<false><<<grid_for(c, c->trace_blocks_per_sm), 128, stack_bytes(c, 128), st>>>(
+            c->ds, fb, pg, level, 0u, wrt::C_WORK, prune_value(c), c->refill | (c->chunk_div << 8));
+        wrt::k_unpack_hits<<<grid_for(c, 4), 256, 0, st>>>(c->ds, o, d, m, fb.hit, (WrtHit*)c->d_scratch[2] + off);
+        CK(cudaGetLastError());
+    }
     CK(cudaMemcpyAsync(hits, c->d_scratch[2], (size_t)n * sizeof(WrtHit), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;

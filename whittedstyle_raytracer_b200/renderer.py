@@ -125,6 +125,13 @@ class CudaStrategy:
         self.ctx._check(self.ctx.lib.wrt_trace_closest(self.ctx.h, o.ctypes.data, d.ctypes.data, len(o), out.ctypes.data))
         return out
 
+    def UpdateInterWavefront(self, rayOrig, rayDir) -> np.ndarray:
+        """UpdateInter answered by the frame's own deep-level closest-hit kernel (wrt_trace_closest_wavefront)."""
+        o, d = _f32(rayOrig, 3), _f32(rayDir, 3)
+        out = np.zeros(len(o), dtype=cabi.HIT_DTYPE)
+        self.ctx._check(self.ctx.lib.wrt_trace_closest_wavefront(self.ctx.h, o.ctypes.data, d.ctypes.data, len(o), out.ctypes.data))
+        return out
+
     def getShadowCoeffi(self, pos, nDir, lightpos) -> np.ndarray:
         """Hard-shadow coefficient per (hit point, shading normal, light position)."""
         return self._shadow(self.ctx.lib.wrt_shadow_hard, pos, nDir, lightpos)

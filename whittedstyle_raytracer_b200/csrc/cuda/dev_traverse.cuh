@@ -367,6 +367,9 @@ __device__ __forceinline__ bool traverse_step4_defer(const float4* __restrict__ 
         if (p1) st.push(l1);
         }
     }
+    // (Taking the next node from the stack BEFORE the leaf test and prefetching its line to L1 meanwhile: closest hit 3.68 ->
+    // 3.64 ms, hard shadows 3.86 -> 3.82 — with ~1000 lanes per SM each prefetching its own 128-byte line, 131 KB of lines
+    // compete for the 88 KB of L1 the stacks leave.  Not kept.)
     if (pend != WRT_NO_LINK && !(tp > limit)) leaf(~pend);
     if (cur == WRT_NO_LINK) {
         if (st.empty()) return false;

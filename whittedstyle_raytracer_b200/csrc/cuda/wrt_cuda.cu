@@ -43,6 +43,7 @@ enum Family { F_RAYGEN, F_TRACE, F_SURFACE, F_SHADOW_HARD, F_SHADOW_SOFT, F_SHAD
 struct TimedLaunch {
     int family;
     cudaEvent_t e0, e1;
+    bool on_chain;
 };
 
 } // namespace
@@ -329,6 +330,7 @@ struct LaunchScope {                      // counts the launch; optionally brack
         ++c->launches;
         if (timed) {
             tl.family = family;
+            tl.on_chain = s == ctx->chain;
             tl.e0 = next_event(c);
             tl.e1 = next_event(c);
             cudaEventRecord(tl.e0, st);
@@ -402,7 +404,9 @@ int enqueue_batch(WrtContext* c, long long slot0, unsigned n, uint8_t* d_image, 
     FrameBuffers& fb = c->fb;
     const DevScene& ds = c->ds;
     cudaStream_t st = c->chain;
-    const bool overlap = c->overlap && !c->kernel_timing;
+    // (kernel timing serialises the frame: every launch on the chain stream.  WRT_TIMING_OVERLAP=1 keeps the two streams and
+    // turns the event pairs into a timeline of the frame as it really runs: WRT_TIMING_DUMP prints start and end of every launch)
+    const bool overlap = c->overlap && (!c->kernel_timing || getenv("WRT_TIMING_OVERLAP") != nullptr);
     cudaStream_t ss = overlap ? c->side : st;
     PrimaryGen pg;
     pg.cam = c->cam; pg.tm = c->tilemap(); pg.slot0 = slot0;
@@ -640,7 +644,13 @@ int finish_frame(WrtContext* c) {
     for (const TimedLaunch& tl : c->timed) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, tl.e0, tl.e1) == cudaSuccess) { c->family_ms[tl.family] += t; ++c->family_launches[tl.family]; }
-        if (dump) fprintf(stderr, "[wrt] launch family %d: %.1f us\n", tl.family, t * 1e3f);
+        if (dump) {
+            float t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&t0, c->ev_begin, tl.e0);
+            cudaEventElapsedTime(&t1, c->ev_begin, tl.e1);
+            fprintf(stderr, "[wrt] launch family %d: %.1f us  (%s stream, %.1f -> %.1f us after the frame's start)\n", tl.family, t * 1e3f,
+                    tl.on_chain ? "chain" : "side", t0 * 1e3f, t1 * 1e3f);
+        }
     }
     return 0;
 }

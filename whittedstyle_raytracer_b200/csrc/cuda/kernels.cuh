@@ -1060,11 +1060,10 @@ __device__ __forceinline__ void filter_pass(const DevScene& s, const SoftListBuf
     }
 }
 
-#ifdef WRT_FILTER_MIN_BLOCKS
-#define WRT_FILTER_BOUNDS __launch_bounds__(128, WRT_FILTER_MIN_BLOCKS)
-#else
-#define WRT_FILTER_BOUNDS __launch_bounds__(128)
+#ifndef WRT_FILTER_MIN_BLOCKS
+#define WRT_FILTER_MIN_BLOCKS 8   // 64 registers, no spills (unbounded: 70 registers, 7 CTAs per SM, 1.51 against 1.44 ms)
 #endif
+#define WRT_FILTER_BOUNDS __launch_bounds__(128, WRT_FILTER_MIN_BLOCKS)
 // Work distribution: blocks of 32 requests are claimed from a global counter (WRT_FILTER_DYNAMIC; the host sizes the grid to
 // what is resident).  The static round-robin over 8 CTAs per SM it replaces ran in two waves — 7 CTAs of 72 registers fit —
 // the second one with a single CTA per SM (ncu: 22-31 % achieved occupancy of 44 % possible).
@@ -1082,22 +1081,27 @@ __global__ void WRT_FILTER_BOUNDS k_soft_filter(const __grid_constant__ DevScene
     unsigned n_empty = 0;
 #if WRT_FILTER_DYNAMIC
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
-    (void)warps; (void)gw;
+    (void)gw;
+    // requests per claim: 32 (one per lane) on a long queue; on a short one — a rank's share of a multi-GPU frame holds
+    // less than a block per warp — 16 or 8, so that the launch does not end with the one warp that drew 32 long lists
+    const unsigned per_claim = nreq >= warps * 64u ? 32u : (nreq >= warps * 16u ? 16u : 8u);
     while (true) {
         unsigned long long claimed = 0;
-        if (lane == 0) claimed = atomicAdd(work, 32ull);
+        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)per_claim);
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
         if (claimed >= nreq) break;
         const unsigned base = (unsigned)claimed;
+        const unsigned lim = base + per_claim < nreq ? base + per_claim : nreq;    // this claim's requests end here
 #else
     for (unsigned base = gw * 32u; base < nreq; base += warps * 32u) {
+        const unsigned lim = nreq;
 #endif
         // ---- A ----
         const unsigned req = base + lane;
         int2 ref = make_int2(0, 0);
         bool ok = false;
         size_t out = 0;
-        if (req < nreq) {
+        if (req < lim) {
             ref = lb.ref[req];
             const float4 o4 = fb.preq_o[q][req];
             const uint4 k = fb.preq_k[q][req];
@@ -1135,7 +1139,7 @@ __global__ void WRT_FILTER_BOUNDS k_soft_filter(const __grid_constant__ DevScene
         }
         // ---- C: an empty list answers the request (all samples lit: the coefficient's start value 0 + 50, what the ray
         // kernel's atomics would add up to); the others go, compacted, to the ray kernel's work list ----
-        const bool live = req < nreq;
+        const bool live = req < lim;
         if (live && final_cnt == 0 && WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) fb.coeff[out] = (float)WRT_SOFT_SAMPLES;
         const unsigned need = __ballot_sync(0xffffffffu, live && final_cnt != 0);
         if (need) {
@@ -1162,12 +1166,17 @@ __global__ void WRT_TRACE_BOUNDS k_soft_list_rays(const __grid_constant__ DevSce
                                    : queue_len(fb.counters, C_NPREQ + q, fb.preq_cap[q]);   // host guarantees nreq * 50 < 2^32
     const unsigned n_rays = nreq * WRT_SOFT_SAMPLES, n_pass = (n_rays + 31u) / 32u;
     unsigned long long* work = reinterpret_cast<unsigned long long*>(fb.counters + work_slot);
+    // passes per claim: WRT_LIST_CHUNK_PASSES on a long queue, fewer when the launch holds less than four such claims per warp
+    // (a rank's share of a multi-GPU frame: the launch then ends with its last claim, not with the warp that drew two)
+    const unsigned warps_total = gridDim.x * (blockDim.x >> 5);
+    const unsigned chunk_passes = n_pass >= warps_total * 4u * WRT_LIST_CHUNK_PASSES ? (unsigned)WRT_LIST_CHUNK_PASSES
+                                  : (n_pass >= warps_total * 8u ? 2u : 1u);
     while (true) {
         unsigned long long claimed = 0;
-        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)WRT_LIST_CHUNK_PASSES);
+        if (lane == 0) claimed = atomicAdd(work, (unsigned long long)chunk_passes);
         claimed = __shfl_sync(0xffffffffu, claimed, 0);
         if (claimed >= n_pass) break;
-        const unsigned p0 = (unsigned)claimed, p1 = p0 + WRT_LIST_CHUNK_PASSES < n_pass ? p0 + WRT_LIST_CHUNK_PASSES : n_pass;
+        const unsigned p0 = (unsigned)claimed, p1 = p0 + chunk_passes < n_pass ? p0 + chunk_passes : n_pass;
 #pragma unroll 1
         for (unsigned pass = p0; pass < p1; pass++) {
             const unsigned j = pass * 32u + lane;

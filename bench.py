@@ -381,9 +381,11 @@ def measure_workload(workload, steps, warmup, dist_env, cpu_seconds, want_clocks
         "traffic": profile_traffic(kname),
         "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu "
                           "capture of this command (cannot be measured outside a profiler)",
-        "binding_bound": "NOT hbm and not tensor: instruction issue + L1 load latency of a divergent per-lane loop; `bound` says "
-                         "hbm only because the schema offers hbm|tensor — `fp32.executed` (ncu counters of the work the kernel "
-                         "really executes) and `lane_issue_frac` are the figures that say how close to the SIMT roof it runs",
+        "binding_bound": "NOT hbm and not tensor: the L1 data pipe of a divergent per-lane walk (every lane fetches its own "
+                         "128-byte node: l1tex__data_pipe_lsu_wavefronts at 87 % of peak on a deep level, profiles/NOTES.md) and "
+                         "instruction issue at half-empty warps; `bound` says hbm only because the schema offers hbm|tensor — "
+                         "`fp32.executed` (ncu counters of the work the kernel really executes) and `lane_issue_frac` say how "
+                         "close to the SIMT roof it runs",
         # FP32, three views: (1) executed — from the committed ncu counters of this kernel (profiles/r02_exec_metrics.json):
         # FADD+FMUL+2*FFMA thread-instructions / its duration, and lane-issue utilisation = IPC/4 x active lanes/32;
         # (2) algorithmic — the reference's own traversal counts per ray x the rays this kernel

@@ -13,6 +13,7 @@
 #include "dev_math.cuh"
 #include "prune_rule.h"
 #include "wide_bvh.h"
+#include "shadow_assoc.h"
 #include "../../../include/wrt_scene.h"
 
 namespace wrt {
@@ -33,6 +34,7 @@ struct DevScene {
     const float4* prim_box;   // per prim {pMin.xyz, 0} {pMax.xyz, 0}: the primitive's own (leaf) box, for the occluder cache
     const float4* tri_aux;    // per prim {unit plane normal, |E1|+|E2|} (w < 0: do not filter): ray-independent terms of the
                               // candidate-list pruning (shaft_cull.h wrt_triangle_aux)
+    const WrtPathCode* path_codes;   // per prim: its root-to-leaf path in the REFERENCE tree (shadow_assoc.h); nullptr: tree deeper than 64
     const float4* attr;       // per prim 4x float4: {n0,uv0.x} {n1,uv0.y} {n2,uv1.x} {uv1.y,uv2.x,uv2.y,0}
     const int4*   ids;        // per prim {material, texture, normalmap, object}
     const int*    object_prim;
@@ -444,25 +446,76 @@ __device__ __forceinline__ const float4* pick_tree(const DevScene& s, f3 dir, fl
 }
 
 // ---- hard shadow: BVHStrategy::ShadowHelper, BVHStrategy.hpp:24-48 ----
-// Product of (1-alpha) over every tested primitive hit with t < dis that is not a light
-// avatar; the walk stops once the product is exactly 0 (0 * x == 0 for finite x).
-__device__ __forceinline__ void shadow_leaf(const DevScene& s, const Ray& r, float dis, int p, float& res) {
+// Product of (1-alpha) over every tested primitive hit with t < dis that is not a light avatar; the walk stops once
+// the product is exactly 0 (0 * x == 0 for finite x).  The reference multiplies in the association of ITS tree (`l * r`), a
+// stack walk in visit order: the same bits for up to two factors != 1, not beyond (shadow_assoc.h).  ShadowAcc therefore
+// keeps the blocking primitives whose factor is not 1; a ray with three or more of them gets its product from
+// wrt_tree_product — the reference's association, rebuilt from the primitives' path codes — so the coefficient is the
+// reference's bit for bit.  (More than WRT_SHADOW_HITS such crossings on one ray, or a reference tree deeper than 64: the
+// visit-order product, within a few ulp.)
+struct ShadowAcc {
+    float res;
+    int n;                                 // blocking primitives with a factor != 1 so far
+    int prim[WRT_SHADOW_HITS];
+    float fac[WRT_SHADOW_HITS];
+    WrtPathCode code[WRT_SHADOW_HITS];     // fetched when the hit is made: the load is long back when the walk ends
+    __device__ __forceinline__ void reset() { res = 1.f; n = 0; }
+    // `collect` false: count only (the frame kernel's first walk of a ray; k_shadow_hard walks a ray with three or more
+    // translucent crossings a second time, collecting — storing every ray's hits cost a third of the kernel's time)
+    __device__ __forceinline__ void add(int p, float f, const WrtPathCode* codes, bool collect) {
+        res = res * f;
+        if (f != 1.f && f != 0.f) {            // (an opaque blocker ends the walk with an exact 0: nothing to associate)
+            if (collect && n < WRT_SHADOW_HITS) {
+                prim[n] = p; fac[n] = f;
+                if (codes) {
+                    const int4 c4 = __ldg(reinterpret_cast<const int4*>(codes + p));
+                    code[n].hi = (unsigned)c4.x; code[n].lo = (unsigned)c4.y; code[n].depth = c4.z; code[n].pad = 0;
+                }
+            }
+            ++n;
+        }
+    }
+    __device__ __forceinline__ bool needs_tree(const WrtPathCode* codes) const {
+        return res != 0.f && n >= 3 && n <= WRT_SHADOW_HITS && codes != nullptr;
+    }
+};
+
+// (out of line: one ray in ten of a glass-bunny frame, a few dozen instructions of sort + reduction on local arrays)
+__device__ __noinline__ float shadow_tree_value(const int* prim, const float* fac, const WrtPathCode* code, int n) {
+    int idx[WRT_SHADOW_HITS];
+    float fs[WRT_SHADOW_HITS];
+    for (int i = 0; i < n; i++) {          // insertion sort by primitive index = the reference tree's leaf order
+        const int key = prim[i];
+        int k = i;
+        while (k > 0 && prim[idx[k - 1]] > key) { idx[k] = idx[k - 1]; --k; }
+        idx[k] = i;
+    }
+    for (int i = 0; i < n; i++) fs[i] = fac[idx[i]];
+    return wrt_tree_product(n, idx, fs, code);             // (codes are looked up as code[idx[i]]: the hits' own copies)
+}
+
+__device__ __forceinline__ float shadow_value(const DevScene& s, const ShadowAcc& acc) {
+    return acc.needs_tree(s.path_codes) ? shadow_tree_value(acc.prim, acc.fac, acc.code, acc.n) : acc.res;
+}
+
+__device__ __forceinline__ void shadow_leaf(const DevScene& s, const Ray& r, float dis, int p, ShadowAcc& acc, bool collect = true) {
     PrimHit h; float oma; unsigned fl;
-    if (prim_test(s, p, r, h, oma, fl) && h.t < dis && !(fl & WRT_PRIM_LIGHT)) res = res * oma;
+    if (prim_test(s, p, r, h, oma, fl) && h.t < dis && !(fl & WRT_PRIM_LIGHT)) acc.add(p, oma, s.path_codes, collect);
 }
 
 __device__ __forceinline__ float shadow_product(const DevScene& s, const float4* nodes, const Ray& r, float dis, Stack& st) {
-    float res = 1.f;
-    if (s.n_nodes == 0) return res;
+    ShadowAcc acc;
+    acc.reset();
+    if (s.n_nodes == 0) return acc.res;
     float te;
     float4 lo = ldg4(nodes), hi = ldg4(nodes + 1);
-    if (!slab(lo, hi, r, te)) return res;
+    if (!slab(lo, hi, r, te)) return acc.res;
     int cur = __float_as_int(lo.w);
-    if (cur < 0) { shadow_leaf(s, r, dis, ~cur, res); return res; }
+    if (cur < 0) { shadow_leaf(s, r, dis, ~cur, acc); return acc.res; }
     st.sp = 0;
     const float never = INFINITY;
-    while (res != 0.f && traverse_step<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, res); })) {}
-    return res;
+    while (acc.res != 0.f && traverse_step<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, acc); })) {}
+    return shadow_value(s, acc);
 }
 
 // ---- soft-shadow visibility: hasIntersection, BVH.hpp:162-186 ----

@@ -67,6 +67,7 @@ struct WrtContext {
     bool textures_complete = true;
     int bvh_depth = 0;
     int stack_rows = 2;
+    std::vector<WrtPathCode> path_codes;   // host copy staged by wrt_upload_scene
 
     // camera / tiling / options
     WrtCamera cam{};
@@ -786,6 +787,8 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     static_assert(sizeof(WrtNode) == 32, "WrtNode must be 32 bytes");
     static_assert(sizeof(WrtMaterial) == 48, "WrtMaterial must be 12 floats");
 
+    c->bvh_depth = tree_depth(s);
+
     // ---- 1. stage + one H2D ----
     struct Part { const void* src; size_t bytes; size_t off; };
     Part parts[] = {
@@ -804,7 +807,31 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
         {s->textures, (size_t)s->n_textures * sizeof(WrtTexture), 0},      // 12
         {s->normalmaps, (size_t)s->n_normalmaps * sizeof(WrtTexture), 0},  // 13
         {s->texels, (size_t)s->n_texels * 12, 0},                    // 14
+        {nullptr, 0, 0},                                             // 15: path codes of the primitives (below)
     };
+    // Root-to-leaf paths of the primitives in the scene's (= the reference's) tree: what the hard-shadow product needs to
+    // multiply in that tree's association (shadow_assoc.h).  A tree deeper than 64 gets none (visit-order product).
+    c->path_codes.clear();
+    if (np > 0 && nn > 0 && c->bvh_depth <= WRT_PATH_BITS) {
+        c->path_codes.assign((size_t)np, WrtPathCode{0u, 0u, 0, 0});
+        struct Item { int rec; int depth; unsigned long long path; };
+        std::vector<Item> todo;
+        todo.push_back({0, 0, 0ull});
+        while (!todo.empty()) {
+            const Item it = todo.back();
+            todo.pop_back();
+            const int link = s->nodes[it.rec].link;
+            if (link < 0) {
+                const int prim = ~link;
+                if (prim >= 0 && prim < np) c->path_codes[prim] = WrtPathCode{(unsigned)(it.path >> 32), (unsigned)it.path, it.depth, 0};
+            } else if (it.depth < WRT_PATH_BITS) {
+                todo.push_back({link, it.depth + 1, it.path});
+                todo.push_back({link + 1, it.depth + 1, it.path | (1ull << (63 - it.depth))});
+            }
+        }
+        parts[15].src = c->path_codes.data();
+        parts[15].bytes = c->path_codes.size() * sizeof(WrtPathCode);
+    }
     size_t total = 0;
     for (Part& p : parts) {
         if (p.bytes && !p.src) return fail("wrt_upload_scene: null array with a non-zero count");
@@ -829,6 +856,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     ds.textures = (const WrtTexture*)dptr(12);
     ds.normalmaps = (const WrtTexture*)dptr(13);
     ds.texels = (const float*)dptr(14);
+    ds.path_codes = parts[15].bytes ? (const WrtPathCode*)dptr(15) : nullptr;
 
     // ---- 2. device-side layouts ----
     float4 *geom = nullptr, *attr = nullptr, *mats = nullptr, *pbox = nullptr, *taux = nullptr, *fnodes = nullptr, *dnodes = nullptr, *onodes = nullptr, *ronodes = nullptr, *wnodes = nullptr;
@@ -943,7 +971,6 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     for (int k = 0; k < 3; k++) { ds.bkg[k] = s->bkgcolor[k]; ds.dc[k] = s->dc[k]; ds.eye[k] = s->eye[k]; }
     ds.eta = s->eta;
     ds.amin = s->amin; ds.amax = s->amax; ds.distmin = s->distmin; ds.distmax = s->distmax;
-    c->bvh_depth = tree_depth(s);
     CK(cudaStreamSynchronize(st));
     auto t_b1 = std::chrono::steady_clock::now();
     const int* rb = (const int*)h_rb;

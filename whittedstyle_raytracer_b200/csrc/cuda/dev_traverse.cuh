@@ -460,12 +460,12 @@ struct ShadowAcc {
     float fac[WRT_SHADOW_HITS];
     WrtPathCode code[WRT_SHADOW_HITS];     // fetched when the hit is made: the load is long back when the walk ends
     __device__ __forceinline__ void reset() { res = 1.f; n = 0; }
-    // `collect` false: count only (the frame kernel's first walk of a ray; k_shadow_hard walks a ray with three or more
-    // translucent crossings a second time, collecting — storing every ray's hits cost a third of the kernel's time)
-    __device__ __forceinline__ void add(int p, float f, const WrtPathCode* codes, bool collect) {
+    // (counting only on the first walk and walking rays with three or more translucent crossings a second time measured
+    // 10 % slower than keeping every such hit: profiles/NOTES.md)
+    __device__ __forceinline__ void add(int p, float f, const WrtPathCode* codes) {
         res = res * f;
         if (f != 1.f && f != 0.f) {            // (an opaque blocker ends the walk with an exact 0: nothing to associate)
-            if (collect && n < WRT_SHADOW_HITS) {
+            if (n < WRT_SHADOW_HITS) {
                 prim[n] = p; fac[n] = f;
                 if (codes) {
                     const int4 c4 = __ldg(reinterpret_cast<const int4*>(codes + p));
@@ -498,9 +498,9 @@ __device__ __forceinline__ float shadow_value(const DevScene& s, const ShadowAcc
     return acc.needs_tree(s.path_codes) ? shadow_tree_value(acc.prim, acc.fac, acc.code, acc.n) : acc.res;
 }
 
-__device__ __forceinline__ void shadow_leaf(const DevScene& s, const Ray& r, float dis, int p, ShadowAcc& acc, bool collect = true) {
+__device__ __forceinline__ void shadow_leaf(const DevScene& s, const Ray& r, float dis, int p, ShadowAcc& acc) {
     PrimHit h; float oma; unsigned fl;
-    if (prim_test(s, p, r, h, oma, fl) && h.t < dis && !(fl & WRT_PRIM_LIGHT)) acc.add(p, oma, s.path_codes, collect);
+    if (prim_test(s, p, r, h, oma, fl) && h.t < dis && !(fl & WRT_PRIM_LIGHT)) acc.add(p, oma, s.path_codes);
 }
 
 __device__ __forceinline__ float shadow_product(const DevScene& s, const float4* nodes, const Ray& r, float dis, Stack& st) {

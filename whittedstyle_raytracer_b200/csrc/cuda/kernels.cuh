@@ -465,8 +465,6 @@ struct HardShadowQuery {
     ShadowAcc acc;
     size_t out;
     int q;
-    int root_link;             // where the walk starts (a ray with >= 3 translucent crossings is walked twice: ShadowAcc)
-    bool collect;
     bool wide;
     bool literal;              // WRT_TRAVERSAL_EXHAUSTIVE: walk the reference-topology tree (its left-to-right product order)
     __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int q_, bool literal_)
@@ -482,7 +480,6 @@ struct HardShadowQuery {
         r = make_ray(orig, raydir);
         out = (size_t)__float_as_uint(o4.w) * (unsigned)s.n_lights + k.x;
         acc.reset();
-        collect = false;
         if (s.n_nodes == 0) return false;
         const bool ref_tree = literal || degenerate_dir(raydir);
         const size_t oct_off = (size_t)ray_octant(raydir) * 2 * (size_t)s.n_nodes;
@@ -492,7 +489,6 @@ struct HardShadowQuery {
         if (!slab_presorted(lo, hi, r, te)) return false;
         cur = __float_as_int(lo.w);
         if (cur < 0) { shadow_leaf(s, r, dis, ~cur, acc); return false; }
-        root_link = cur;
         wide = WRT_WIDE4 && !ref_tree;
         if (wide) nodes = s.wnodes + (WRT_WIDE_FLOAT4_PER_RECORD / 2) * oct_off;
         return true;
@@ -501,24 +497,16 @@ struct HardShadowQuery {
         const float never = INFINITY;
         bool more;
 #if WRT_LEAF_DEFER >= 2
-        if (WRT_WIDE4 && wide) more = traverse_step4_defer<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, acc, collect); });
+        if (WRT_WIDE4 && wide) more = traverse_step4_defer<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, acc); });
 #else
-        if (WRT_WIDE4 && wide) more = traverse_step4<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, acc, collect); });
+        if (WRT_WIDE4 && wide) more = traverse_step4<false>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, acc); });
 #endif
-        else more = traverse_step<false, true>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, acc, collect); });
+        else more = traverse_step<false, true>(nodes, r, st, cur, never, [&](int p) { shadow_leaf(s, r, dis, p, acc); });
         return more && acc.res != 0.f;
     }
-    __device__ __forceinline__ bool finish(int& cur, Stack& st) {
-        // three or more translucent crossings: the product in the reference tree's association (shadow_assoc.h) — the ray
-        // is walked once more, this time keeping its blockers (one ray in twenty of a glass-bunny frame)
-        if (!collect && acc.res != 0.f && acc.n >= 3 && s.path_codes != nullptr) {
-            collect = true;
-            acc.reset();
-            st.sp = 0;
-            cur = root_link;
-            return true;
-        }
-        const float v = collect ? shadow_value(s, acc) : acc.res;
+    __device__ __forceinline__ bool finish(int&, Stack&) {
+        // three or more translucent crossings: the product in the reference tree's association (shadow_assoc.h)
+        const float v = shadow_value(s, acc);
         if (WRT_IN_BOUNDS(out, (size_t)fb.n_node_cap * s.n_lights)) fb.coeff[out] = v;
         return false;
     }

@@ -80,6 +80,10 @@ int wrt_trace_closest(WrtContext* ctx, const float* orig, const float* dir, int6
  * so that the parity tests can hold the frame kernel itself to the oracle on arbitrary ray batches
  * (IIntersectStrategy::UpdateInter, include/IIntersectStrategy.h:10-11). */
 int wrt_trace_closest_wavefront(WrtContext* ctx, const float* orig, const float* dir, int64_t n, WrtHit* hits);
+/* BVHStrategy::getShadowCoeffi / ShadowHelper (include/BVHStrategy.hpp:13-48): the product of (1 - alpha) over the blocking
+ * leaves, multiplied in the association of the caller's tree (`l * r` at every inner node) — the reference's float bit
+ * for bit, whichever tree the kernel walks (csrc/cuda/shadow_assoc.h; beyond 12 translucent crossings on one ray or a
+ * tree deeper than 64 levels: the same factors in visit order). */
 int wrt_shadow_hard(WrtContext* ctx, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff);
 int wrt_shadow_soft(WrtContext* ctx, const float* pos, const float* ndir, const float* lightpos, int64_t n, float* coeff);
 int wrt_shadow_directional(WrtContext* ctx, const float* pos, const int32_t* self_object, const float* lightdir4,

@@ -64,4 +64,37 @@ WRT_ASSOC_HD float wrt_tree_product(int k, const int* prim, const float* f, cons
     return sp ? v[0] : 1.f;
 }
 
+#ifdef __cplusplus
+#include <vector>
+/* Host: the path codes of a flattened tree's primitives (include/wrt_scene.h — record 0 is the root; `link` >= 0: the
+ * children are records `link` (left) and `link + 1` (right); `link` < 0: the leaf of primitive ~link).  What
+ * wrt_upload_scene stages for the kernels; tests/shadow_assoc_check.cpp runs it on the scenes' own trees.  False (and no
+ * codes) for a tree with an inner node at depth WRT_PATH_BITS or more than n_nodes reachable records (not a tree). */
+template <class Node>
+inline bool wrt_make_path_codes(const Node* nodes, int n_nodes, int n_prims, std::vector<WrtPathCode>& out) {
+    out.clear();
+    if (n_prims <= 0 || n_nodes <= 0) return false;
+    out.assign((size_t)n_prims, WrtPathCode{0u, 0u, 0, 0});
+    struct Item { int rec; int depth; unsigned long long path; };
+    std::vector<Item> todo;
+    todo.push_back(Item{0, 0, 0ull});
+    long long visited = 0;
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        if (++visited > (long long)n_nodes || it.rec < 0 || it.rec >= n_nodes) { out.clear(); return false; }
+        const int link = nodes[it.rec].link;
+        if (link < 0) {
+            const int prim = ~link;
+            if (prim >= 0 && prim < n_prims) out[(size_t)prim] = WrtPathCode{(unsigned)(it.path >> 32), (unsigned)it.path, it.depth, 0};
+        } else {
+            if (it.depth >= WRT_PATH_BITS) { out.clear(); return false; }
+            todo.push_back(Item{link, it.depth + 1, it.path});
+            todo.push_back(Item{link + 1, it.depth + 1, it.path | (1ull << (63 - it.depth))});
+        }
+    }
+    return true;
+}
+#endif
+
 #endif /* WRT_SHADOW_ASSOC_H */

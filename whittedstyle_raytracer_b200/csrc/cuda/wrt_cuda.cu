@@ -811,24 +811,7 @@ int wrt_upload_scene(WrtContext* c, const WrtSceneDesc* s) {
     };
     // Root-to-leaf paths of the primitives in the scene's (= the reference's) tree: what the hard-shadow product needs to
     // multiply in that tree's association (shadow_assoc.h).  A tree deeper than 64 gets none (visit-order product).
-    c->path_codes.clear();
-    if (np > 0 && nn > 0 && c->bvh_depth <= WRT_PATH_BITS) {
-        c->path_codes.assign((size_t)np, WrtPathCode{0u, 0u, 0, 0});
-        struct Item { int rec; int depth; unsigned long long path; };
-        std::vector<Item> todo;
-        todo.push_back({0, 0, 0ull});
-        while (!todo.empty()) {
-            const Item it = todo.back();
-            todo.pop_back();
-            const int link = s->nodes[it.rec].link;
-            if (link < 0) {
-                const int prim = ~link;
-                if (prim >= 0 && prim < np) c->path_codes[prim] = WrtPathCode{(unsigned)(it.path >> 32), (unsigned)it.path, it.depth, 0};
-            } else if (it.depth < WRT_PATH_BITS) {
-                todo.push_back({link, it.depth + 1, it.path});
-                todo.push_back({link + 1, it.depth + 1, it.path | (1ull << (63 - it.depth))});
-            }
-        }
+    if (wrt_make_path_codes(s->nodes, nn, np, c->path_codes)) {
         parts[15].src = c->path_codes.data();
         parts[15].bytes = c->path_codes.size() * sizeof(WrtPathCode);
     }

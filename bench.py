@@ -11,7 +11,8 @@ Prints ONE JSON line (rank 0).  `value` = rays of the whole frame / device time 
 resident in HBM; `e2e` = the same through the host-buffer C-ABI call (scene H2D upload +
 render + image D2H inside the timed region).  `--impl reference` times the UNMODIFIED
 reference (oracle/_ref, single-threaded by construction) on a bounded pixel sample of the
-same frame.
+same frame; beside its value the line carries `all_cores`: the same sample traced by one
+independent reference process per host core (what the whole host could do; not the reference's mode).
 """
 from __future__ import annotations
 
@@ -183,6 +184,64 @@ def cpu_reference_sample(scene, workdir, workload, glass, target_seconds):
                        f"(oracle/whitted_oracle.c, OpenMP, {cores} threads); oracle/_ref was not available")
 
 
+def _reference_worker(job):
+    """One of P independent processes of the all-cores figure: loads the unmodified reference, traces its interleaved
+    share of the pixel sample, returns (rays, seconds of its trace_pixels call)."""
+    workdir, workload, glass, bunny, rays_file, part, parts = job
+    sys.path.insert(0, str(REPO / "tests"))
+    import numpy as np
+    import oracle_bindings as ob
+    od = np.load(rays_file, mmap_mode="r")                  # (o, d) pairs, shared through the page cache
+    o, d = np.array(od[part::parts, 0]), np.array(od[part::parts, 1])
+    with quiet_stdout():
+        ref = ob.ReferenceScene(workdir, workload, glass=glass, bunny=bunny)
+        ref.counters(reset=True)
+        _, secs = ref.trace_pixels(o, d)
+        closest, shadow = ref.counters(reset=True)
+    return closest + shadow, float(secs)
+
+
+def cpu_reference_all_cores(scene, workdir, workload, glass, target_seconds, procs=None):
+    """The host's whole-socket figure beside the 1-thread one: P independent processes of the unmodified reference, each
+    tracing an interleaved share of a (P times larger) pixel sample.  NOT how the reference runs — it has no threading
+    (Renderer.hpp:104-131 is one serial loop) — so it is reported beside the arm's value, never as it.  None when the
+    reference library did not travel."""
+    sys.path.insert(0, str(REPO / "tests"))
+    import multiprocessing as mp
+    import numpy as np
+    import oracle_bindings as ob
+    if not ob.have_reference():
+        return None
+    from whittedstyle_raytracer_b200 import fixtures
+    procs = procs or max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    procs = min(procs, 64)                                  # bounded: process start + scene load per worker, memory
+    w, h = scene.width, scene.height
+    soft = scene.desc.shadow_type != 0
+    rays_per_px = 90.0 if soft else 4.0
+    ref_rate = 1.5e6 if soft else 0.7e6
+    want_px = min(float(w * h), 2.1e6, max(256.0 * procs, target_seconds * ref_rate * procs / rays_per_px))
+    stride = max(1, int(round((w * h / want_px) ** 0.5)))
+    o, d = ob.OracleScene(scene).primary_rays()
+    o = o.reshape(h, w, 3)[::stride, ::stride].reshape(-1, 3)
+    d = d.reshape(h, w, 3)[::stride, ::stride].reshape(-1, 3)
+    # (neighbouring sample pixels go to different processes: the bunny's pixels, where the rays are, spread evenly)
+    rays_file = str(Path(workdir) / "all_cores_rays.npy")
+    np.save(rays_file, np.stack([o, d], axis=1).astype(np.float32))
+    bunny = bool(fixtures.BENCH_CONFIGS[workload].get("bunny", True))
+    jobs = [(str(workdir), workload, glass, bunny, rays_file, k, procs) for k in range(procs)]
+    t0 = time.time()
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = pool.map_async(_reference_worker, jobs).get(timeout=60.0 + 10.0 * target_seconds)   # (a dead worker must not hang the arm)
+    wall = time.time() - t0
+    rays = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return dict(value=rays / slowest / 1e6, unit=UNIT, cores=procs, kind="reference x P processes", rays=rays,
+                seconds=slowest, wall_seconds_with_process_start_and_scene_load=wall,
+                sample=f"every {stride}th pixel in x and y of the {w}x{h} frame ({len(o)} primary rays, {rays} rays), "
+                       f"interleaved over {procs} independent processes of the unmodified reference; rate = all rays / the "
+                       f"slowest process's trace time.  Not the reference's own mode of operation (it is single-threaded)")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -210,6 +269,11 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_all_cores:
+        try:
+            line["all_cores"] = cpu_reference_all_cores(scene, workdir, args.workload, glass, min(8.0, per_step))
+        except Exception as e:                                   # the arm's own number must not depend on it
+            line["all_cores"] = {"unavailable": f"{type(e).__name__}: {e}"}
     emit(line)
     return 0
 
@@ -553,6 +617,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-per-config", action="store_true", help="skip the other configs' short runs (per_config)")
+    ap.add_argument("--no-all-cores", action="store_true",
+                    help="reference arm: skip the extra figure from P independent reference processes (all_cores)")
     ap.add_argument("--per-config-cpu-seconds", type=float, default=4.0)
     ap.add_argument("--ref-step-seconds", type=float, default=None,
                     help="--impl reference: CPU seconds per step's pixel sample (default: 150 s / (steps + warmup), 1..10 s)")

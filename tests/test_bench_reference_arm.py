@@ -21,6 +21,12 @@ def test_reference_arm_prints_one_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True
+    # beside the single-threaded arm: the same sample through one independent reference process per host core
+    ac = line["all_cores"]
+    if line["cpu_baseline"]["kind"] == "reference":
+        assert ac["cores"] >= 1 and ac["value"] > 0 and ac["rays"] > 0 and "independent processes" in ac["sample"]
+    else:
+        assert ac is None
 
 
 def test_reference_arm_under_torchrun_only_rank0_prints():

@@ -127,11 +127,29 @@ def test_million_random_rays_bit_exact(workdir):
     r.ctx.close()
 
 
+@pytest.mark.parametrize("case", ["glass_row", "glass_bunny"])
+def test_hard_shadow_association_matches_the_reference_golden(workdir, case):
+    """The same property against the UNMODIFIED reference's own coefficients (tests/golden/assoc_<case>.npz, made by
+    tools/gen_assoc_golden.py; the oracle is pinned to the same files in tests/test_oracle_vs_reference.py): 20 000 shadow
+    rays along a row of six glass spheres of different alphas / through the glass bunny, bit for bit in both traversal
+    modes (BVHStrategy::ShadowHelper, BVHStrategy.hpp:24-48)."""
+    g = np.load(GOLD / f"assoc_{case}.npz", allow_pickle=False)
+    fixtures.write_config(workdir, f"assoc_{case}", str(g["config"]))
+    scene = Scene.from_workdir(workdir, f"assoc_{case}", bunny=bool(g["bunny"]))
+    ref = g["hard"]
+    r = Renderer(scene)
+    for traversal in (TRAVERSAL_PRUNED, TRAVERSAL_EXHAUSTIVE):
+        r.ctx.set_options(traversal=traversal)
+        got = r.interStrategy.getShadowCoeffi(g["pos"], g["ndir"], g["light"])
+        assert np.array_equal(got, ref), (traversal, int((got != ref).sum()))
+    r.ctx.close()
+
+
 def test_hard_shadow_product_has_the_reference_association(workdir):
     """BVHStrategy::ShadowHelper multiplies the (1 - alpha) factors in the association of the reference's tree (`l * r`,
     BVHStrategy.hpp:43-47); a stack walk multiplies in visit order, which differs in the last bits from the third crossing
     on (csrc/cuda/shadow_assoc.h rebuilds the reference's association from the primitives' path codes).  Shadow rays along
-    a row of seven glass spheres of different alphas — up to 12 crossings with a factor != 1 — must give the oracle's
+    a row of six glass spheres of different alphas — up to six different factors != 1 on a ray — must give the oracle's
     (= the reference recursion's) coefficient bit for bit in both traversal modes, through the batch query and through a
     rendered frame; so must rays through the glass bunny (equal factors: 0.8^4 already depends on the association)."""
     alphas = [0.1, 0.25, 0.4, 0.55, 0.7, 0.85]

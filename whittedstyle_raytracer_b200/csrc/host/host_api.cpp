@@ -82,7 +82,8 @@ int64_t wrt_scene_upload_bytes(const WrtScene* s) {
     const wrt::HostScene& h = s->hs;
     return (int64_t)(h.nodes.size() * sizeof(WrtNode) + h.prim_geom.size() * 4 + h.prim_normals.size() * 4 +
                      h.prim_uv.size() * 4 + h.prim_flags.size() * 4 * 6 + h.materials.size() * sizeof(WrtMaterial) +
-                     h.lights.size() * sizeof(WrtLight) + h.texels.size() * 4);
+                     h.lights.size() * sizeof(WrtLight) + h.texels.size() * 4 +
+                     h.prim_flags.size() * 16);     // + the primitives' path codes wrt_upload_scene derives and stages (shadow_assoc.h)
 }
 
 const char* wrt_scene_output_name(const WrtScene* s) { return s->out_name.c_str(); }

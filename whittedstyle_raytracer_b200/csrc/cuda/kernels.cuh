@@ -466,7 +466,7 @@ struct HardShadowQuery {
     size_t out;
     int q;
     bool wide;
-    bool literal;              // WRT_TRAVERSAL_EXHAUSTIVE: walk the reference-topology tree (its left-to-right product order)
+    bool literal;              // WRT_TRAVERSAL_EXHAUSTIVE: walk the reference-topology tree (the product's association comes from ShadowAcc either way)
     __device__ __forceinline__ HardShadowQuery(const DevScene& s_, const FrameBuffers& fb_, int q_, bool literal_)
         : s(s_), fb(fb_), q(q_), literal(literal_) {}
     __device__ __forceinline__ bool begin(unsigned long long item, int& cur, Stack&) {
